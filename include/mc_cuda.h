@@ -1,0 +1,178 @@
+/*
+ * mc_cuda.h -- C ABI of the B200 (sm_100a) EM hot path of MULTICLUST.
+ *
+ * This is the drop-in boundary of SURVEY.md section 8(b): a thin layer around
+ * the reference's L2 "EM hot path" (the functions declared at
+ * multiclust.h:371-388).  The host program keeps every policy decision the
+ * reference makes in C -- slot rotation, accept/reject of accelerated steps,
+ * stop()/converged(), the exit(0) rules (em_alg.c:44-207, accel_em.c:35-114)
+ * -- and calls down here only for the data-parallel work.  Plain pointers and
+ * sizes, no C++ or torch types.  One host thread per context; no hidden global
+ * state; every device buffer is owned by the context.
+ *
+ * Flat layouts (all parameters IEEE double, as in the reference):
+ *   J[l]    = allele slots of locus l, INCLUDING the phantom slot the
+ *             reference creates for loci with missing data
+ *             (read_file.c:527-530); off[l] = sum_{l'<l} J[l'], T = off[L]
+ *   codes   = uint8 [I][L][P], 0..J[l]-1, 255 = missing copy      (dat->IL)
+ *   p       = double [K][T], p[k*T + off[l] + j]                  (mod->vpklm[s])
+ *   eta     = double [I][K] (admixture) or [K] (mixture, or -c)   (mod->vetaik[s] / vetak[s])
+ *   slots   = 0..2, the reference's three rotating parameter copies
+ *             (multiclust.h:265-271)
+ *
+ * Every function returns MC_OK or an MC_ERR_* code; mc_last_error() gives the
+ * message.  There is no CPU fallback: without a CUDA device mc_create fails.
+ */
+#ifndef MC_CUDA_H
+#define MC_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "mc_synth.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mc_ctx mc_ctx;
+
+enum {
+	MC_OK = 0,
+	MC_ERR_CUDA = 1,	/* a CUDA runtime call failed */
+	MC_ERR_ARG = 2,		/* invalid argument */
+	MC_ERR_STATE = 3,	/* call made in the wrong order (no data / no model) */
+	MC_ERR_NOMEM = 4,
+	MC_ERR_UNSUPPORTED = 5	/* e.g. ploidy > 16 or > 254 alleles at a locus */
+};
+
+#define MC_ABI_VERSION 1
+
+/* message of the last error raised through `ctx` (or creation, if ctx NULL) */
+const char *mc_last_error(const mc_ctx *ctx);
+int mc_abi_version(void);
+
+/* ---- context ---------------------------------------------------------- */
+
+/* One context per GPU.  `device` is a CUDA ordinal. */
+int mc_create(mc_ctx **ctx, int device);
+void mc_destroy(mc_ctx *ctx);
+/* Run every later launch on an existing cudaStream_t (e.g. the caller's
+ * torch stream); NULL restores the context's own stream. */
+int mc_set_stream(mc_ctx *ctx, void *cuda_stream);
+int mc_sync(mc_ctx *ctx);
+
+/* ---- data: replaces dat->IL / ILM / uniquealleles as the path reads them
+ *      (multiclust.h:223-250, read_file.c:633-663) ------------------------ */
+
+/* Upload recoded genotypes from HOST memory and build the device layout. */
+int mc_set_data(mc_ctx *ctx, int64_t I, int32_t L, int32_t P,
+	const int32_t *J, const uint8_t *codes);
+/* Generate the synthetic workload of include/mc_synth.h directly in HBM for
+ * individuals [i_first, i_first + I) (bench sizes never touch the host).
+ * Recodes like the reference parser would; J is available afterwards. */
+int mc_set_data_synth(mc_ctx *ctx, int64_t I, int32_t L, const mcs_params *g,
+	int64_t i_first);
+int mc_get_dims(const mc_ctx *ctx, int64_t *I, int32_t *L, int32_t *P,
+	int64_t *T);
+int mc_get_J(const mc_ctx *ctx, int32_t *J);
+/* download natural-layout codes [I][L][P] (tests, round trips) */
+int mc_get_codes(mc_ctx *ctx, uint8_t *codes);
+
+/* ---- model: replaces allocate_model_for_k (multiclust.c:1181-1279) ------ */
+
+/* q = number of secant pairs kept (0 without acceleration, else opt->q);
+ * eta_lb / p_lb are the bounds of synchronize() (multiclust.c:812-815). */
+int mc_alloc_model(mc_ctx *ctx, int32_t K, int admixture, int eta_constrained,
+	int q, double eta_lb, double p_lb, int do_projection);
+int mc_eta_len(const mc_ctx *ctx, int64_t *n);
+int mc_set_params(mc_ctx *ctx, int slot, const double *eta, const double *p);
+int mc_get_params(mc_ctx *ctx, int slot, double *eta, double *p);
+
+/* ---- the hot path ------------------------------------------------------ */
+
+/* E-step on slot `from`, M-step (+ simplex projection) into slot `to`;
+ * returns the log likelihood of slot `from`, one step late like the
+ * reference.  Replaces em_step() minus stop() (em_alg.c:195-207 ->
+ * e_step_admixture_orig 291-486 + m_step_admixture_orig 592-754, or
+ * e_step_mixture 763-897 + m_step_mixture 907-1011).  from == to is the
+ * reference's in-place EM.  Leaves D_ik / v_ik of this E-step on the device. */
+int mc_em_step(mc_ctx *ctx, int from, int to, double *ll);
+
+/* log_likelihood() (log_likelihood.c:56-62, 96-232); touches no posterior. */
+int mc_loglik(mc_ctx *ctx, int slot, double *ll);
+
+/* Posterior sums of the last E-step: D_ik = sum_{l,j} d_iklj (admixture, what
+ * write_file.c:359-381,446-459,525-543 reduce diklm to) or v_ik (mixture). */
+int mc_get_posterior(mc_ctx *ctx, double *out);
+/* argmax partition on device (write_file.c:350-382, 582-600) */
+int mc_partition(mc_ctx *ctx, int32_t *I_K, int32_t *count_K);
+
+/* secant pair `pair` (0..q-1): which = 0 -> u, 1 -> v;
+ * delta = x[slot_t] - x[slot_f]  (em_2_steps, em_alg.c:1104-1161) */
+int mc_delta(mc_ctx *ctx, int which, int pair, int slot_t, int slot_f);
+
+/* step_size() sums (accel_em.c:142-184): out = {utu, utvu, vutvu} of pair.
+ * eta_part / p_part are returned separately so that an individual-sharded
+ * run can add the eta parts of all ranks; either pointer may be NULL. */
+int mc_step_dots(mc_ctx *ctx, int pair, double eta_part[3], double p_part[3]);
+/* qn_accelerated_update() sums (accel_em.c:291-310): {u[q1].u[q2], u[q1].v[q2]} */
+int mc_qn_dots(mc_ctx *ctx, int q1, int q2, double eta_part[2], double p_part[2]);
+
+/* accelerated_update() (accel_em.c:440-541) without its log_likelihood call:
+ * qn1 == 0: x[t] = x[p] - 2 s u + s^2 (v - u)   (SQUAREM, -s 1..3)
+ * qn1 != 0: x[t] = x[p] + u + s v               (QN q=1, -s 4)
+ * followed by the projections when enabled. */
+int mc_accel_update(mc_ctx *ctx, int qn1, int slot_t, int slot_p, int pair,
+	double s);
+/* qn_accelerated_update() (accel_em.c:364-415) without the dot products, the
+ * inverse and the log_likelihood call: x[t] = x[p] + u[uindex], then for row
+ * j and column n in the reference's cyclic order starting at delta_index:
+ * x[t] += v[pair(j)] * Ainv[j*q+n] * cutu[n]; then the projections. */
+int mc_qn_update(mc_ctx *ctx, int slot_t, int slot_p, int uindex,
+	int delta_index, const double *Ainv, const double *cutu);
+
+/* simplex_project_eta / simplex_project_pklm on a whole slot (simplex.c) */
+int mc_project(mc_ctx *ctx, int slot);
+int mc_copy_slot(mc_ctx *ctx, int dst, int src);
+
+/* ---- individual-sharded fits: one context per GPU holds a
+ *      slice of individuals; p is replicated --------------------------------
+ * mc_em_step_local runs the E-step and everything that needs only this
+ * rank's individuals (eta rows of slot `to`, D_ik / v_ik), and leaves the
+ * partial sums that must be added over ranks in the exchange buffer:
+ * [K*T allele-count sums | ll | K pooled-eta sums], all double.  The caller
+ * sums the buffer over ranks (NCCL all-reduce on `*dev_ptr`, or any other
+ * mechanism; nothing to do for a single rank) and then calls
+ * mc_em_step_finish, which normalises and projects p (and the pooled eta of
+ * the mixture / -c models) into slot `to` on every rank identically.
+ * mc_em_step == mc_em_step_local + mc_em_step_finish. */
+int mc_em_step_local(mc_ctx *ctx, int from, int to);
+int mc_exchange_buffer(mc_ctx *ctx, void **dev_ptr, size_t *n_doubles);
+int mc_em_step_finish(mc_ctx *ctx, int to, double *ll);
+
+/* ---- introspection for bench / profiles --------------------------------- */
+
+typedef struct {
+	int32_t K, k_split, k_per_lane;		/* lanes per locus, k values per lane */
+	int32_t loci_per_warp, warps, groups;	/* tile = warps*groups*loci_per_warp loci */
+	int32_t n_tiles, n_chunks, n_units, grid, block;
+	int32_t indiv_per_block, ploidy_padded;
+	int64_t smem_bytes;
+	int64_t algorithmic_bytes_em;	/* I*L*P + 16*I*K + 16*K*T */
+	int64_t algorithmic_bytes_ll;	/* I*L*P +  8*I*K +  8*K*T */
+} mc_plan_info;
+int mc_get_plan(const mc_ctx *ctx, mc_plan_info *out);
+
+/* kernels launched through this context so far */
+int64_t mc_launch_count(const mc_ctx *ctx);
+/* When enabled, the dominant (genotype-streaming) kernel of every
+ * mc_em_step / mc_loglik is bracketed by CUDA events on the launch stream. */
+int mc_profile_enable(mc_ctx *ctx, int on);
+int mc_profile_read(mc_ctx *ctx, int64_t *n_launches, double *total_ms);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* MC_CUDA_H */

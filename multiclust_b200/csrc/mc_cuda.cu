@@ -1,0 +1,1060 @@
+/*
+ * mc_cuda.cu -- context, work planning and the C ABI of include/mc_cuda.h.
+ *
+ * Build (see multiclust_b200/build.py):
+ *   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared \
+ *        -Xcompiler -fPIC -Iinclude -o libmc_cuda.so mc_cuda.cu
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "mc_cuda.h"
+#include "mc_kernels.cuh"
+
+#define KH_MAX 6
+#define SMEM_LIMIT (227 * 1024)
+
+static std::string g_create_error;
+
+struct mc_ctx {
+	int device = 0;
+	cudaStream_t own_stream = nullptr, stream = nullptr;
+	std::string err;
+	int64_t launches = 0;
+	int num_sms = 148;
+
+	/* data */
+	int64_t I = 0, T = 0;
+	int L = 0, P = 0, PP = 0, IB = 0;
+	std::vector<int32_t> J, off;
+	unsigned char *d_nat = nullptr;		/* [I][L][P] */
+	int *d_J = nullptr, *d_off = nullptr;
+
+	/* model */
+	bool have_model = false;
+	int K = 0, admixture = 0, eta_constrained = 0, per_indiv = 0, q = 0,
+		do_proj = 1;
+	double eta_lb = 0, p_lb = 0;
+	int64_t neta = 0, np = 0;
+	double *d_p[3] = { nullptr, nullptr, nullptr };
+	double *d_eta[3] = { nullptr, nullptr, nullptr };
+	std::vector<double *> d_up, d_vp, d_ue, d_ve;
+	double *d_post = nullptr;	/* D_ik or v_ik [I][K] */
+	double *d_lli = nullptr;	/* mixture: per-individual ll [I] */
+	double *d_logp = nullptr;	/* mixture: log p table [K][T] */
+
+	/* plan */
+	TileArgs ta;
+	int k_split = 1, KH = 1, grid = 0, block = 0;
+	size_t smem_em = 0;
+	int *d_slot_locus = nullptr, *d_slot_off = nullptr, *d_slot_J = nullptr,
+		*d_group_rowbase = nullptr, *d_group_rows = nullptr,
+		*d_tile_rows = nullptr;
+	unsigned char *d_tiled = nullptr;
+	double *d_Apart = nullptr, *d_Npart = nullptr, *d_llpart = nullptr;
+	double *d_xbuf = nullptr;	/* [K*T | ll | K] */
+	double *d_red = nullptr;	/* reduction partials */
+	double *d_small = nullptr;	/* small results for the host */
+	int *d_IK = nullptr;
+
+	/* profiling of the streaming kernel */
+	bool profile = false;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+	int64_t prof_n = 0;
+	double prof_ms = 0;
+};
+
+/* ---------------------------------------------------------------- errors */
+
+static int fail(mc_ctx *c, int code, const char *fmt, ...)
+{
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	if (c)
+		c->err = buf;
+	else
+		g_create_error = buf;
+	return code;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+	return fail(c, MC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
+		cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+#define LAUNCH_CHECK(name) do { cudaError_t e_ = cudaGetLastError(); \
+	c->launches++; if (e_ != cudaSuccess) \
+	return fail(c, MC_ERR_CUDA, "launch of %s failed: %s", name, \
+		cudaGetErrorString(e_)); } while (0)
+
+extern "C" const char *mc_last_error(const mc_ctx *c)
+{
+	return c ? c->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int mc_abi_version(void) { return MC_ABI_VERSION; }
+
+static int grid_for(const mc_ctx *c, long long n, int threads)
+{
+	long long g = (n + threads - 1) / threads;
+	long long cap = (long long)c->num_sms * 8;
+	if (g > cap) g = cap;
+	if (g < 1) g = 1;
+	return (int)g;
+}
+
+template <typename T> static void dfree(T *&p)
+{
+	if (p)
+		cudaFree(p);
+	p = nullptr;
+}
+
+/* --------------------------------------------------------------- context */
+
+extern "C" int mc_create(mc_ctx **out, int device)
+{
+	mc_ctx *c = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0)
+		return fail(nullptr, MC_ERR_CUDA, "no CUDA device: %s (the MULTICLUST "
+			"EM path has no CPU fallback)", cudaGetErrorString(e));
+	if (device < 0 || device >= n)
+		return fail(nullptr, MC_ERR_ARG, "device %d out of range (0..%d)",
+			device, n - 1);
+	c = new mc_ctx();
+	c->device = device;
+	if ((e = cudaSetDevice(device)) != cudaSuccess
+		|| (e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+		delete c;
+		return fail(nullptr, MC_ERR_CUDA, "cannot initialise device %d: %s",
+			device, cudaGetErrorString(e));
+	}
+	c->stream = c->own_stream;
+	cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+	if (cudaMalloc(&c->d_small, 64 * sizeof(double)) != cudaSuccess) {
+		delete c;
+		return fail(nullptr, MC_ERR_NOMEM, "cudaMalloc failed");
+	}
+	*out = c;
+	return MC_OK;
+}
+
+static void free_plan(mc_ctx *c)
+{
+	dfree(c->d_slot_locus); dfree(c->d_slot_off); dfree(c->d_slot_J);
+	dfree(c->d_group_rowbase); dfree(c->d_group_rows); dfree(c->d_tile_rows);
+	dfree(c->d_tiled); dfree(c->d_Apart); dfree(c->d_Npart);
+	dfree(c->d_llpart); dfree(c->d_xbuf); dfree(c->d_red);
+}
+
+static void free_model(mc_ctx *c)
+{
+	for (int s = 0; s < 3; s++) {
+		dfree(c->d_p[s]);
+		dfree(c->d_eta[s]);
+	}
+	for (auto *x : c->d_up) cudaFree(x);
+	for (auto *x : c->d_vp) cudaFree(x);
+	for (auto *x : c->d_ue) cudaFree(x);
+	for (auto *x : c->d_ve) cudaFree(x);
+	c->d_up.clear(); c->d_vp.clear(); c->d_ue.clear(); c->d_ve.clear();
+	dfree(c->d_post); dfree(c->d_lli); dfree(c->d_logp); dfree(c->d_IK);
+	free_plan(c);
+	c->have_model = false;
+}
+
+static void free_data(mc_ctx *c)
+{
+	free_model(c);
+	dfree(c->d_nat); dfree(c->d_J); dfree(c->d_off);
+	c->I = 0;
+}
+
+extern "C" void mc_destroy(mc_ctx *c)
+{
+	if (!c)
+		return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	free_data(c);
+	dfree(c->d_small);
+	for (auto &ev : c->prof_events) {
+		cudaEventDestroy(ev.first);
+		cudaEventDestroy(ev.second);
+	}
+	cudaStreamDestroy(c->own_stream);
+	delete c;
+}
+
+extern "C" int mc_set_stream(mc_ctx *c, void *s)
+{
+	if (!c)
+		return MC_ERR_ARG;
+	CK(cudaStreamSynchronize(c->stream));
+	c->stream = s ? (cudaStream_t)s : c->own_stream;
+	return MC_OK;
+}
+
+extern "C" int mc_sync(mc_ctx *c)
+{
+	if (!c)
+		return MC_ERR_ARG;
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	return MC_OK;
+}
+
+/* ------------------------------------------------------------------ data */
+
+static int set_dims(mc_ctx *c, int64_t I, int32_t L, int32_t P, const int32_t *J)
+{
+	if (I <= 0 || L <= 0 || P <= 0)
+		return fail(c, MC_ERR_ARG, "bad dimensions I=%lld L=%d P=%d",
+			(long long)I, L, P);
+	if (P > 16)
+		return fail(c, MC_ERR_UNSUPPORTED, "ploidy %d > 16 is not supported", P);
+	free_data(c);
+	c->I = I; c->L = L; c->P = P;
+	c->PP = 1;
+	while (c->PP < P)
+		c->PP <<= 1;
+	c->IB = c->PP >= 2 ? 16 / c->PP : 8;
+	c->J.assign(J, J + L);
+	c->off.assign((size_t)L + 1, 0);
+	for (int l = 0; l < L; l++) {
+		if (J[l] < 0 || J[l] > 255)
+			return fail(c, MC_ERR_UNSUPPORTED, "locus %d has %d allele "
+				"slots; 8-bit codes allow at most 255", l, J[l]);
+		c->off[l + 1] = c->off[l] + J[l];
+	}
+	c->T = c->off[L];
+	CK(cudaMalloc(&c->d_J, sizeof(int) * (size_t)L));
+	CK(cudaMalloc(&c->d_off, sizeof(int) * ((size_t)L + 1)));
+	CK(cudaMemcpyAsync(c->d_J, c->J.data(), sizeof(int) * (size_t)L,
+		cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->d_off, c->off.data(), sizeof(int) * ((size_t)L + 1),
+		cudaMemcpyHostToDevice, c->stream));
+	return MC_OK;
+}
+
+extern "C" int mc_set_data(mc_ctx *c, int64_t I, int32_t L, int32_t P,
+	const int32_t *J, const uint8_t *codes)
+{
+	if (!c || !J || !codes)
+		return fail(c, MC_ERR_ARG, "mc_set_data: null argument");
+	CK(cudaSetDevice(c->device));
+	int rc = set_dims(c, I, L, P, J);
+	if (rc)
+		return rc;
+	const size_t n = (size_t)I * L * P;
+	CK(cudaMalloc(&c->d_nat, n));
+	CK(cudaMemcpyAsync(c->d_nat, codes, n, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return MC_OK;
+}
+
+extern "C" int mc_set_data_synth(mc_ctx *c, int64_t I, int32_t L,
+	const mcs_params *g, int64_t i_first)
+{
+	if (!c || !g)
+		return fail(c, MC_ERR_ARG, "mc_set_data_synth: null argument");
+	if (g->jmax < 2 || g->jmax > 254 || g->ploidy < 1 || g->ploidy > 16 || g->K < 1)
+		return fail(c, MC_ERR_ARG, "mc_set_data_synth: bad generator parameters");
+	CK(cudaSetDevice(c->device));
+	free_data(c);
+	const int P = g->ploidy;
+	const size_t n = (size_t)I * L * P;
+	unsigned *d_present = nullptr, *d_missing = nullptr;
+	unsigned char *d_map = nullptr;
+	CK(cudaMalloc(&c->d_nat, n));
+	CK(cudaMalloc(&d_present, sizeof(unsigned) * 8 * (size_t)L));
+	CK(cudaMalloc(&d_missing, sizeof(unsigned) * (size_t)L));
+	CK(cudaMemsetAsync(d_present, 0, sizeof(unsigned) * 8 * (size_t)L, c->stream));
+	CK(cudaMemsetAsync(d_missing, 0, sizeof(unsigned) * (size_t)L, c->stream));
+	k_synth_fill<<<grid_for(c, I * (long long)L, 256), 256, 0, c->stream>>>(
+		c->d_nat, I, L, *g, i_first, d_present, d_missing);
+	LAUNCH_CHECK("k_synth_fill");
+	std::vector<unsigned> present((size_t)L * 8), missing((size_t)L);
+	CK(cudaMemcpyAsync(present.data(), d_present, sizeof(unsigned) * 8 * (size_t)L,
+		cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(missing.data(), d_missing, sizeof(unsigned) * (size_t)L,
+		cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	/* recode like the reference parser: unobserved alleles get no slot,
+	 * a locus with a missing copy gets the phantom slot (read_file.c:527-530) */
+	std::vector<int32_t> J((size_t)L);
+	std::vector<unsigned char> map((size_t)L * 256, MC_MISSING);
+	for (int l = 0; l < L; l++) {
+		int nreal = 0;
+		for (int code = 0; code < 255; code++)
+			if (present[(size_t)l * 8 + (code >> 5)] >> (code & 31) & 1u)
+				map[(size_t)l * 256 + code] = (unsigned char)nreal++;
+		J[l] = nreal ? nreal + (missing[l] ? 1 : 0) : 0;
+	}
+	CK(cudaMalloc(&d_map, (size_t)L * 256));
+	CK(cudaMemcpyAsync(d_map, map.data(), (size_t)L * 256, cudaMemcpyHostToDevice, c->stream));
+	k_synth_remap<<<grid_for(c, I * (long long)L, 256), 256, 0, c->stream>>>(
+		c->d_nat, I, L, P, d_map);
+	LAUNCH_CHECK("k_synth_remap");
+	CK(cudaStreamSynchronize(c->stream));
+	cudaFree(d_present); cudaFree(d_missing); cudaFree(d_map);
+	/* set_dims frees data: keep the generated codes across it */
+	unsigned char *keep = c->d_nat;
+	c->d_nat = nullptr;
+	int rc = set_dims(c, I, L, P, J.data());
+	c->d_nat = keep;
+	return rc;
+}
+
+extern "C" int mc_get_dims(const mc_ctx *c, int64_t *I, int32_t *L, int32_t *P,
+	int64_t *T)
+{
+	if (!c || !c->I)
+		return MC_ERR_STATE;
+	if (I) *I = c->I;
+	if (L) *L = c->L;
+	if (P) *P = c->P;
+	if (T) *T = c->T;
+	return MC_OK;
+}
+
+extern "C" int mc_get_J(const mc_ctx *c, int32_t *J)
+{
+	if (!c || !c->I || !J)
+		return MC_ERR_STATE;
+	memcpy(J, c->J.data(), sizeof(int32_t) * (size_t)c->L);
+	return MC_OK;
+}
+
+extern "C" int mc_get_codes(mc_ctx *c, uint8_t *codes)
+{
+	if (!c || !c->I || !codes)
+		return fail(c, MC_ERR_STATE, "mc_get_codes: no data");
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync(codes, c->d_nat, (size_t)c->I * c->L * c->P,
+		cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return MC_OK;
+}
+
+/* ------------------------------------------------------------------ plan */
+
+struct HostPlan {
+	int W, NG, LW, tile_slots, n_tiles, max_rows;
+	std::vector<int> slot_locus, slot_off, slot_J, group_rowbase, group_rows,
+		tile_rows;
+	size_t smem;
+};
+
+static size_t smem_need(int max_rows, int KH, int W, int ks, int IB, int nbuf)
+{
+	size_t rows = (size_t)max_rows * KH * 32 * sizeof(double) * nbuf;
+	size_t scr = (size_t)2 * W * ks * IB * KH * sizeof(double);
+	return rows + scr + (size_t)W * sizeof(double) + 64;
+}
+
+/* Deal loci (sorted by slot count, descending) round-robin to tiles so every
+ * tile gets the same mix; inside a tile consecutive slots have similar J, so
+ * the LW loci sharing a warp's shared-memory rows waste few of them. */
+static void build_tiles(const mc_ctx *c, int W, int NG, int LW, HostPlan &hp)
+{
+	const int L = c->L;
+	hp.W = W; hp.NG = NG; hp.LW = LW;
+	hp.tile_slots = W * NG * LW;
+	hp.n_tiles = (L + hp.tile_slots - 1) / hp.tile_slots;
+	std::vector<int> order((size_t)L);
+	for (int l = 0; l < L; l++)
+		order[l] = l;
+	std::stable_sort(order.begin(), order.end(),
+		[&](int a, int b) { return c->J[a] > c->J[b]; });
+	const size_t ns = (size_t)hp.n_tiles * hp.tile_slots;
+	hp.slot_locus.assign(ns, -1);
+	hp.slot_off.assign(ns, 0);
+	hp.slot_J.assign(ns, 0);
+	for (int r = 0; r < L; r++) {
+		const int t = r % hp.n_tiles, s = r / hp.n_tiles, l = order[r];
+		hp.slot_locus[(size_t)t * hp.tile_slots + s] = l;
+		hp.slot_off[(size_t)t * hp.tile_slots + s] = c->off[l];
+		hp.slot_J[(size_t)t * hp.tile_slots + s] = c->J[l];
+	}
+	hp.group_rowbase.assign((size_t)hp.n_tiles * NG * W, 0);
+	hp.group_rows.assign((size_t)hp.n_tiles * NG * W, 1);
+	hp.tile_rows.assign((size_t)hp.n_tiles, 0);
+	hp.max_rows = 0;
+	for (int t = 0; t < hp.n_tiles; t++) {
+		int rows = 0;
+		for (int gw = 0; gw < NG * W; gw++) {
+			int mx = 1;	/* at least one row: missing codes read row 0 */
+			for (int lw = 0; lw < LW; lw++)
+				mx = std::max(mx, hp.slot_J[(size_t)t * hp.tile_slots + (size_t)gw * LW + lw]);
+			hp.group_rowbase[(size_t)t * NG * W + gw] = rows;
+			hp.group_rows[(size_t)t * NG * W + gw] = mx;
+			rows += mx;
+		}
+		hp.tile_rows[t] = rows;
+		hp.max_rows = std::max(hp.max_rows, rows);
+	}
+}
+
+template <typename T>
+static int upload(mc_ctx *c, T *&dst, const std::vector<T> &src)
+{
+	CK(cudaMalloc(&dst, sizeof(T) * std::max<size_t>(src.size(), 1)));
+	CK(cudaMemcpyAsync(dst, src.data(), sizeof(T) * src.size(),
+		cudaMemcpyHostToDevice, c->stream));
+	return MC_OK;
+}
+
+static int make_plan(mc_ctx *c)
+{
+	const int K = c->K;
+	int ks = 1;
+	while ((K + ks - 1) / ks > KH_MAX && ks < 32)
+		ks <<= 1;
+	const int KH = (K + ks - 1) / ks;
+	if (KH > KH_MAX)
+		return fail(c, MC_ERR_UNSUPPORTED, "K=%d exceeds the supported "
+			"maximum of %d clusters", K, KH_MAX * 32);
+	const int LW = 32 / ks;
+	const int nbuf = 2;	/* p rows + accumulator rows */
+	c->k_split = ks;
+	c->KH = KH;
+
+	/* largest tile that fits shared memory; prefer many warps */
+	HostPlan best;
+	bool found = false;
+	const int max_slots = ((c->L + LW - 1) / LW) * LW;
+	for (int W = 8; W >= 1 && !found; W--) {
+		int NG = std::max(1, std::min(64, max_slots / (W * LW)));
+		for (; NG >= 1; NG--) {
+			/* do not build tiles much larger than the data needs */
+			if (NG > 1 && (long long)W * (NG - 1) * LW >= c->L)
+				continue;
+			HostPlan hp;
+			build_tiles(c, W, NG, LW, hp);
+			hp.smem = smem_need(hp.max_rows, KH, W, ks, c->IB, nbuf);
+			if (hp.smem <= SMEM_LIMIT) {
+				best = std::move(hp);
+				found = true;
+				break;
+			}
+		}
+	}
+	if (!found)
+		return fail(c, MC_ERR_UNSUPPORTED, "a single locus group needs more "
+			"than %d bytes of shared memory (K=%d)", SMEM_LIMIT, K);
+
+	const long long n_blocks = (c->I + c->IB - 1) / c->IB;
+	/* chunks of individuals: enough units to balance the persistent grid */
+	int C = 1;
+	{
+		const long long sms = c->num_sms;
+		double best_eff = -1;
+		const long long cmax = std::min<long long>(n_blocks,
+			std::max<long long>(1, (8 * sms + best.n_tiles - 1) / best.n_tiles));
+		for (long long cc = 1; cc <= cmax; cc++) {
+			const long long units = cc * best.n_tiles;
+			const long long rounds = (units + sms - 1) / sms;
+			double eff = (double)units / (double)(rounds * sms);
+			/* mild preference for fewer chunks (fewer partial sums) */
+			eff -= 0.002 * (double)cc;
+			if (eff > best_eff + 1e-12) {
+				best_eff = eff;
+				C = (int)cc;
+			}
+		}
+	}
+
+	TileArgs &ta = c->ta;
+	memset(&ta, 0, sizeof ta);
+	ta.K = K; ta.k_split = ks; ta.loci_per_warp = LW; ta.warps = best.W;
+	ta.groups = best.NG; ta.n_tiles = best.n_tiles; ta.n_chunks = C;
+	ta.n_units = best.n_tiles * C; ta.tile_slots = best.tile_slots;
+	ta.n_blocks = n_blocks; ta.I = c->I; ta.Ipad = n_blocks * c->IB; ta.T = c->T;
+	ta.max_rows = best.max_rows;
+	const int UB = c->IB * c->PP;
+	ta.tile_stride = (long long)n_blocks * best.tile_slots * UB;
+	c->smem_em = best.smem;
+	c->block = best.W * 32;
+	c->grid = std::min(ta.n_units, c->num_sms);
+
+	int rc;
+	if ((rc = upload(c, c->d_slot_locus, best.slot_locus))) return rc;
+	if ((rc = upload(c, c->d_slot_off, best.slot_off))) return rc;
+	if ((rc = upload(c, c->d_slot_J, best.slot_J))) return rc;
+	if ((rc = upload(c, c->d_group_rowbase, best.group_rowbase))) return rc;
+	if ((rc = upload(c, c->d_group_rows, best.group_rows))) return rc;
+	if ((rc = upload(c, c->d_tile_rows, best.tile_rows))) return rc;
+	ta.slot_locus = c->d_slot_locus; ta.slot_off = c->d_slot_off;
+	ta.slot_J = c->d_slot_J; ta.group_rowbase = c->d_group_rowbase;
+	ta.group_rows = c->d_group_rows; ta.tile_rows = c->d_tile_rows;
+
+	CK(cudaMalloc(&c->d_tiled, (size_t)ta.tile_stride * best.n_tiles));
+	k_tile_codes<<<grid_for(c, (long long)best.n_tiles * n_blocks * best.tile_slots, 256),
+		256, 0, c->stream>>>(c->d_nat, c->d_tiled, c->d_slot_locus, best.n_tiles,
+		best.tile_slots, n_blocks, c->I, c->L, c->P, c->PP, c->IB, ta.tile_stride);
+	LAUNCH_CHECK("k_tile_codes");
+	ta.codes = c->d_tiled;
+
+	CK(cudaMalloc(&c->d_Apart, sizeof(double) * (size_t)best.n_tiles * ta.Ipad * K));
+	CK(cudaMalloc(&c->d_Npart, sizeof(double) * (size_t)C * K * std::max<int64_t>(c->T, 1)));
+	CK(cudaMalloc(&c->d_llpart, sizeof(double) * (size_t)ta.n_units));
+	CK(cudaMalloc(&c->d_xbuf, sizeof(double) * ((size_t)K * c->T + 1 + K)));
+	CK(cudaMalloc(&c->d_red, sizeof(double) * (size_t)RED_BLOCKS * 8));
+	CK(cudaMemsetAsync(c->d_Npart, 0, sizeof(double) * (size_t)C * K * std::max<int64_t>(c->T, 1), c->stream));
+	CK(cudaMemsetAsync(c->d_xbuf, 0, sizeof(double) * ((size_t)K * c->T + 1 + K), c->stream));
+	ta.Apart = c->d_Apart; ta.Npart = c->d_Npart; ta.llpart = c->d_llpart;
+	CK(cudaStreamSynchronize(c->stream));
+	return MC_OK;
+}
+
+/* ----------------------------------------------------------------- model */
+
+extern "C" int mc_alloc_model(mc_ctx *c, int32_t K, int admixture,
+	int eta_constrained, int q, double eta_lb, double p_lb, int do_projection)
+{
+	if (!c)
+		return MC_ERR_ARG;
+	if (!c->I)
+		return fail(c, MC_ERR_STATE, "mc_alloc_model: no data loaded");
+	if (K < 1 || q < 0 || q > MC_QMAX)
+		return fail(c, MC_ERR_ARG, "mc_alloc_model: bad K=%d or q=%d", K, q);
+	CK(cudaSetDevice(c->device));
+	free_model(c);
+	c->K = K; c->admixture = admixture ? 1 : 0;
+	c->eta_constrained = eta_constrained ? 1 : 0;
+	c->per_indiv = admixture && !eta_constrained;
+	c->q = q; c->eta_lb = eta_lb; c->p_lb = p_lb; c->do_proj = do_projection ? 1 : 0;
+	c->neta = c->per_indiv ? c->I * K : K;
+	c->np = (int64_t)K * c->T;
+	const size_t npb = sizeof(double) * (size_t)std::max<int64_t>(c->np, 1);
+	const size_t neb = sizeof(double) * (size_t)c->neta;
+	for (int s = 0; s < 3; s++) {
+		CK(cudaMalloc(&c->d_p[s], npb));
+		CK(cudaMalloc(&c->d_eta[s], neb));
+		CK(cudaMemsetAsync(c->d_p[s], 0, npb, c->stream));
+		CK(cudaMemsetAsync(c->d_eta[s], 0, neb, c->stream));
+	}
+	for (int s = 0; s < q; s++) {
+		double *a, *b, *d, *e;
+		CK(cudaMalloc(&a, npb)); CK(cudaMalloc(&b, npb));
+		CK(cudaMalloc(&d, neb)); CK(cudaMalloc(&e, neb));
+		c->d_up.push_back(a); c->d_vp.push_back(b);
+		c->d_ue.push_back(d); c->d_ve.push_back(e);
+	}
+	CK(cudaMalloc(&c->d_post, sizeof(double) * (size_t)c->I * K));
+	CK(cudaMemsetAsync(c->d_post, 0, sizeof(double) * (size_t)c->I * K, c->stream));
+	CK(cudaMalloc(&c->d_IK, sizeof(int) * (size_t)c->I));
+	if (!c->admixture) {
+		CK(cudaMalloc(&c->d_lli, sizeof(double) * (size_t)c->I));
+		CK(cudaMalloc(&c->d_logp, npb));
+	}
+	int rc = make_plan(c);
+	if (rc)
+		return rc;
+	c->have_model = true;
+	return MC_OK;
+}
+
+extern "C" int mc_eta_len(const mc_ctx *c, int64_t *n)
+{
+	if (!c || !c->have_model)
+		return MC_ERR_STATE;
+	*n = c->neta;
+	return MC_OK;
+}
+
+#define NEED_MODEL() do { if (!c) return MC_ERR_ARG; if (!c->have_model) \
+	return fail(c, MC_ERR_STATE, "%s: no model allocated", __func__); \
+	CK(cudaSetDevice(c->device)); } while (0)
+#define CHECK_SLOT(s) do { if ((s) < 0 || (s) > 2) \
+	return fail(c, MC_ERR_ARG, "%s: slot %d out of range", __func__, (s)); } while (0)
+
+extern "C" int mc_set_params(mc_ctx *c, int slot, const double *eta, const double *p)
+{
+	NEED_MODEL();
+	CHECK_SLOT(slot);
+	if (eta)
+		CK(cudaMemcpyAsync(c->d_eta[slot], eta, sizeof(double) * (size_t)c->neta,
+			cudaMemcpyHostToDevice, c->stream));
+	if (p)
+		CK(cudaMemcpyAsync(c->d_p[slot], p, sizeof(double) * (size_t)c->np,
+			cudaMemcpyHostToDevice, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return MC_OK;
+}
+
+extern "C" int mc_get_params(mc_ctx *c, int slot, double *eta, double *p)
+{
+	NEED_MODEL();
+	CHECK_SLOT(slot);
+	if (eta)
+		CK(cudaMemcpyAsync(eta, c->d_eta[slot], sizeof(double) * (size_t)c->neta,
+			cudaMemcpyDeviceToHost, c->stream));
+	if (p)
+		CK(cudaMemcpyAsync(p, c->d_p[slot], sizeof(double) * (size_t)c->np,
+			cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return MC_OK;
+}
+
+extern "C" int mc_copy_slot(mc_ctx *c, int dst, int src)
+{
+	NEED_MODEL();
+	CHECK_SLOT(dst);
+	CHECK_SLOT(src);
+	if (dst == src)
+		return MC_OK;
+	CK(cudaMemcpyAsync(c->d_eta[dst], c->d_eta[src], sizeof(double) * (size_t)c->neta,
+		cudaMemcpyDeviceToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->d_p[dst], c->d_p[src], sizeof(double) * (size_t)c->np,
+		cudaMemcpyDeviceToDevice, c->stream));
+	return MC_OK;
+}
+
+/* --------------------------------------------------- tile kernel dispatch */
+
+typedef void (*tile_fn)(const TileArgs);
+
+template <int KH, int MODE> static tile_fn pick_pp(int PP)
+{
+	switch (PP) {
+	case 1: return tile_kernel<KH, 1, MODE>;
+	case 2: return tile_kernel<KH, 2, MODE>;
+	case 4: return tile_kernel<KH, 4, MODE>;
+	case 8: return tile_kernel<KH, 8, MODE>;
+	case 16: return tile_kernel<KH, 16, MODE>;
+	}
+	return nullptr;
+}
+
+template <int MODE> static tile_fn pick_kh(int KH, int PP)
+{
+	switch (KH) {
+	case 1: return pick_pp<1, MODE>(PP);
+	case 2: return pick_pp<2, MODE>(PP);
+	case 3: return pick_pp<3, MODE>(PP);
+	case 4: return pick_pp<4, MODE>(PP);
+	case 5: return pick_pp<5, MODE>(PP);
+	case 6: return pick_pp<6, MODE>(PP);
+	}
+	return nullptr;
+}
+
+static tile_fn pick_kernel(int mode, int KH, int PP)
+{
+	switch (mode) {
+	case MODE_ADMIX_EM: return pick_kh<MODE_ADMIX_EM>(KH, PP);
+	case MODE_ADMIX_LL: return pick_kh<MODE_ADMIX_LL>(KH, PP);
+	case MODE_MIX_E: return pick_kh<MODE_MIX_E>(KH, PP);
+	case MODE_MIX_M: return pick_kh<MODE_MIX_M>(KH, PP);
+	}
+	return nullptr;
+}
+
+static int launch_tile(mc_ctx *c, int mode, const double *p, const double *eta,
+	long long eta_stride)
+{
+	tile_fn fn = pick_kernel(mode, c->KH, c->PP);
+	if (!fn)
+		return fail(c, MC_ERR_UNSUPPORTED, "no kernel for KH=%d PP=%d", c->KH, c->PP);
+	TileArgs ta = c->ta;
+	ta.p = p; ta.eta = eta; ta.eta_stride = eta_stride;
+	CK(cudaFuncSetAttribute((const void *)fn,
+		cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_em));
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	if (c->profile) {
+		CK(cudaEventCreate(&e0));
+		CK(cudaEventCreate(&e1));
+		CK(cudaEventRecord(e0, c->stream));
+	}
+	fn<<<c->grid, c->block, c->smem_em, c->stream>>>(ta);
+	LAUNCH_CHECK("tile_kernel");
+	if (c->profile) {
+		CK(cudaEventRecord(e1, c->stream));
+		c->prof_events.push_back({ e0, e1 });
+	}
+	return MC_OK;
+}
+
+/* sum d_llpart[0..n) (or any vector) into *out on the device */
+static int reduce_vector(mc_ctx *c, const double *x, long long n, double *out)
+{
+	k_colsum_partial<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(x, n, 1, 1, c->d_red);
+	LAUNCH_CHECK("k_colsum_partial");
+	k_colsum_final<<<1, RED_THREADS, 0, c->stream>>>(c->d_red, RED_BLOCKS, 1, out);
+	LAUNCH_CHECK("k_colsum_final");
+	return MC_OK;
+}
+
+/* column sums of an [rows][K] matrix into out[0..K) */
+static int reduce_columns(mc_ctx *c, const double *x, long long rows, int K, double *out)
+{
+	for (int k0 = 0; k0 < K; k0 += 8) {
+		const int nc = std::min(8, K - k0);
+		k_colsum_partial<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(x + k0, rows, nc, K, c->d_red);
+		LAUNCH_CHECK("k_colsum_partial");
+		k_colsum_final<<<1, RED_THREADS, 0, c->stream>>>(c->d_red, RED_BLOCKS, nc, out + k0);
+		LAUNCH_CHECK("k_colsum_final");
+	}
+	return MC_OK;
+}
+
+/* -------------------------------------------------------------- EM step */
+
+/* layout of the exchange buffer */
+static inline double *xb_N(mc_ctx *c) { return c->d_xbuf; }
+static inline double *xb_ll(mc_ctx *c) { return c->d_xbuf + c->np; }
+static inline double *xb_S(mc_ctx *c) { return c->d_xbuf + c->np + 1; }
+
+extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
+{
+	NEED_MODEL();
+	CHECK_SLOT(from);
+	CHECK_SLOT(to);
+	const int K = c->K;
+	int rc;
+	if (c->admixture) {
+		rc = launch_tile(c, MODE_ADMIX_EM, c->d_p[from], c->d_eta[from],
+			c->per_indiv ? K : 0);
+		if (rc) return rc;
+		k_sum_chunks<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_Npart,
+			c->ta.n_chunks, c->np, 0.0, xb_N(c));
+		LAUNCH_CHECK("k_sum_chunks");
+		if ((rc = reduce_vector(c, c->d_llpart, c->ta.n_units, xb_ll(c)))) return rc;
+		/* eta side: D_ik = eta_ik * A_ik needs only this context's
+		 * individuals; the streaming kernel is done with slot `from`, so
+		 * from == to (in-place EM) is safe */
+		k_admix_eta<<<grid_for(c, c->I, 128), 128, 0, c->stream>>>(c->d_Apart,
+			c->ta.n_tiles, c->ta.Ipad, c->I, K, c->d_eta[from],
+			c->per_indiv ? K : 0, c->d_eta[to], c->d_post, c->per_indiv,
+			c->do_proj, c->eta_lb);
+		LAUNCH_CHECK("k_admix_eta");
+		if (!c->per_indiv)	/* pooled eta: S_k = sum_i D_ik */
+			if ((rc = reduce_columns(c, c->d_post, c->I, K, xb_S(c)))) return rc;
+	} else {
+		k_log_table<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_p[from],
+			c->d_logp, c->np, 1);
+		LAUNCH_CHECK("k_log_table");
+		if ((rc = launch_tile(c, MODE_MIX_E, c->d_logp, nullptr, 0))) return rc;
+		k_mix_post<<<grid_for(c, c->I, 128), 128, 0, c->stream>>>(c->d_Apart,
+			c->ta.n_tiles, c->ta.Ipad, c->I, K, c->d_eta[from], c->d_post,
+			c->d_lli, 0);
+		LAUNCH_CHECK("k_mix_post");
+		if ((rc = reduce_vector(c, c->d_lli, c->I, xb_ll(c)))) return rc;
+		if ((rc = launch_tile(c, MODE_MIX_M, nullptr, c->d_post, K))) return rc;
+		k_sum_chunks<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_Npart,
+			c->ta.n_chunks, c->np, 0.0, xb_N(c));
+		LAUNCH_CHECK("k_sum_chunks");
+		if ((rc = reduce_columns(c, c->d_post, c->I, K, xb_S(c)))) return rc;
+	}
+	return MC_OK;
+}
+
+extern "C" int mc_exchange_buffer(mc_ctx *c, void **dev_ptr, size_t *n)
+{
+	NEED_MODEL();
+	if (dev_ptr) *dev_ptr = c->d_xbuf;
+	if (n) *n = (size_t)c->np + 1 + c->K;
+	return MC_OK;
+}
+
+extern "C" int mc_em_step_finish(mc_ctx *c, int to, double *ll)
+{
+	NEED_MODEL();
+	CHECK_SLOT(to);
+	const int K = c->K;
+	if (!c->per_indiv) {
+		k_update_eta_pooled<<<1, 32, 0, c->stream>>>(xb_S(c), c->d_eta[to], K,
+			c->do_proj, c->eta_lb);
+		LAUNCH_CHECK("k_update_eta_pooled");
+	}
+	const double *N = xb_N(c);
+	if (!c->admixture) {
+		/* pseudo-count p_lower_bound on every slot (em_alg.c:972) */
+		k_sum_chunks<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(xb_N(c), 1,
+			c->np, c->p_lb, c->d_Npart);
+		LAUNCH_CHECK("k_sum_chunks");
+		N = c->d_Npart;
+	}
+	k_update_p<<<grid_for(c, (long long)K * c->L, 128), 128, 0, c->stream>>>(
+		N, c->d_p[to], c->d_J, c->d_off, K, c->L, c->T, c->do_proj, c->p_lb);
+	LAUNCH_CHECK("k_update_p");
+	if (ll) {
+		CK(cudaMemcpyAsync(ll, xb_ll(c), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	return MC_OK;
+}
+
+extern "C" int mc_em_step(mc_ctx *c, int from, int to, double *ll)
+{
+	int rc = mc_em_step_local(c, from, to);
+	if (rc)
+		return rc;
+	return mc_em_step_finish(c, to, ll);
+}
+
+extern "C" int mc_loglik(mc_ctx *c, int slot, double *ll)
+{
+	NEED_MODEL();
+	CHECK_SLOT(slot);
+	int rc;
+	if (c->admixture) {
+		rc = launch_tile(c, MODE_ADMIX_LL, c->d_p[slot], c->d_eta[slot],
+			c->per_indiv ? c->K : 0);
+		if (rc) return rc;
+		if ((rc = reduce_vector(c, c->d_llpart, c->ta.n_units, xb_ll(c)))) return rc;
+	} else {
+		k_log_table<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_p[slot],
+			c->d_logp, c->np, 0);
+		LAUNCH_CHECK("k_log_table");
+		if ((rc = launch_tile(c, MODE_MIX_E, c->d_logp, nullptr, 0))) return rc;
+		/* the posterior of the last E-step must survive: use the per-
+		 * individual ll buffer only, rows go through Apart in place */
+		k_mix_post<<<grid_for(c, c->I, 128), 128, 0, c->stream>>>(c->d_Apart,
+			c->ta.n_tiles, c->ta.Ipad, c->I, c->K, c->d_eta[slot],
+			c->d_Apart, c->d_lli, 1);
+		LAUNCH_CHECK("k_mix_post");
+		if ((rc = reduce_vector(c, c->d_lli, c->I, xb_ll(c)))) return rc;
+	}
+	if (ll) {
+		CK(cudaMemcpyAsync(ll, xb_ll(c), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	return MC_OK;
+}
+
+extern "C" int mc_get_posterior(mc_ctx *c, double *out)
+{
+	NEED_MODEL();
+	CK(cudaMemcpyAsync(out, c->d_post, sizeof(double) * (size_t)c->I * c->K,
+		cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return MC_OK;
+}
+
+extern "C" int mc_partition(mc_ctx *c, int32_t *I_K, int32_t *count_K)
+{
+	NEED_MODEL();
+	k_partition<<<grid_for(c, c->I, 256), 256, 0, c->stream>>>(c->d_post, c->I, c->K, c->d_IK);
+	LAUNCH_CHECK("k_partition");
+	std::vector<int32_t> tmp;
+	int32_t *dst = I_K;
+	if (!dst) {
+		tmp.resize((size_t)c->I);
+		dst = tmp.data();
+	}
+	CK(cudaMemcpyAsync(dst, c->d_IK, sizeof(int) * (size_t)c->I, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	if (count_K) {
+		for (int k = 0; k < c->K; k++)
+			count_K[k] = 0;
+		for (int64_t i = 0; i < c->I; i++)
+			count_K[dst[i]]++;
+	}
+	return MC_OK;
+}
+
+/* ------------------------------------------------ acceleration plumbing */
+
+#define CHECK_PAIR(x) do { if ((x) < 0 || (x) >= c->q) \
+	return fail(c, MC_ERR_ARG, "%s: secant pair %d out of range (q=%d)", \
+		__func__, (x), c->q); } while (0)
+
+extern "C" int mc_delta(mc_ctx *c, int which, int pair, int slot_t, int slot_f)
+{
+	NEED_MODEL();
+	CHECK_PAIR(pair);
+	CHECK_SLOT(slot_t);
+	CHECK_SLOT(slot_f);
+	double *dp = which ? c->d_vp[pair] : c->d_up[pair];
+	double *de = which ? c->d_ve[pair] : c->d_ue[pair];
+	k_delta<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(dp, c->d_p[slot_t], c->d_p[slot_f], c->np);
+	LAUNCH_CHECK("k_delta");
+	k_delta<<<grid_for(c, c->neta, 256), 256, 0, c->stream>>>(de, c->d_eta[slot_t], c->d_eta[slot_f], c->neta);
+	LAUNCH_CHECK("k_delta");
+	return MC_OK;
+}
+
+static int fetch_small(mc_ctx *c, double *dst, int off, int n)
+{
+	CK(cudaMemcpyAsync(dst, c->d_small + off, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+	return MC_OK;
+}
+
+extern "C" int mc_step_dots(mc_ctx *c, int pair, double eta_part[3], double p_part[3])
+{
+	NEED_MODEL();
+	CHECK_PAIR(pair);
+	double z[3] = { 0, 0, 0 };
+	int rc;
+	k_step_dots<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->d_ue[pair], c->d_ve[pair], c->neta, c->d_red);
+	LAUNCH_CHECK("k_step_dots");
+	k_colsum_final<<<1, RED_THREADS, 0, c->stream>>>(c->d_red, RED_BLOCKS, 3, c->d_small);
+	LAUNCH_CHECK("k_colsum_final");
+	k_step_dots<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->d_up[pair], c->d_vp[pair], c->np, c->d_red + RED_BLOCKS * 3);
+	LAUNCH_CHECK("k_step_dots");
+	k_colsum_final<<<1, RED_THREADS, 0, c->stream>>>(c->d_red + RED_BLOCKS * 3, RED_BLOCKS, 3, c->d_small + 3);
+	LAUNCH_CHECK("k_colsum_final");
+	if ((rc = fetch_small(c, eta_part ? eta_part : z, 0, 3))) return rc;
+	double z2[3];
+	if ((rc = fetch_small(c, p_part ? p_part : z2, 3, 3))) return rc;
+	CK(cudaStreamSynchronize(c->stream));
+	return MC_OK;
+}
+
+extern "C" int mc_qn_dots(mc_ctx *c, int q1, int q2, double eta_part[2], double p_part[2])
+{
+	NEED_MODEL();
+	CHECK_PAIR(q1);
+	CHECK_PAIR(q2);
+	double z[2], z2[2];
+	int rc;
+	k_qn_dots<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->d_ue[q1], c->d_ue[q2], c->d_ve[q2], c->neta, c->d_red);
+	LAUNCH_CHECK("k_qn_dots");
+	k_colsum_final<<<1, RED_THREADS, 0, c->stream>>>(c->d_red, RED_BLOCKS, 2, c->d_small);
+	LAUNCH_CHECK("k_colsum_final");
+	k_qn_dots<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->d_up[q1], c->d_up[q2], c->d_vp[q2], c->np, c->d_red + RED_BLOCKS * 3);
+	LAUNCH_CHECK("k_qn_dots");
+	k_colsum_final<<<1, RED_THREADS, 0, c->stream>>>(c->d_red + RED_BLOCKS * 3, RED_BLOCKS, 2, c->d_small + 3);
+	LAUNCH_CHECK("k_colsum_final");
+	if ((rc = fetch_small(c, eta_part ? eta_part : z, 0, 2))) return rc;
+	if ((rc = fetch_small(c, p_part ? p_part : z2, 3, 2))) return rc;
+	CK(cudaStreamSynchronize(c->stream));
+	return MC_OK;
+}
+
+static int project_slot(mc_ctx *c, int slot)
+{
+	k_project_p<<<grid_for(c, (long long)c->K * c->L, 128), 128, 0, c->stream>>>(
+		c->d_p[slot], c->d_J, c->d_off, c->K, c->L, c->T, c->p_lb);
+	LAUNCH_CHECK("k_project_p");
+	const long long rows = c->per_indiv ? c->I : 1;
+	k_project_eta<<<grid_for(c, rows, 128), 128, 0, c->stream>>>(c->d_eta[slot], rows, c->K, c->eta_lb);
+	LAUNCH_CHECK("k_project_eta");
+	return MC_OK;
+}
+
+extern "C" int mc_project(mc_ctx *c, int slot)
+{
+	NEED_MODEL();
+	CHECK_SLOT(slot);
+	return project_slot(c, slot);
+}
+
+extern "C" int mc_accel_update(mc_ctx *c, int qn1, int slot_t, int slot_p, int pair, double s)
+{
+	NEED_MODEL();
+	CHECK_PAIR(pair);
+	CHECK_SLOT(slot_t);
+	CHECK_SLOT(slot_p);
+	k_accel_update<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_p[slot_t],
+		c->d_p[slot_p], c->d_up[pair], c->d_vp[pair], c->np, s, qn1);
+	LAUNCH_CHECK("k_accel_update");
+	k_accel_update<<<grid_for(c, c->neta, 256), 256, 0, c->stream>>>(c->d_eta[slot_t],
+		c->d_eta[slot_p], c->d_ue[pair], c->d_ve[pair], c->neta, s, qn1);
+	LAUNCH_CHECK("k_accel_update");
+	if (c->do_proj)
+		return project_slot(c, slot_t);
+	return MC_OK;
+}
+
+extern "C" int mc_qn_update(mc_ctx *c, int slot_t, int slot_p, int uindex,
+	int delta_index, const double *Ainv, const double *cutu)
+{
+	NEED_MODEL();
+	CHECK_SLOT(slot_t);
+	CHECK_SLOT(slot_p);
+	CHECK_PAIR(uindex);
+	CHECK_PAIR(delta_index);
+	if (!Ainv || !cutu)
+		return fail(c, MC_ERR_ARG, "mc_qn_update: null coefficients");
+	const int q = c->q;
+	QnArgs qp, qe;
+	memset(&qp, 0, sizeof qp);
+	qp.q = q;
+	/* row j uses the pair (delta_index + j) % q (accel_em.c:378-402) */
+	for (int j = 0; j < q; j++)
+		for (int n = 0; n < q; n++) {
+			qp.coef[j][n][0] = Ainv[j * q + n];
+			qp.coef[j][n][1] = cutu[n];
+		}
+	qe = qp;
+	for (int j = 0; j < q; j++) {
+		qp.v[j] = c->d_vp[(delta_index + j) % q];
+		qe.v[j] = c->d_ve[(delta_index + j) % q];
+	}
+	k_qn_update<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_p[slot_t],
+		c->d_p[slot_p], c->d_up[uindex], c->np, qp);
+	LAUNCH_CHECK("k_qn_update");
+	k_qn_update<<<grid_for(c, c->neta, 256), 256, 0, c->stream>>>(c->d_eta[slot_t],
+		c->d_eta[slot_p], c->d_ue[uindex], c->neta, qe);
+	LAUNCH_CHECK("k_qn_update");
+	if (c->do_proj)
+		return project_slot(c, slot_t);
+	return MC_OK;
+}
+
+/* -------------------------------------------------------- introspection */
+
+extern "C" int mc_get_plan(const mc_ctx *c, mc_plan_info *o)
+{
+	if (!c || !c->have_model || !o)
+		return MC_ERR_STATE;
+	o->K = c->K; o->k_split = c->k_split; o->k_per_lane = c->KH;
+	o->loci_per_warp = c->ta.loci_per_warp; o->warps = c->ta.warps;
+	o->groups = c->ta.groups; o->n_tiles = c->ta.n_tiles;
+	o->n_chunks = c->ta.n_chunks; o->n_units = c->ta.n_units;
+	o->grid = c->grid; o->block = c->block;
+	o->indiv_per_block = c->IB; o->ploidy_padded = c->PP;
+	o->smem_bytes = (int64_t)c->smem_em;
+	const int64_t g = c->I * (int64_t)c->L * c->P;
+	o->algorithmic_bytes_em = g + 16 * c->I * (int64_t)c->K + 16 * (int64_t)c->K * c->T;
+	o->algorithmic_bytes_ll = g + 8 * c->I * (int64_t)c->K + 8 * (int64_t)c->K * c->T;
+	return MC_OK;
+}
+
+extern "C" int64_t mc_launch_count(const mc_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int mc_profile_enable(mc_ctx *c, int on)
+{
+	if (!c)
+		return MC_ERR_ARG;
+	c->profile = on != 0;
+	return MC_OK;
+}
+
+extern "C" int mc_profile_read(mc_ctx *c, int64_t *n, double *ms)
+{
+	if (!c)
+		return MC_ERR_ARG;
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	for (auto &ev : c->prof_events) {
+		float t = 0;
+		CK(cudaEventElapsedTime(&t, ev.first, ev.second));
+		c->prof_ms += t;
+		c->prof_n++;
+		cudaEventDestroy(ev.first);
+		cudaEventDestroy(ev.second);
+	}
+	c->prof_events.clear();
+	if (n) *n = c->prof_n;
+	if (ms) *ms = c->prof_ms;
+	c->prof_n = 0;
+	c->prof_ms = 0;
+	return MC_OK;
+}

@@ -1,0 +1,771 @@
+/*
+ * mc_kernels.cuh -- sm_100a kernels of the MULTICLUST EM hot path.
+ *
+ * One templated genotype-streaming kernel (`tile_kernel`) covers the four
+ * data passes of the reference, selected by MODE:
+ *   MODE_ADMIX_EM  e_step_admixture_orig + the sums m_step_admixture_orig
+ *                  needs (em_alg.c:325-433, 604-725), fused, never
+ *                  materialising d_iklm (multiclust.c:1197 allocates I*K*T)
+ *   MODE_ADMIX_LL  logL_admixture (log_likelihood.c:128-144)
+ *   MODE_MIX_E     per-individual sum of log p over the observed copies
+ *                  (e_step_mixture em_alg.c:793-827, logL_mixture
+ *                  log_likelihood.c:189-203)
+ *   MODE_MIX_M     allele-count sums of m_step_mixture (em_alg.c:965-986)
+ *
+ * Mapping:
+ *   - loci are dealt to tiles; a CTA owns one tile for one chunk of
+ *     individuals ("unit"), units are striped over a persistent grid;
+ *   - inside a warp, lane = locus_in_warp * k_split + kh: k_split adjacent
+ *     lanes share a locus and each holds KH = ceil(K / k_split) of the K
+ *     clusters in registers;
+ *   - the tile's p rows and allele-count accumulators live in shared memory in
+ *     a lane-interleaved layout [row][kk][lane], so every 64-bit access of a
+ *     half warp hits 16 distinct bank pairs whatever the allele codes are, and
+ *     each accumulator column is private to one thread: no atomics, and the
+ *     summation order is fixed (deterministic);
+ *   - genotypes are read straight from HBM as one 16-byte vector per (locus,
+ *     block of individuals) from a tile-major layout, so a warp reads a
+ *     contiguous run of 16-byte units; they are not staged through shared
+ *     memory because the shared-memory pipe is this kernel's binding resource;
+ *   - per-individual sums (A_ik) are kept in registers for a block of
+ *     individuals, folded across the lanes of a warp by a recursive-halving
+ *     shuffle reduction and across warps through a small scratch buffer.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MC_MISSING 255
+
+enum { MODE_ADMIX_EM = 0, MODE_ADMIX_LL = 1, MODE_MIX_E = 2, MODE_MIX_M = 3 };
+
+struct TileArgs {
+	/* plan */
+	int K, k_split, loci_per_warp, warps, groups;
+	int n_tiles, n_chunks, n_units;
+	int tile_slots;			/* warps * groups * loci_per_warp */
+	long long n_blocks;		/* blocks of IB individuals */
+	long long I, Ipad, T;
+	/* per tile tables */
+	const int *slot_locus;		/* [n_tiles][tile_slots], -1 = padding */
+	const int *slot_off;		/* [n_tiles][tile_slots] off[l] */
+	const int *slot_J;		/* [n_tiles][tile_slots] J[l] */
+	const int *group_rowbase;	/* [n_tiles][groups*warps] first smem row */
+	const int *group_rows;		/* [n_tiles][groups*warps] rows (max J) */
+	const int *tile_rows;		/* [n_tiles] total rows */
+	int max_rows;			/* max over tiles: smem sizing */
+	/* data */
+	const unsigned char *codes;	/* tile-major units */
+	long long tile_stride;		/* bytes between tiles */
+	/* parameters */
+	const double *p;		/* [K][T] p (admixture) or log p (mixture E) */
+	const double *eta;		/* eta rows / v_ik rows */
+	long long eta_stride;		/* K, or 0 for a shared row */
+	/* outputs */
+	double *Apart;			/* [n_tiles][Ipad][K] */
+	double *Npart;			/* [n_chunks][K*T] */
+	double *llpart;			/* [n_units] */
+};
+
+__device__ __forceinline__ double mc_rcp(double x)
+{
+#ifdef MC_EXACT_DIV
+	return 1.0 / x;
+#else
+	/* MUFU.RCP64H seed + two Newton steps: ~1 ulp, a third of the
+	 * instructions of the IEEE division sequence */
+	double r, e;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+	e = fma(-x, r, 1.0);
+	r = fma(r, e, r);
+	e = fma(-x, r, 1.0);
+	r = fma(r, e, r);
+	return r;
+#endif
+}
+
+__device__ __forceinline__ double shfl_xor_f64(double v, int mask)
+{
+	int lo = __double2loint(v), hi = __double2hiint(v);
+	lo = __shfl_xor_sync(0xffffffffu, lo, mask);
+	hi = __shfl_xor_sync(0xffffffffu, hi, mask);
+	return __hiloint2double(hi, lo);
+}
+
+/* one recursive-halving step over N live values: lanes whose `mask` bit is
+ * clear keep the lower half, the others the upper half */
+template <int N>
+__device__ __forceinline__ void rs_step(double *a, int mask, int lane,
+	int &lo, int &hi)
+{
+	constexpr int H = (N + 1) / 2;
+	const bool up = (lane & mask) != 0;
+#pragma unroll
+	for (int j = 0; j < H; j++) {
+		double vlo = a[j];
+		double vhi = (j + H < N) ? a[j + H] : 0.0;
+		double send = up ? vlo : vhi;
+		double keep = up ? vhi : vlo;
+		a[j] = keep + shfl_xor_f64(send, mask);
+	}
+	if (up)
+		lo += H;
+	else
+		hi = min(hi, lo + H);
+}
+
+/* sum a[0..V) over the lanes that share lane % k_split; on return lane holds
+ * the totals of indices [lo, hi) in a[0..hi-lo) */
+template <int V>
+__device__ __forceinline__ void lane_reduce_scatter(double *a, int k_split,
+	int lane, int &lo, int &hi)
+{
+	constexpr int N1 = (V + 1) / 2, N2 = (N1 + 1) / 2, N3 = (N2 + 1) / 2,
+		N4 = (N3 + 1) / 2;
+	lo = 0;
+	hi = V;
+	if (k_split <= 16) rs_step<V>(a, 16, lane, lo, hi);
+	if (k_split <= 8) rs_step<N1>(a, 8, lane, lo, hi);
+	if (k_split <= 4) rs_step<N2>(a, 4, lane, lo, hi);
+	if (k_split <= 2) rs_step<N3>(a, 2, lane, lo, hi);
+	if (k_split <= 1) rs_step<N4>(a, 1, lane, lo, hi);
+}
+
+template <int PP> struct UnitT;
+template <> struct UnitT<1> { typedef uint2 type; };	/* 8 individuals x 1 */
+template <> struct UnitT<2> { typedef uint4 type; };	/* 8 x 2 */
+template <> struct UnitT<4> { typedef uint4 type; };	/* 4 x 4 */
+template <> struct UnitT<8> { typedef uint4 type; };	/* 2 x 8 */
+template <> struct UnitT<16> { typedef uint4 type; };	/* 1 x 16 */
+
+__device__ __forceinline__ unsigned unit_byte(const uint4 &u, int b)
+{
+	unsigned w = b < 8 ? (b < 4 ? u.x : u.y) : (b < 12 ? u.z : u.w);
+	return (w >> ((b & 3) * 8)) & 0xffu;
+}
+__device__ __forceinline__ unsigned unit_byte(const uint2 &u, int b)
+{
+	unsigned w = b < 4 ? u.x : u.y;
+	return (w >> ((b & 3) * 8)) & 0xffu;
+}
+
+template <int KH, int PP, int MODE>
+__global__ void __launch_bounds__(256, 1) tile_kernel(const TileArgs a)
+{
+	constexpr int IB = (PP >= 2) ? 16 / PP : 8;	/* individuals per unit */
+	constexpr int UB = IB * PP;			/* bytes per unit */
+	constexpr int V = IB * KH;			/* A values per lane */
+	constexpr bool HAS_A = (MODE == MODE_ADMIX_EM || MODE == MODE_MIX_E);
+	constexpr bool HAS_B = (MODE == MODE_ADMIX_EM || MODE == MODE_MIX_M);
+	constexpr bool HAS_P = (MODE != MODE_MIX_M);
+	constexpr bool HAS_LL = (MODE == MODE_ADMIX_EM || MODE == MODE_ADMIX_LL);
+	typedef typename UnitT<PP>::type unit_t;
+
+	extern __shared__ double smem[];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int W = a.warps, NG = a.groups, LW = a.loci_per_warp;
+	const int ks = a.k_split;
+	const int kh = lane % ks, lw = lane / ks;
+	const int k0 = kh * KH;
+	const int RS = KH * 32;		/* doubles per smem row */
+	double *p_s = smem;
+	double *B_s = p_s + (HAS_P ? (size_t)a.max_rows * RS : 0);
+	double *scr = B_s + (HAS_B ? (size_t)a.max_rows * RS : 0);
+	/* scratch: [2][W][ks][V] then W doubles for the ll reduction */
+	double *llred = scr + (HAS_A ? 2 * W * ks * V : 0);
+	int buf = 0;
+
+	for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+		const int t = u % a.n_tiles, c = u / a.n_tiles;
+		const long long b0 = a.n_blocks * c / a.n_chunks;
+		const long long b1 = a.n_blocks * (c + 1) / a.n_chunks;
+		const int *s_locus = a.slot_locus + (size_t)t * a.tile_slots;
+		const int *s_off = a.slot_off + (size_t)t * a.tile_slots;
+		const int *s_J = a.slot_J + (size_t)t * a.tile_slots;
+		const int *g_rowbase = a.group_rowbase + (size_t)t * NG * W;
+		const int *g_rows = a.group_rows + (size_t)t * NG * W;
+
+		__syncthreads();	/* previous unit has left shared memory */
+		/* ---- stage this thread's columns of the tile ---- */
+		for (int g = 0; g < NG; g++) {
+			const int s = (g * W + w) * LW + lw;
+			const int loc = s_locus[s], Jl = s_J[s], ol = s_off[s];
+			const int rb = g_rowbase[g * W + w], nr = g_rows[g * W + w];
+			for (int j = 0; j < nr; j++)
+#pragma unroll
+				for (int kk = 0; kk < KH; kk++) {
+					const size_t x = ((size_t)(rb + j) * KH + kk) * 32 + lane;
+					if (HAS_P) {
+						double v = 0.0;
+						if (loc >= 0 && j < Jl && k0 + kk < a.K)
+							v = a.p[(size_t)(k0 + kk) * a.T + ol + j];
+						p_s[x] = v;
+					}
+					if (HAS_B)
+						B_s[x] = 0.0;
+				}
+		}
+		/* columns are thread private: no barrier needed before use */
+
+		double prod = 1.0, ll_slow = 0.0;
+		long long esum = 0;
+		const unsigned char *tile_codes = a.codes + (size_t)t * a.tile_stride;
+
+		for (long long b = b0; b < b1; b++) {
+			double A[HAS_A ? V : 1];
+			if (HAS_A) {
+#pragma unroll
+				for (int v = 0; v < V; v++)
+					A[v] = 0.0;
+			}
+			for (int g = 0; g < NG; g++) {
+				const int s = (g * W + w) * LW + lw;
+				const int rb = g_rowbase[g * W + w];
+				const unit_t cu = *reinterpret_cast<const unit_t *>(
+					tile_codes + ((size_t)b * a.tile_slots + s) * UB);
+#pragma unroll
+				for (int ii = 0; ii < IB; ii++) {
+					double e[KH];
+					if (MODE != MODE_MIX_E) {
+						const long long i = b * IB + ii;
+						const double *er = a.eta + (size_t)(i < a.I ? i : 0) * a.eta_stride + k0;
+#pragma unroll
+						for (int kk = 0; kk < KH; kk++)
+							e[kk] = (k0 + kk < a.K && i < a.I) ? er[kk] : 0.0;
+					}
+#pragma unroll
+					for (int ap = 0; ap < PP; ap++) {
+						const unsigned code = unit_byte(cu, ii * PP + ap);
+						const bool valid = code != MC_MISSING;
+						const size_t x0 = ((size_t)(rb + (valid ? code : 0u)) * KH) * 32 + lane;
+						double pr[KH];
+						if (HAS_P) {
+#pragma unroll
+							for (int kk = 0; kk < KH; kk++)
+								pr[kk] = p_s[x0 + kk * 32];
+						}
+						if (MODE == MODE_MIX_E) {
+#pragma unroll
+							for (int kk = 0; kk < KH; kk++)
+								A[ii * KH + kk] += valid ? pr[kk] : 0.0;
+						} else if (MODE == MODE_MIX_M) {
+#pragma unroll
+							for (int kk = 0; kk < KH; kk++)
+								B_s[x0 + kk * 32] += valid ? e[kk] : 0.0;
+						} else {
+							double tmp = 0.0;
+#pragma unroll
+							for (int kk = 0; kk < KH; kk++)
+								tmp = fma(e[kk], pr[kk], tmp);
+							for (int m = 1; m < ks; m <<= 1)
+								tmp += shfl_xor_f64(tmp, m);
+							tmp = valid ? tmp : 1.0;
+							/* log(tmp) = exponent*ln2 + log(mantissa): the
+							 * mantissas are multiplied up and logged once */
+							const int hi = __double2hiint(tmp);
+							const int ex = (hi >> 20) & 0x7ff;
+							if (hi < 0 || ex == 0 || ex == 0x7ff) {
+								ll_slow += log(tmp);
+							} else {
+								esum += ex - 1023;
+								prod *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000,
+									__double2loint(tmp));
+							}
+							if (MODE == MODE_ADMIX_EM) {
+								const double wgt = valid ? mc_rcp(tmp) : 0.0;
+#pragma unroll
+								for (int kk = 0; kk < KH; kk++) {
+									A[ii * KH + kk] = fma(pr[kk], wgt, A[ii * KH + kk]);
+									B_s[x0 + kk * 32] = fma(e[kk], wgt, B_s[x0 + kk * 32]);
+								}
+							}
+						}
+					}
+				}
+				if (HAS_LL) {
+					/* prod < 2^(IB*PP): fold its exponent away */
+					const int hi = __double2hiint(prod);
+					esum += ((hi >> 20) & 0x7ff) - 1023;
+					prod = __hiloint2double((hi & 0x000fffff) | 0x3ff00000,
+						__double2loint(prod));
+				}
+			}
+			if (HAS_A) {
+				/* fold the block's sums over loci: lanes, then warps */
+				int lo, hi;
+				lane_reduce_scatter<V>(A, ks, lane, lo, hi);
+				double *mine = scr + ((size_t)(buf * W + w) * ks + kh) * V;
+#pragma unroll
+				for (int v = 0; v < V; v++)
+					if (v < hi - lo)
+						mine[lo + v] = A[v];
+				__syncthreads();
+				for (int idx = threadIdx.x; idx < ks * V; idx += blockDim.x) {
+					const int rkh = idx / V, v = idx % V;
+					const int ii = v / KH, kk = v % KH;
+					const int k = rkh * KH + kk;
+					double sum = 0.0;
+					for (int ww = 0; ww < W; ww++)
+						sum += scr[((size_t)(buf * W + ww) * ks + rkh) * V + v];
+					if (k < a.K)
+						a.Apart[((size_t)t * a.Ipad + b * IB + ii) * a.K + k] = sum;
+				}
+				buf ^= 1;
+			}
+		}
+
+		/* ---- flush this unit ---- */
+		if (HAS_B) {
+			double *Np = a.Npart + (size_t)c * a.K * a.T;
+			for (int g = 0; g < NG; g++) {
+				const int s = (g * W + w) * LW + lw;
+				const int loc = s_locus[s], Jl = s_J[s], ol = s_off[s];
+				const int rb = g_rowbase[g * W + w];
+				if (loc < 0)
+					continue;
+				for (int j = 0; j < Jl; j++)
+#pragma unroll
+					for (int kk = 0; kk < KH; kk++)
+						if (k0 + kk < a.K) {
+							const size_t x = ((size_t)(rb + j) * KH + kk) * 32 + lane;
+							/* d_iklj = eta p / tmp: the factor p_klj is
+							 * common to the whole column, applied once */
+							double v = B_s[x];
+							if (MODE == MODE_ADMIX_EM)
+								v *= p_s[x];
+							Np[(size_t)(k0 + kk) * a.T + ol + j] = v;
+						}
+			}
+		}
+		if (HAS_LL) {
+			double ll = (kh == 0) ? (log(prod) + (double)esum * 0.693147180559945309417232121458 + ll_slow) : 0.0;
+#pragma unroll
+			for (int m = 16; m >= 1; m >>= 1)
+				ll += shfl_xor_f64(ll, m);
+			__syncthreads();
+			if (lane == 0)
+				llred[w] = ll;
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				double sum = 0.0;
+				for (int ww = 0; ww < W; ww++)
+					sum += llred[ww];
+				a.llpart[u] = sum;
+			}
+		}
+	}
+}
+
+/* ------------------------------------------------------------------ */
+/* natural [I][L][P] codes -> tile-major 16-byte units                  */
+
+__global__ void k_tile_codes(const unsigned char *nat, unsigned char *out,
+	const int *slot_locus, int n_tiles, int tile_slots, long long n_blocks,
+	long long I, int L, int P, int PP, int IB, long long tile_stride)
+{
+	const long long n = (long long)n_tiles * n_blocks * tile_slots;
+	const int UB = IB * PP;
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		const int s = (int)(x % tile_slots);
+		const long long b = (x / tile_slots) % n_blocks;
+		const int t = (int)(x / tile_slots / n_blocks);
+		const int loc = slot_locus[(size_t)t * tile_slots + s];
+		unsigned char *o = out + (size_t)t * tile_stride + ((size_t)b * tile_slots + s) * UB;
+		for (int ii = 0; ii < IB; ii++) {
+			const long long i = b * IB + ii;
+			for (int ap = 0; ap < PP; ap++) {
+				unsigned char c = MC_MISSING;
+				if (loc >= 0 && i < I && ap < P)
+					c = nat[((size_t)i * L + loc) * P + ap];
+				o[ii * PP + ap] = c;
+			}
+		}
+	}
+}
+
+/* ------------------------------------------------------------------ */
+/* Michelot projection with a floor (simplex.c:109-143) on a strided row */
+
+__device__ __forceinline__ void project_row(double *x, int n, double floor_)
+{
+	unsigned fixed[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };	/* n <= 256 */
+	int nfree = n;
+	while (nfree) {
+		double csum = 0.0;
+		for (int i = 0; i < n; i++)
+			csum += x[i];
+		const double shift = (csum - 1.0) / nfree;
+		bool done = true;
+		for (int i = 0; i < n; i++)
+			if (!(fixed[i >> 5] >> (i & 31) & 1u)) {
+				double v = x[i] - shift;
+				if (v < floor_) {
+					v = floor_;
+					fixed[i >> 5] |= 1u << (i & 31);
+					nfree--;
+					done = false;
+				}
+				x[i] = v;
+			}
+		if (done)
+			break;
+	}
+}
+
+/* p rows: one thread per (k, l) */
+__global__ void k_project_p(double *p, const int *J, const int *off, int K,
+	int L, long long T, double lb)
+{
+	const long long n = (long long)K * L;
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		const int k = (int)(x / L), l = (int)(x % L);
+		project_row(p + (size_t)k * T + off[l], J[l], lb);
+	}
+}
+
+/* eta rows: one thread per row of length K */
+__global__ void k_project_eta(double *eta, long long rows, int K, double lb)
+{
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows;
+		i += (long long)gridDim.x * blockDim.x)
+		project_row(eta + (size_t)i * K, K, lb);
+}
+
+/* ------------------------------------------------------------------ */
+/* admixture M-step, eta side (em_alg.c:650-702): A_ik = sum over tiles,
+ * D_ik = eta_ik A_ik, eta_ik = D_ik / sum_k D_ik, projection             */
+
+__global__ void k_admix_eta(const double *Apart, int n_tiles, long long Ipad,
+	long long I, int K, const double *eta_f, long long eta_stride,
+	double *eta_t, double *D, int per_indiv, int do_proj, double lb)
+{
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < I;
+		i += (long long)gridDim.x * blockDim.x) {
+		double s = 0.0;
+		for (int k = 0; k < K; k++) {
+			double acc = 0.0;
+			for (int t = 0; t < n_tiles; t++)
+				acc += Apart[((size_t)t * Ipad + i) * K + k];
+			const double d = eta_f[(size_t)i * eta_stride + k] * acc;
+			D[(size_t)i * K + k] = d;
+			s += d;
+		}
+		if (per_indiv) {
+			double *row = eta_t + (size_t)i * K;
+			for (int k = 0; k < K; k++)
+				row[k] = D[(size_t)i * K + k] / s;
+			if (do_proj)
+				project_row(row, K, lb);
+		}
+	}
+}
+
+/* mixture E-step tail (em_alg.c:828-882) / logL_mixture tail
+ * (log_likelihood.c:203-228): a_ik = log eta_k + sum of log p               */
+__global__ void k_mix_post(const double *Apart, int n_tiles, long long Ipad,
+	long long I, int K, const double *eta, double *vik, double *ll_i,
+	int ll_only)
+{
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < I;
+		i += (long long)gridDim.x * blockDim.x) {
+		double mx = -INFINITY;
+		double *v = vik + (size_t)i * K;	/* scratch row when ll_only */
+		for (int k = 0; k < K; k++) {
+			double acc = 0.0;
+			for (int t = 0; t < n_tiles; t++)
+				acc += Apart[((size_t)t * Ipad + i) * K + k];
+			acc += log(eta[k]);
+			v[k] = acc;
+			if (acc > mx)
+				mx = acc;
+		}
+		if (!ll_only) {
+			double s = 0.0;
+			for (int k = 0; k < K; k++) {
+				v[k] = exp(v[k] - mx);
+				s += v[k];
+			}
+			for (int k = 0; k < K; k++)
+				v[k] /= s;
+			ll_i[i] = log(s) + mx;
+		} else {
+			double te = exp(mx), scale = 0.0, s = 0.0;
+			if (te == 0.0 || te == HUGE_VAL) {
+				scale = (te == HUGE_VAL) ? mx : -mx;
+				do {
+					scale *= 0.5;
+					te = exp(scale);
+				} while (te == HUGE_VAL);
+				scale = mx - scale;
+			}
+			for (int k = 0; k < K; k++)
+				s += exp(v[k] - scale);
+			ll_i[i] = log(s) + scale;
+		}
+	}
+}
+
+/* ------------------------------------------------------------------ */
+/* deterministic reductions: fixed grid, fixed tree                      */
+
+#define RED_BLOCKS 296
+#define RED_THREADS 256
+
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+#pragma unroll
+	for (int m = 16; m >= 1; m >>= 1)
+		v += shfl_xor_f64(v, m);
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0)
+		sh[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double s = 0.0;
+	if (threadIdx.x == 0)
+		for (int w = 0; w < (int)(blockDim.x >> 5); w++)
+			s += sh[w];
+	return s;	/* valid in thread 0 */
+}
+
+/* out[b*ncol + c] = sum over this block's rows of x[r*ncol + c], c < ncol <= 8 */
+__global__ void k_colsum_partial(const double *x, long long rows, int ncol,
+	long long row_stride, double *part)
+{
+	__shared__ double sh[RED_THREADS / 32];
+	for (int c = 0; c < ncol; c++) {
+		double v = 0.0;
+		for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
+			r += (long long)gridDim.x * blockDim.x)
+			v += x[(size_t)r * row_stride + c];
+		v = block_sum(v, sh);
+		if (threadIdx.x == 0)
+			part[(size_t)blockIdx.x * ncol + c] = v;
+	}
+}
+
+/* final stage: one block, out[c] (+)= sum_b part[b*ncol + c] */
+__global__ void k_colsum_final(const double *part, int nblocks, int ncol,
+	double *out)
+{
+	__shared__ double sh[RED_THREADS / 32];
+	for (int c = 0; c < ncol; c++) {
+		double v = 0.0;
+		for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+			v += part[(size_t)b * ncol + c];
+		v = block_sum(v, sh);
+		if (threadIdx.x == 0)
+			out[c] = v;
+	}
+}
+
+/* N[x] = sum_c Npart[c][x] (+ add) : allele-count sums over chunks */
+__global__ void k_sum_chunks(const double *Npart, int n_chunks, long long n,
+	double add, double *out)
+{
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		double s = add;
+		for (int c = 0; c < n_chunks; c++)
+			s += Npart[(size_t)c * n + x];
+		out[x] = s;
+	}
+}
+
+/* p side of both M-steps (em_alg.c:706-752, 965-1010): normalise each (k,l)
+ * row of the count sums and project */
+__global__ void k_update_p(const double *N, double *p_t, const int *J,
+	const int *off, int K, int L, long long T, int do_proj, double lb)
+{
+	const long long n = (long long)K * L;
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		const int k = (int)(x / L), l = (int)(x % L);
+		const double *nr = N + (size_t)k * T + off[l];
+		double *row = p_t + (size_t)k * T + off[l];
+		const int Jl = J[l];
+		double s = 0.0;
+		for (int j = 0; j < Jl; j++)
+			s += nr[j];
+		for (int j = 0; j < Jl; j++)
+			row[j] = nr[j] / s;
+		if (do_proj)
+			project_row(row, Jl, lb);
+	}
+}
+
+/* pooled eta (em_alg.c:604-648, 916-962): eta_k = S_k / sum S, projection */
+__global__ void k_update_eta_pooled(const double *S, double *eta_t, int K,
+	int do_proj, double lb)
+{
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		double s = 0.0;
+		for (int k = 0; k < K; k++)
+			s += S[k];
+		for (int k = 0; k < K; k++)
+			eta_t[k] = S[k] / s;
+		if (do_proj)
+			project_row(eta_t, K, lb);
+	}
+}
+
+/* log p table for the mixture passes; zero_skip reproduces the E-step's
+ * "p == 0 contributes nothing" rule (em_alg.c:797-804) */
+__global__ void k_log_table(const double *p, double *lp, long long n,
+	int zero_skip)
+{
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		const double v = p[x];
+		lp[x] = (zero_skip && v == 0.0) ? 0.0 : log(v);
+	}
+}
+
+/* ------------------------------------------------------------------ */
+/* parameter-space kernels of the acceleration schemes                   */
+
+__global__ void k_delta(double *d, const double *xt, const double *xf,
+	long long n)
+{
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x)
+		d[x] = xt[x] - xf[x];
+}
+
+/* {u.u, u.(v-u), (v-u).(v-u)} (accel_em.c:142-184) -> part[b][3] */
+__global__ void k_step_dots(const double *u, const double *v, long long n,
+	double *part)
+{
+	__shared__ double sh[RED_THREADS / 32];
+	double a = 0.0, b = 0.0, c = 0.0;
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		const double uu = u[x], r = v[x] - uu;
+		a += uu * uu;
+		b += uu * r;
+		c += r * r;
+	}
+	a = block_sum(a, sh);
+	b = block_sum(b, sh);
+	c = block_sum(c, sh);
+	if (threadIdx.x == 0) {
+		part[(size_t)blockIdx.x * 3 + 0] = a;
+		part[(size_t)blockIdx.x * 3 + 1] = b;
+		part[(size_t)blockIdx.x * 3 + 2] = c;
+	}
+}
+
+/* {u1.u2, u1.v2} (accel_em.c:291-310) -> part[b][2] */
+__global__ void k_qn_dots(const double *u1, const double *u2, const double *v2,
+	long long n, double *part)
+{
+	__shared__ double sh[RED_THREADS / 32];
+	double a = 0.0, b = 0.0;
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		const double uu = u1[x];
+		a += uu * u2[x];
+		b += uu * v2[x];
+	}
+	a = block_sum(a, sh);
+	b = block_sum(b, sh);
+	if (threadIdx.x == 0) {
+		part[(size_t)blockIdx.x * 2 + 0] = a;
+		part[(size_t)blockIdx.x * 2 + 1] = b;
+	}
+}
+
+/* accel_em.c:449-466 / 486-503, same expression shapes as the reference */
+__global__ void k_accel_update(double *xt, const double *xp, const double *u,
+	const double *v, long long n, double s, int qn1)
+{
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		if (qn1)
+			xt[x] = __dadd_rn(__dadd_rn(xp[x], u[x]), __dmul_rn(s, v[x]));
+		else
+			xt[x] = __dadd_rn(__dadd_rn(xp[x], -__dmul_rn(__dmul_rn(2.0, s), u[x])),
+				__dmul_rn(__dmul_rn(s, s), __dadd_rn(v[x], -u[x])));
+	}
+}
+
+#define MC_QMAX 3
+struct QnArgs {
+	const double *v[MC_QMAX];	/* v of the pair used by row j */
+	double coef[MC_QMAX][MC_QMAX][2];	/* Ainv[j][n], cutu[n] */
+	int q;
+};
+
+/* accel_em.c:364-402 */
+__global__ void k_qn_update(double *xt, const double *xp, const double *uu,
+	long long n, const QnArgs qa)
+{
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		double acc = __dadd_rn(xp[x], uu[x]);
+		for (int j = 0; j < qa.q; j++) {
+			const double vv = qa.v[j][x];
+			for (int m = 0; m < qa.q; m++)
+				acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(vv, qa.coef[j][m][0]),
+					qa.coef[j][m][1]));
+		}
+		xt[x] = acc;
+	}
+}
+
+/* argmax_k of the posterior, first maximum wins (write_file.c:369-375,590-598) */
+__global__ void k_partition(const double *post, long long I, int K, int *I_K)
+{
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < I;
+		i += (long long)gridDim.x * blockDim.x) {
+		const double *r = post + (size_t)i * K;
+		int best = 0;
+		double m = r[0];
+		for (int k = 1; k < K; k++)
+			if (r[k] > m) {
+				m = r[k];
+				best = k;
+			}
+		I_K[i] = best;
+	}
+}
+
+/* ------------------------------------------------------------------ */
+/* synthetic data straight into HBM (include/mc_synth.h)                 */
+
+__global__ void k_synth_fill(unsigned char *nat, long long I, int L,
+	mcs_params g, long long i_first, unsigned *present /* [L][8] */,
+	unsigned *missing /* [L] */)
+{
+	const long long n = I * (long long)L;
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		const long long i = x / L;
+		const int l = (int)(x % L);
+		for (int ap = 0; ap < g.ploidy; ap++) {
+			const unsigned char c = mcs_code(&g, i_first + i, l, ap);
+			nat[(size_t)x * g.ploidy + ap] = c;
+			if (c == MC_MISSING)
+				atomicOr(&missing[l], 1u);
+			else
+				atomicOr(&present[(size_t)l * 8 + (c >> 5)], 1u << (c & 31));
+		}
+	}
+}
+
+__global__ void k_synth_remap(unsigned char *nat, long long I, int L, int P,
+	const unsigned char *map /* [L][256] */)
+{
+	const long long n = I * (long long)L;
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		const int l = (int)(x % L);
+		for (int ap = 0; ap < P; ap++) {
+			const unsigned char c = nat[(size_t)x * P + ap];
+			if (c != MC_MISSING)
+				nat[(size_t)x * P + ap] = map[(size_t)l * 256 + c];
+		}
+	}
+}
