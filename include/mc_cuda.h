@@ -150,6 +150,12 @@ int mc_copy_slot(mc_ctx *ctx, int dst, int src);
 int mc_em_step_local(mc_ctx *ctx, int from, int to);
 int mc_exchange_buffer(mc_ctx *ctx, void **dev_ptr, size_t *n_doubles);
 int mc_em_step_finish(mc_ctx *ctx, int to, double *ll);
+/* Deterministic alternative to an all-reduce: `gathered` is a DEVICE buffer
+ * holding the exchange buffers of all ranks back to back (the result of an
+ * all-gather, n_ranks * n_doubles); they are added in rank order into this
+ * context's exchange buffer, so every rank computes bit-identical sums
+ * whatever algorithm the collective library picked. */
+int mc_exchange_sum(mc_ctx *ctx, const void *gathered, int n_ranks);
 
 /* ---- introspection for bench / profiles --------------------------------- */
 

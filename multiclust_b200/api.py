@@ -19,7 +19,7 @@ SYMBOLS = [
     "mc_get_posterior", "mc_partition", "mc_delta", "mc_step_dots",
     "mc_qn_dots", "mc_accel_update", "mc_qn_update", "mc_project",
     "mc_copy_slot", "mc_em_step_local", "mc_exchange_buffer",
-    "mc_em_step_finish", "mc_get_plan", "mc_launch_count",
+    "mc_em_step_finish", "mc_exchange_sum", "mc_get_plan", "mc_launch_count",
     "mc_profile_enable", "mc_profile_read",
 ]
 
@@ -101,6 +101,7 @@ def load_library():
     L.mc_em_step_local.argtypes = [vp, C.c_int, C.c_int]
     L.mc_exchange_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mc_em_step_finish.argtypes = [vp, C.c_int, dp]
+    L.mc_exchange_sum.argtypes = [vp, vp, C.c_int]
     L.mc_get_plan.argtypes = [vp, C.POINTER(PlanInfo)]
     L.mc_launch_count.restype = C.c_int64
     L.mc_launch_count.argtypes = [vp]
@@ -220,6 +221,10 @@ class Context:
         self._ck(self.lib.mc_em_step_finish(self.h, to, C.byref(ll) if want_ll else None),
                  "mc_em_step_finish")
         return ll.value
+
+    def exchange_sum(self, gathered_ptr, n_ranks):
+        self._ck(self.lib.mc_exchange_sum(self.h, C.c_void_p(gathered_ptr), n_ranks),
+                 "mc_exchange_sum")
 
     def loglik(self, slot=0):
         ll = C.c_double()

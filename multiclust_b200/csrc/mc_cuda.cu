@@ -771,6 +771,18 @@ extern "C" int mc_exchange_buffer(mc_ctx *c, void **dev_ptr, size_t *n)
 	return MC_OK;
 }
 
+extern "C" int mc_exchange_sum(mc_ctx *c, const void *gathered, int n_ranks)
+{
+	NEED_MODEL();
+	if (!gathered || n_ranks < 1)
+		return fail(c, MC_ERR_ARG, "mc_exchange_sum: bad arguments");
+	const long long n = c->np + 1 + c->K;
+	k_sum_chunks<<<grid_for(c, n, 256), 256, 0, c->stream>>>(
+		(const double *)gathered, n_ranks, n, 0.0, c->d_xbuf);
+	LAUNCH_CHECK("k_sum_chunks");
+	return MC_OK;
+}
+
 extern "C" int mc_em_step_finish(mc_ctx *c, int to, double *ll)
 {
 	NEED_MODEL();

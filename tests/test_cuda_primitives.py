@@ -1,0 +1,242 @@
+"""GPU parity of every C-ABI entry point against the CPU oracle on the same
+seeded inputs (sizes the oracle finishes in well under a second).
+
+Tolerances are the north star's: log likelihood within 1e-9 relative,
+parameters / posterior sums within 1e-7 absolute.  Single calls are expected
+to agree far more tightly; the tight bounds asserted here (1e-12 / 1e-11)
+document how much slack the multi-iteration tests have."""
+import numpy as np
+import pytest
+
+from common import gen_data, random_params
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-9
+PAR_ATOL = 1e-7
+TIGHT = 1e-11
+
+SHAPES = [
+    # I, L, K, jmax, miss_bp, P
+    (60, 40, 3, 5, 300, 2),
+    (37, 133, 10, 20, 500, 2),     # config-3 shaped: K=10, <=20 alleles, 5 % missing
+    (45, 70, 8, 2, 0, 4),          # config-5 shaped: biallelic tetraploid
+    (33, 50, 5, 2, 200, 2),
+    (9, 7, 2, 3, 1000, 1),         # haploid, fewer individuals than a block
+    (20, 300, 17, 6, 100, 3),      # K > one lane's share, odd ploidy
+    (130, 20, 40, 4, 0, 2),        # large K (k_split > 1 with padding)
+]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from multiclust_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def setup_pair(orc, ctx, tmp_path, shape, admixture, eta_constrained=0, q=0,
+               accel=0, proj=1):
+    I, L, K, jmax, miss, P = shape
+    d = gen_data(tmp_path, I, L, K=min(K, 6), jmax=jmax, miss=miss, P=P)
+    fit = orc.Fit(d["J"], d["codes"], admixture=admixture,
+                  eta_constrained=eta_constrained, accel=accel, do_projection=proj)
+    fit.alloc(K)
+    ctx.set_data(d["J"], d["codes"])
+    lb = fit.lower_bound
+    ctx.alloc_model(K, admixture=admixture, eta_constrained=eta_constrained,
+                    q=q, eta_lb=lb, p_lb=lb, do_projection=proj)
+    rng = np.random.default_rng(1234 + I + L)
+    per_indiv = bool(admixture and not eta_constrained)
+    eta, p = random_params(rng, I, K, d["J"], per_indiv)
+    fit.set_params(0, eta, p)
+    ctx.set_params(0, eta, p)
+    return d, fit, eta, p
+
+
+def check_step(orc, ctx, fit, frm, to):
+    fit.set_indices(0, frm, to)
+    ll_o = fit.e_step()
+    fit.m_step()
+    ll_g = ctx.em_step(frm, to)
+    assert abs(ll_g - ll_o) <= LL_RTOL * abs(ll_o)
+    assert abs(ll_g - ll_o) <= 1e-12 * abs(ll_o) + 1e-12
+    eo, po = fit.get_params(to)
+    eg, pg = ctx.get_params(to)
+    assert np.max(np.abs(eg - eo)) < TIGHT
+    assert np.max(np.abs(pg - po)) < TIGHT
+    assert np.max(np.abs(ctx.posterior() - fit.posterior())) < 1e-9
+    return ll_o
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_admixture_em_step_and_loglik(orc, ctx, tmp_path, shape):
+    d, fit, eta, p = setup_pair(orc, ctx, tmp_path, shape, admixture=1)
+    ll_o = fit.log_likelihood(0)
+    ll_g = ctx.loglik(0)
+    assert abs(ll_g - ll_o) <= 1e-12 * abs(ll_o)
+    check_step(orc, ctx, fit, 0, 1)       # out of place
+    check_step(orc, ctx, fit, 1, 1)       # in place, like unaccelerated EM
+    check_step(orc, ctx, fit, 1, 2)
+    # the log likelihood of the new slot, and the posterior untouched by it
+    post = ctx.posterior()
+    assert abs(ctx.loglik(2) - fit.log_likelihood(2)) <= 1e-12 * abs(ll_o)
+    assert np.array_equal(post, ctx.posterior())
+
+
+@pytest.mark.parametrize("shape", SHAPES[:4])
+def test_admixture_pooled_eta(orc, ctx, tmp_path, shape):
+    d, fit, eta, p = setup_pair(orc, ctx, tmp_path, shape, admixture=1, eta_constrained=1)
+    check_step(orc, ctx, fit, 0, 0)
+    check_step(orc, ctx, fit, 0, 1)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_mixture_em_step_and_loglik(orc, ctx, tmp_path, shape):
+    d, fit, eta, p = setup_pair(orc, ctx, tmp_path, shape, admixture=0)
+    ll_o = fit.log_likelihood(0)
+    assert abs(ctx.loglik(0) - ll_o) <= 1e-12 * abs(ll_o)
+    check_step(orc, ctx, fit, 0, 1)
+    check_step(orc, ctx, fit, 1, 1)
+    ik, cnt = ctx.partition()
+    assert np.array_equal(ik, np.argmax(fit.posterior(), axis=1))
+    assert cnt.sum() == d["I"]
+
+
+def test_no_projection(orc, ctx, tmp_path):
+    d, fit, eta, p = setup_pair(orc, ctx, tmp_path, SHAPES[0], admixture=1, proj=0)
+    check_step(orc, ctx, fit, 0, 0)
+
+
+def test_projection_kernel(orc, ctx, tmp_path):
+    """simplex_project_eta / simplex_project_pklm on rows that need clamping"""
+    d, fit, eta, p = setup_pair(orc, ctx, tmp_path, SHAPES[0], admixture=1)
+    rng = np.random.default_rng(7)
+    K, I, J = 3, d["I"], d["J"]
+    eta2 = eta + rng.normal(0, 0.4, eta.size)
+    p2 = p + rng.normal(0, 0.4, p.size)
+    ctx.set_params(1, eta2, p2)
+    ctx.project(1)
+    eg, pg = ctx.get_params(1)
+    lb = fit.lower_bound
+    eo = np.concatenate([orc.project(eta2[i * K:(i + 1) * K], lb) for i in range(I)])
+    T = int(J.sum())
+    off = np.concatenate([[0], np.cumsum(J)])
+    po = p2.copy()
+    for k in range(K):
+        for l in range(len(J)):
+            a, b = k * T + off[l], k * T + off[l + 1]
+            po[a:b] = orc.project(p2[a:b], lb)
+    assert np.array_equal(eg, eo)       # same operations in the same order
+    assert np.array_equal(pg, po)
+
+
+def test_secant_pairs_and_updates(orc, ctx, tmp_path):
+    """mc_delta, mc_step_dots, mc_qn_dots, mc_accel_update, mc_qn_update"""
+    shape = SHAPES[1]
+    I, L, K = shape[0], shape[1], shape[2]
+    d, fit, eta, p = setup_pair(orc, ctx, tmp_path, shape, admixture=1, q=2, accel=5)
+    rng = np.random.default_rng(99)
+    T = fit.T
+    xs = []
+    for s in range(3):
+        e, pp = random_params(rng, I, K, d["J"], True)
+        ctx.set_params(s, e, pp)
+        xs.append((e, pp))
+    ctx.delta(0, 0, 1, 0)   # u0 = x1 - x0
+    ctx.delta(1, 0, 2, 1)   # v0 = x2 - x1
+    ctx.delta(0, 1, 2, 0)   # u1 = x2 - x0
+    ctx.delta(1, 1, 0, 1)   # v1 = x0 - x1
+    ue0, up0 = xs[1][0] - xs[0][0], xs[1][1] - xs[0][1]
+    ve0, vp0 = xs[2][0] - xs[1][0], xs[2][1] - xs[1][1]
+    ue1, up1 = xs[2][0] - xs[0][0], xs[2][1] - xs[0][1]
+    ve1, vp1 = xs[0][0] - xs[1][0], xs[0][1] - xs[1][1]
+    e3, p3 = ctx.step_dots(0)
+    ref_e = [ue0 @ ue0, ue0 @ (ve0 - ue0), (ve0 - ue0) @ (ve0 - ue0)]
+    ref_p = [up0 @ up0, up0 @ (vp0 - up0), (vp0 - up0) @ (vp0 - up0)]
+    assert np.allclose(e3, ref_e, rtol=1e-12, atol=0)
+    assert np.allclose(p3, ref_p, rtol=1e-12, atol=0)
+    e2, p2 = ctx.qn_dots(0, 1)
+    assert np.allclose(e2, [ue0 @ ue1, ue0 @ ve1], rtol=1e-11, atol=1e-14)
+    assert np.allclose(p2, [up0 @ up1, up0 @ vp1], rtol=1e-11, atol=1e-14)
+    # SQUAREM and QN1 extrapolations (projection applied afterwards)
+    lb = fit.lower_bound
+    off = np.concatenate([[0], np.cumsum(d["J"])])
+
+    def project_all(e, pp):
+        e = np.concatenate([orc.project(e[i * K:(i + 1) * K], lb) for i in range(I)])
+        pp = pp.copy()
+        for k in range(K):
+            for l in range(L):
+                a, b = k * T + off[l], k * T + off[l + 1]
+                pp[a:b] = orc.project(pp[a:b], lb)
+        return e, pp
+
+    s = -1.7
+    for qn1 in (0, 1):
+        ctx.accel_update(qn1, 2, 0, 0, s)
+        eg, pg = ctx.get_params(2)
+        if qn1:
+            er = xs[0][0] + ue0 + s * ve0
+            pr = xs[0][1] + up0 + s * vp0
+        else:
+            er = xs[0][0] - 2 * s * ue0 + s * s * (ve0 - ue0)
+            pr = xs[0][1] - 2 * s * up0 + s * s * (vp0 - up0)
+        er, pr = project_all(er, pr)
+        assert np.array_equal(eg, er)
+        assert np.array_equal(pg, pr)
+    # QN q=2 update: x[p] + u[uindex] + sum_jn v[(delta+j)%q] * Ainv[j][n] * cutu[n]
+    Ainv = np.array([[0.3, -0.2], [0.15, 0.4]])
+    cutu = np.array([0.7, -0.1])
+    ctx.set_params(2, xs[2][0], xs[2][1])
+    ctx.qn_update(1, 0, 1, 1, Ainv, cutu)
+    eg, pg = ctx.get_params(1)
+    er, pr = xs[0][0] + ue1, xs[0][1] + up1
+    vs_e, vs_p = [ve1, ve0], [vp1, vp0]       # rows start at delta_index = 1
+    for j in range(2):
+        for n in range(2):
+            er = er + vs_e[j] * Ainv[j, n] * cutu[n]
+            pr = pr + vs_p[j] * Ainv[j, n] * cutu[n]
+    er, pr = project_all(er, pr)
+    assert np.array_equal(eg, er)
+    assert np.array_equal(pg, pr)
+
+
+def test_determinism(orc, ctx, tmp_path):
+    """bitwise repeatable: fixed reduction order, no float atomics"""
+    d, fit, eta, p = setup_pair(orc, ctx, tmp_path, SHAPES[1], admixture=1)
+    out = []
+    for rep in range(3):
+        ctx.set_params(0, eta, p)
+        lls = [ctx.em_step(0, 0) for _ in range(4)]
+        e, pp = ctx.get_params(0)
+        out.append((lls, e.copy(), pp.copy()))
+    for rep in (1, 2):
+        assert out[rep][0] == out[0][0]
+        assert np.array_equal(out[rep][1], out[0][1])
+        assert np.array_equal(out[rep][2], out[0][2])
+
+
+def test_split_step_equals_whole_step(orc, ctx, tmp_path):
+    """mc_em_step == mc_em_step_local + (exchange) + mc_em_step_finish"""
+    d, fit, eta, p = setup_pair(orc, ctx, tmp_path, SHAPES[0], admixture=1)
+    ll1 = ctx.em_step(0, 1)
+    e1, p1 = ctx.get_params(1)
+    ctx.em_step_local(0, 2)
+    ptr, n = ctx.exchange_buffer()
+    assert n == 3 * fit.T + 1 + 3
+    ll2 = ctx.em_step_finish(2)
+    e2, p2 = ctx.get_params(2)
+    assert ll1 == ll2 and np.array_equal(e1, e2) and np.array_equal(p1, p2)
+
+
+def test_synthetic_generator_matches_host(orc, ctx, tmp_path):
+    """mc_set_data_synth (device fill) == mc_gen (host C) byte for byte"""
+    from multiclust_b200 import SynthParams
+    I, L = 70, 90
+    d = gen_data(tmp_path, I, L, K=4, jmax=7, miss=400, P=2)
+    sp = SynthParams(seed=20261018, K=4, jmax=7, miss_bp=400, ploidy=2)
+    ctx.set_data_synth(I, L, sp)
+    assert np.array_equal(ctx.get_J(), d["J"])
+    assert np.array_equal(ctx.get_codes(), d["codes"])
