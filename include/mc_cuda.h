@@ -89,6 +89,15 @@ int mc_eta_len(const mc_ctx *ctx, int64_t *n);
 int mc_set_params(mc_ctx *ctx, int slot, const double *eta, const double *p);
 int mc_get_params(mc_ctx *ctx, int slot, double *eta, double *p);
 
+/* random_initialize_admixture (rnd_init.c:349-357, 456-482): `z` is a HOST
+ * array [I][L][P] holding the cluster drawn for every allele copy (missing
+ * copies included, the reference draws for them too) in the reference's
+ * i, l, a order -- the host owns the rand() stream.  The device forms the hard
+ * assignment d_iklj = 1 for every (k, allele) pair that occurs in individual i
+ * at locus l (set, not incremented: two copies of one allele drawn to the same
+ * k count once) and runs the M-step (with projections) into `slot`. */
+int mc_init_admixture(mc_ctx *ctx, int slot, const uint8_t *z);
+
 /* ---- the hot path ------------------------------------------------------ */
 
 /* E-step on slot `from`, M-step (+ simplex projection) into slot `to`;

@@ -15,7 +15,7 @@ SYMBOLS = [
     "mc_last_error", "mc_abi_version", "mc_create", "mc_destroy",
     "mc_set_stream", "mc_sync", "mc_set_data", "mc_set_data_synth",
     "mc_get_dims", "mc_get_J", "mc_get_codes", "mc_alloc_model", "mc_eta_len",
-    "mc_set_params", "mc_get_params", "mc_em_step", "mc_loglik",
+    "mc_set_params", "mc_get_params", "mc_init_admixture", "mc_em_step", "mc_loglik",
     "mc_get_posterior", "mc_partition", "mc_delta", "mc_step_dots",
     "mc_qn_dots", "mc_accel_update", "mc_qn_update", "mc_project",
     "mc_copy_slot", "mc_em_step_local", "mc_exchange_buffer",
@@ -86,6 +86,7 @@ def load_library():
     L.mc_eta_len.argtypes = [vp, C.POINTER(C.c_int64)]
     L.mc_set_params.argtypes = [vp, C.c_int, vp, vp]
     L.mc_get_params.argtypes = [vp, C.c_int, vp, vp]
+    L.mc_init_admixture.argtypes = [vp, C.c_int, vp]
     L.mc_em_step.argtypes = [vp, C.c_int, C.c_int, dp]
     L.mc_loglik.argtypes = [vp, C.c_int, dp]
     L.mc_get_posterior.argtypes = [vp, vp]
@@ -201,6 +202,11 @@ class Context:
         p = np.empty(self.K * self.T)
         self._ck(self.lib.mc_get_params(self.h, slot, _ptr(eta), _ptr(p)), "mc_get_params")
         return eta, p
+
+    def init_admixture(self, slot, z):
+        z = np.ascontiguousarray(z, dtype=np.uint8)
+        assert z.size == self.I * self.L * self.P
+        self._ck(self.lib.mc_init_admixture(self.h, slot, _ptr(z)), "mc_init_admixture")
 
     # -- hot path
     def em_step(self, frm=0, to=0):

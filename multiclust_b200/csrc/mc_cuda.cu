@@ -360,8 +360,9 @@ struct HostPlan {
 
 static size_t smem_need(int max_rows, int KH, int W, int ks, int IB, int nbuf)
 {
-	size_t rows = (size_t)max_rows * KH * 32 * sizeof(double) * nbuf;
-	size_t scr = (size_t)2 * W * ks * IB * KH * sizeof(double);
+	/* + 1: the all-zero row that missing copies read */
+	size_t rows = (size_t)(max_rows + 1) * KH * 32 * sizeof(double) * nbuf;
+	size_t scr = (size_t)2 * MC_NB * W * ks * IB * KH * sizeof(double);
 	return rows + scr + (size_t)W * sizeof(double) + 64;
 }
 
@@ -420,8 +421,13 @@ static int upload(mc_ctx *c, T *&dst, const std::vector<T> &src)
 static int make_plan(mc_ctx *c)
 {
 	const int K = c->K;
-	int ks = 1;
-	while ((K + ks - 1) / ks > KH_MAX && ks < 32)
+	int ks = 1, kh_max = KH_MAX;
+	if (const char *ev = getenv("MC_KH_MAX")) {	/* tuning knob */
+		const int v = atoi(ev);
+		if (v >= 1 && v <= KH_MAX)
+			kh_max = v;
+	}
+	while ((K + ks - 1) / ks > kh_max && ks < 32)
 		ks <<= 1;
 	const int KH = (K + ks - 1) / ks;
 	if (KH > KH_MAX)
@@ -809,6 +815,44 @@ extern "C" int mc_em_step_finish(mc_ctx *c, int to, double *ll)
 		CK(cudaStreamSynchronize(c->stream));
 	}
 	return MC_OK;
+}
+
+/* admixture initialiser: hard assignment + M-step (rnd_init.c:349-357) */
+extern "C" int mc_init_admixture(mc_ctx *c, int slot, const uint8_t *z)
+{
+	NEED_MODEL();
+	CHECK_SLOT(slot);
+	if (!z)
+		return fail(c, MC_ERR_ARG, "mc_init_admixture: null assignment");
+	if (!c->admixture)
+		return fail(c, MC_ERR_STATE, "mc_init_admixture: not an admixture model");
+	if (c->K > 255)
+		return fail(c, MC_ERR_UNSUPPORTED, "mc_init_admixture: K > 255");
+	const size_t n = (size_t)c->I * c->L * c->P;
+	unsigned char *d_z = nullptr;
+	unsigned *d_N = nullptr;
+	CK(cudaMalloc(&d_z, n));
+	CK(cudaMalloc(&d_N, sizeof(unsigned) * (size_t)std::max<int64_t>(c->np, 1)));
+	CK(cudaMemcpyAsync(d_z, z, n, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemsetAsync(d_N, 0, sizeof(unsigned) * (size_t)std::max<int64_t>(c->np, 1), c->stream));
+	k_init_counts<<<grid_for(c, c->I, 128), 128, 0, c->stream>>>(c->d_nat, d_z,
+		c->I, c->L, c->P, c->K, c->d_off, c->T, c->d_post, d_N);
+	LAUNCH_CHECK("k_init_counts");
+	k_u32_to_f64<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(d_N, xb_N(c), c->np);
+	LAUNCH_CHECK("k_u32_to_f64");
+	int rc;
+	if (c->per_indiv) {
+		k_eta_from_D<<<grid_for(c, c->I, 128), 128, 0, c->stream>>>(c->d_post,
+			c->d_eta[slot], c->I, c->K, c->do_proj, c->eta_lb);
+		LAUNCH_CHECK("k_eta_from_D");
+	} else {
+		if ((rc = reduce_columns(c, c->d_post, c->I, c->K, xb_S(c)))) return rc;
+	}
+	rc = mc_em_step_finish(c, slot, nullptr);
+	CK(cudaStreamSynchronize(c->stream));
+	cudaFree(d_z);
+	cudaFree(d_N);
+	return rc;
 }
 
 extern "C" int mc_em_step(mc_ctx *c, int from, int to, double *ll)

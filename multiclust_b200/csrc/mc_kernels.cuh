@@ -132,35 +132,54 @@ __device__ __forceinline__ void lane_reduce_scatter(double *a, int k_split,
 	if (k_split <= 1) rs_step<N4>(a, 1, lane, lo, hi);
 }
 
-template <int PP> struct UnitT;
-template <> struct UnitT<1> { typedef uint2 type; };	/* 8 individuals x 1 */
-template <> struct UnitT<2> { typedef uint4 type; };	/* 8 x 2 */
-template <> struct UnitT<4> { typedef uint4 type; };	/* 4 x 4 */
-template <> struct UnitT<8> { typedef uint4 type; };	/* 2 x 8 */
-template <> struct UnitT<16> { typedef uint4 type; };	/* 1 x 16 */
-
-__device__ __forceinline__ unsigned unit_byte(const uint4 &u, int b)
+/* byte e (0..7) of an 8-byte group of allele codes */
+__device__ __forceinline__ unsigned group_byte(const uint2 &u, int e)
 {
-	unsigned w = b < 8 ? (b < 4 ? u.x : u.y) : (b < 12 ? u.z : u.w);
-	return (w >> ((b & 3) * 8)) & 0xffu;
-}
-__device__ __forceinline__ unsigned unit_byte(const uint2 &u, int b)
-{
-	unsigned w = b < 4 ? u.x : u.y;
-	return (w >> ((b & 3) * 8)) & 0xffu;
+	return ((e < 4 ? u.x : u.y) >> ((e & 3) * 8)) & 0xffu;
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *ptr)
+{
+	asm volatile("prefetch.global.L1 [%0];" :: "l"(ptr));
+}
+
+/* A-blocks (groups of individuals whose sums are folded together) reduced
+ * across warps per barrier */
+#define MC_NB 4
+
+/*
+ * Work inside a thread is organised in GROUPS of 8 allele copies of one locus
+ * (4 diploid individuals, 2 tetraploids, ...).  Each group runs in phases of
+ * straight-line code so that independent work is in flight together -- with
+ * one CTA of a few warps per SM (shared memory holds the tile),
+ * instruction-level parallelism is what hides the shared-memory and FP64
+ * latencies:
+ *   1. the 8 p rows are read from shared memory;
+ *   2. the 8 sums tmp = sum_k eta_ik p_klj, folded over the k_split lanes;
+ *   3. w = c / tmp and the log-likelihood term for the 8 copies;
+ *   4. A_ik += p_klj w (registers);
+ *   5. B_klj += eta_ik w, a read-modify-write of this thread's private
+ *      shared-memory column, in copy order (two copies may share an allele).
+ * The allele codes of the next group are loaded, and the eta rows of the next
+ * individuals prefetched into L1, while the current group is computed.
+ */
 template <int KH, int PP, int MODE>
 __global__ void __launch_bounds__(256, 1) tile_kernel(const TileArgs a)
 {
 	constexpr int IB = (PP >= 2) ? 16 / PP : 8;	/* individuals per unit */
-	constexpr int UB = IB * PP;			/* bytes per unit */
-	constexpr int V = IB * KH;			/* A values per lane */
+	constexpr int UB = IB * PP;			/* bytes per unit: 8 or 16 */
+	constexpr int NH = UB / 8;			/* groups of 8 copies per unit */
+	constexpr int NI = (PP >= 8) ? 1 : 8 / PP;	/* individuals per group */
+	constexpr int EPI = 8 / NI;			/* copies per individual in a group */
+	constexpr int V = NI * KH;			/* A values per lane */
+	constexpr bool SPAN = (PP > 8);			/* one individual spans both groups */
+	constexpr int ABU = SPAN ? 1 : NH;		/* A-blocks per unit */
+	constexpr int HPA = SPAN ? NH : 1;		/* groups per A-block */
 	constexpr bool HAS_A = (MODE == MODE_ADMIX_EM || MODE == MODE_MIX_E);
 	constexpr bool HAS_B = (MODE == MODE_ADMIX_EM || MODE == MODE_MIX_M);
 	constexpr bool HAS_P = (MODE != MODE_MIX_M);
+	constexpr bool HAS_E = (MODE != MODE_MIX_E);
 	constexpr bool HAS_LL = (MODE == MODE_ADMIX_EM || MODE == MODE_ADMIX_LL);
-	typedef typename UnitT<PP>::type unit_t;
 
 	extern __shared__ double smem[];
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -168,13 +187,21 @@ __global__ void __launch_bounds__(256, 1) tile_kernel(const TileArgs a)
 	const int ks = a.k_split;
 	const int kh = lane % ks, lw = lane / ks;
 	const int k0 = kh * KH;
-	const int RS = KH * 32;		/* doubles per smem row */
+	constexpr int RS = KH * 32;		/* doubles per smem row */
+	/* one extra all-zero row (index max_rows) serves the missing copies */
+	const int zrow = a.max_rows;
 	double *p_s = smem;
-	double *B_s = p_s + (HAS_P ? (size_t)a.max_rows * RS : 0);
-	double *scr = B_s + (HAS_B ? (size_t)a.max_rows * RS : 0);
-	/* scratch: [2][W][ks][V] then W doubles for the ll reduction */
-	double *llred = scr + (HAS_A ? 2 * W * ks * V : 0);
-	int buf = 0;
+	double *B_s = p_s + (HAS_P ? (size_t)(a.max_rows + 1) * RS : 0);
+	double *scr = B_s + (HAS_B ? (size_t)(a.max_rows + 1) * RS : 0);
+	/* scratch: [2][MC_NB][W][ks][V] then W doubles for the ll reduction */
+	double *llred = scr + (HAS_A ? 2 * MC_NB * W * ks * V : 0);
+	int set = 0;
+	/* clamped cluster index: lanes past K read a valid eta entry and meet
+	 * p = 0 in their (never flushed) columns */
+	int kofs[KH];
+#pragma unroll
+	for (int kk = 0; kk < KH; kk++)
+		kofs[kk] = min(k0 + kk, a.K - 1);
 
 	for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
 		const int t = u % a.n_tiles, c = u / a.n_tiles;
@@ -195,7 +222,7 @@ __global__ void __launch_bounds__(256, 1) tile_kernel(const TileArgs a)
 			for (int j = 0; j < nr; j++)
 #pragma unroll
 				for (int kk = 0; kk < KH; kk++) {
-					const size_t x = ((size_t)(rb + j) * KH + kk) * 32 + lane;
+					const int x = ((rb + j) * KH + kk) * 32 + lane;
 					if (HAS_P) {
 						double v = 0.0;
 						if (loc >= 0 && j < Jl && k0 + kk < a.K)
@@ -206,112 +233,214 @@ __global__ void __launch_bounds__(256, 1) tile_kernel(const TileArgs a)
 						B_s[x] = 0.0;
 				}
 		}
+#pragma unroll
+		for (int kk = 0; kk < KH; kk++) {
+			const int x = (zrow * KH + kk) * 32 + lane;
+			if (HAS_P)
+				p_s[x] = 0.0;
+			if (HAS_B)
+				B_s[x] = 0.0;
+		}
 		/* columns are thread private: no barrier needed before use */
 
 		double prod = 1.0, ll_slow = 0.0;
 		long long esum = 0;
 		const unsigned char *tile_codes = a.codes + (size_t)t * a.tile_stride;
+		const long long nab = (b1 - b0) * ABU;
+		/* position (A-block, group in block, locus group) of the 8-byte
+		 * code group that is loaded one step ahead */
+		long long pab = 0;
+		int phh = 0, pg = 0;
+		auto code_ptr = [&]() {
+			const long long b = b0 + pab / ABU;
+			const int h = (int)(pab % ABU) + phh;
+			const int s = (pg * W + w) * LW + lw;
+			return reinterpret_cast<const uint2 *>(tile_codes
+				+ ((size_t)b * a.tile_slots + s) * UB + h * 8);
+		};
+		uint2 cw_next = make_uint2(0xffffffffu, 0xffffffffu);
+		if (nab > 0)
+			cw_next = __ldg(code_ptr());
 
-		for (long long b = b0; b < b1; b++) {
+		for (long long ab = 0; ab < nab; ab++) {
+			const long long b = b0 + ab / ABU;
+			const int h0 = (int)(ab % ABU);
+			const long long i0 = b * IB + (h0 * 8) / PP;
+			const int slot = (int)(ab % MC_NB);
 			double A[HAS_A ? V : 1];
 			if (HAS_A) {
 #pragma unroll
 				for (int v = 0; v < V; v++)
 					A[v] = 0.0;
 			}
+			double e[HAS_E ? V : 1];
+			if (HAS_E) {
+#pragma unroll
+				for (int n = 0; n < NI; n++) {
+					const long long i = min(i0 + n, a.I - 1);
+					const double *er = a.eta + (size_t)i * a.eta_stride;
+#pragma unroll
+					for (int kk = 0; kk < KH; kk++)
+						e[n * KH + kk] = __ldg(er + kofs[kk]);
+				}
+				/* next A-block's rows -> L1 */
+				if (lane < NI && a.eta_stride) {
+					const long long in = min(i0 + (SPAN ? 1 : NI) + lane, a.I - 1);
+					prefetch_l1(a.eta + (size_t)in * a.eta_stride + k0);
+				}
+			}
+#pragma unroll
+			for (int hh = 0; hh < HPA; hh++)
 			for (int g = 0; g < NG; g++) {
-				const int s = (g * W + w) * LW + lw;
 				const int rb = g_rowbase[g * W + w];
-				const unit_t cu = *reinterpret_cast<const unit_t *>(
-					tile_codes + ((size_t)b * a.tile_slots + s) * UB);
-#pragma unroll
-				for (int ii = 0; ii < IB; ii++) {
-					double e[KH];
-					if (MODE != MODE_MIX_E) {
-						const long long i = b * IB + ii;
-						const double *er = a.eta + (size_t)(i < a.I ? i : 0) * a.eta_stride + k0;
-#pragma unroll
-						for (int kk = 0; kk < KH; kk++)
-							e[kk] = (k0 + kk < a.K && i < a.I) ? er[kk] : 0.0;
-					}
-#pragma unroll
-					for (int ap = 0; ap < PP; ap++) {
-						const unsigned code = unit_byte(cu, ii * PP + ap);
-						const bool valid = code != MC_MISSING;
-						const size_t x0 = ((size_t)(rb + (valid ? code : 0u)) * KH) * 32 + lane;
-						double pr[KH];
-						if (HAS_P) {
-#pragma unroll
-							for (int kk = 0; kk < KH; kk++)
-								pr[kk] = p_s[x0 + kk * 32];
-						}
-						if (MODE == MODE_MIX_E) {
-#pragma unroll
-							for (int kk = 0; kk < KH; kk++)
-								A[ii * KH + kk] += valid ? pr[kk] : 0.0;
-						} else if (MODE == MODE_MIX_M) {
-#pragma unroll
-							for (int kk = 0; kk < KH; kk++)
-								B_s[x0 + kk * 32] += valid ? e[kk] : 0.0;
-						} else {
-							double tmp = 0.0;
-#pragma unroll
-							for (int kk = 0; kk < KH; kk++)
-								tmp = fma(e[kk], pr[kk], tmp);
-							for (int m = 1; m < ks; m <<= 1)
-								tmp += shfl_xor_f64(tmp, m);
-							tmp = valid ? tmp : 1.0;
-							/* log(tmp) = exponent*ln2 + log(mantissa): the
-							 * mantissas are multiplied up and logged once */
-							const int hi = __double2hiint(tmp);
-							const int ex = (hi >> 20) & 0x7ff;
-							if (hi < 0 || ex == 0 || ex == 0x7ff) {
-								ll_slow += log(tmp);
-							} else {
-								esum += ex - 1023;
-								prod *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000,
-									__double2loint(tmp));
-							}
-							if (MODE == MODE_ADMIX_EM) {
-								const double wgt = valid ? mc_rcp(tmp) : 0.0;
-#pragma unroll
-								for (int kk = 0; kk < KH; kk++) {
-									A[ii * KH + kk] = fma(pr[kk], wgt, A[ii * KH + kk]);
-									B_s[x0 + kk * 32] = fma(e[kk], wgt, B_s[x0 + kk * 32]);
-								}
-							}
-						}
+				const uint2 cw = cw_next;
+				if (++pg == NG) {
+					pg = 0;
+					if (++phh == HPA) {
+						phh = 0;
+						++pab;
 					}
 				}
-				if (HAS_LL) {
-					/* prod < 2^(IB*PP): fold its exponent away */
-					const int hi = __double2hiint(prod);
-					esum += ((hi >> 20) & 0x7ff) - 1023;
-					prod = __hiloint2double((hi & 0x000fffff) | 0x3ff00000,
-						__double2loint(prod));
+				if (pab < nab)
+					cw_next = __ldg(code_ptr());
+				int x0[8];
+				bool valid[8];
+#pragma unroll
+				for (int q = 0; q < 8; q++) {
+					const unsigned code = group_byte(cw, q);
+					valid[q] = code != MC_MISSING;
+					x0[q] = (valid[q] ? rb + (int)code : zrow) * RS + lane;
+				}
+				/* phase 1: p rows */
+				double pr[HAS_P ? 8 * KH : 1];
+				if (HAS_P) {
+#pragma unroll
+					for (int q = 0; q < 8; q++)
+#pragma unroll
+						for (int kk = 0; kk < KH; kk++)
+							pr[q * KH + kk] = p_s[x0[q] + kk * 32];
+				}
+				if (MODE == MODE_MIX_E) {
+#pragma unroll
+					for (int q = 0; q < 8; q++)
+#pragma unroll
+						for (int kk = 0; kk < KH; kk++)
+							A[(q / EPI) * KH + kk] += pr[q * KH + kk];
+					continue;
+				}
+				double wgt[8];
+				if (MODE == MODE_MIX_M) {
+#pragma unroll
+					for (int q = 0; q < 8; q++)
+						wgt[q] = valid[q] ? 1.0 : 0.0;
+				} else {
+					/* phase 2: tmp */
+					double tmp[8];
+#pragma unroll
+					for (int q = 0; q < 8; q++) {
+						double v = 0.0;
+#pragma unroll
+						for (int kk = 0; kk < KH; kk++)
+							v = fma(e[(q / EPI) * KH + kk], pr[q * KH + kk], v);
+						tmp[q] = v;
+					}
+#pragma unroll
+					for (int m = 1; m < 32; m <<= 1)
+						if (m < ks) {
+#pragma unroll
+							for (int q = 0; q < 8; q++)
+								tmp[q] += shfl_xor_f64(tmp[q], m);
+						}
+					/* phase 3: weights and log-likelihood terms.
+					 * log(tmp) = exponent*ln2 + log(mantissa): the
+					 * mantissas are multiplied up and logged once;
+					 * zero / subnormal / non-finite sums (never
+					 * seen in a healthy fit) take the slow path
+					 * after the straight-line code */
+					unsigned bad = 0;
+#pragma unroll
+					for (int q = 0; q < 8; q++) {
+						tmp[q] = valid[q] ? tmp[q] : 1.0;
+						/* positive and normal <=> high word in
+						 * [0x00100000, 0x7ff00000) */
+						bad |= (unsigned)(__double2hiint(tmp[q]) - 0x00100000)
+							>= 0x7fe00000u;
+						if (MODE == MODE_ADMIX_EM)
+							wgt[q] = valid[q] ? mc_rcp(tmp[q]) : 0.0;
+					}
+					if (!bad) {
+						int es = 0;
+#pragma unroll
+						for (int q = 0; q < 8; q++) {
+							const int hi = __double2hiint(tmp[q]);
+							es += hi >> 20;
+							prod *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000,
+								__double2loint(tmp[q]));
+						}
+						/* prod < 2^8: fold its exponent away */
+						const int hi = __double2hiint(prod);
+						es += (hi >> 20) - 9 * 1023;
+						prod = __hiloint2double((hi & 0x000fffff) | 0x3ff00000,
+							__double2loint(prod));
+						esum += es;
+					} else {
+						for (int q = 0; q < 8; q++)
+							ll_slow += log(tmp[q]);
+					}
+				}
+				if (MODE == MODE_ADMIX_EM) {
+					/* phase 4: A */
+#pragma unroll
+					for (int q = 0; q < 8; q++)
+#pragma unroll
+						for (int kk = 0; kk < KH; kk++)
+							A[(q / EPI) * KH + kk] = fma(pr[q * KH + kk], wgt[q],
+								A[(q / EPI) * KH + kk]);
+				}
+				if (HAS_B) {
+					/* phase 5: B, copy by copy */
+#pragma unroll
+					for (int q = 0; q < 8; q++) {
+						double bv[KH];
+#pragma unroll
+						for (int kk = 0; kk < KH; kk++)
+							bv[kk] = B_s[x0[q] + kk * 32];
+#pragma unroll
+						for (int kk = 0; kk < KH; kk++)
+							B_s[x0[q] + kk * 32] = fma(e[(q / EPI) * KH + kk],
+								wgt[q], bv[kk]);
+					}
 				}
 			}
 			if (HAS_A) {
-				/* fold the block's sums over loci: lanes, then warps */
+				/* fold the A-block's sums over loci: lanes now, warps
+				 * once per MC_NB A-blocks */
 				int lo, hi;
 				lane_reduce_scatter<V>(A, ks, lane, lo, hi);
-				double *mine = scr + ((size_t)(buf * W + w) * ks + kh) * V;
+				double *mine = scr + ((((size_t)set * MC_NB + slot) * W + w) * ks + kh) * V;
 #pragma unroll
 				for (int v = 0; v < V; v++)
 					if (v < hi - lo)
 						mine[lo + v] = A[v];
-				__syncthreads();
-				for (int idx = threadIdx.x; idx < ks * V; idx += blockDim.x) {
-					const int rkh = idx / V, v = idx % V;
-					const int ii = v / KH, kk = v % KH;
-					const int k = rkh * KH + kk;
-					double sum = 0.0;
-					for (int ww = 0; ww < W; ww++)
-						sum += scr[((size_t)(buf * W + ww) * ks + rkh) * V + v];
-					if (k < a.K)
-						a.Apart[((size_t)t * a.Ipad + b * IB + ii) * a.K + k] = sum;
+				if (slot == MC_NB - 1 || ab == nab - 1) {
+					__syncthreads();
+					const int nslot = slot + 1;
+					for (int idx = threadIdx.x; idx < nslot * ks * V; idx += blockDim.x) {
+						const int sl = idx / (ks * V), r = idx % (ks * V);
+						const int rkh = r / V, v = r % V;
+						const int n = v / KH, kk = v % KH;
+						const int k = rkh * KH + kk;
+						const long long abs_ = ab - slot + sl;
+						const long long is = (b0 + abs_ / ABU) * IB
+							+ ((int)(abs_ % ABU) * 8) / PP + n;
+						double sum = 0.0;
+						for (int ww = 0; ww < W; ww++)
+							sum += scr[((((size_t)set * MC_NB + sl) * W + ww) * ks + rkh) * V + v];
+						if (k < a.K)
+							a.Apart[((size_t)t * a.Ipad + is) * a.K + k] = sum;
+					}
+					set ^= 1;
 				}
-				buf ^= 1;
 			}
 		}
 
@@ -328,7 +457,7 @@ __global__ void __launch_bounds__(256, 1) tile_kernel(const TileArgs a)
 #pragma unroll
 					for (int kk = 0; kk < KH; kk++)
 						if (k0 + kk < a.K) {
-							const size_t x = ((size_t)(rb + j) * KH + kk) * 32 + lane;
+							const int x = ((rb + j) * KH + kk) * 32 + lane;
 							/* d_iklj = eta p / tmp: the factor p_klj is
 							 * common to the whole column, applied once */
 							double v = B_s[x];
@@ -729,6 +858,59 @@ __global__ void k_partition(const double *post, long long I, int K, int *I_K)
 				best = k;
 			}
 		I_K[i] = best;
+	}
+}
+
+/* ------------------------------------------------------------------ */
+/* admixture initialiser (rnd_init.c:456-482): hard assignment counts     */
+
+__global__ void k_init_counts(const unsigned char *nat, const unsigned char *z,
+	long long I, int L, int P, int K, const int *off, long long T,
+	double *D /* [I][K] */, unsigned *N /* [K][T] */)
+{
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < I;
+		i += (long long)gridDim.x * blockDim.x) {
+		for (int k = 0; k < K; k++)
+			D[(size_t)i * K + k] = 0.0;
+		for (int l = 0; l < L; l++) {
+			const unsigned char *c = nat + ((size_t)i * L + l) * P;
+			const unsigned char *zz = z + ((size_t)i * L + l) * P;
+			for (int ap = 0; ap < P; ap++) {
+				if (c[ap] == MC_MISSING)
+					continue;
+				bool seen = false;
+				for (int b = 0; b < ap; b++)
+					seen |= (c[b] == c[ap] && zz[b] == zz[ap]);
+				if (seen)
+					continue;
+				D[(size_t)i * K + zz[ap]] += 1.0;
+				atomicAdd(&N[(size_t)zz[ap] * T + off[l] + c[ap]], 1u);
+			}
+		}
+	}
+}
+
+__global__ void k_u32_to_f64(const unsigned *x, double *y, long long n)
+{
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+		i += (long long)gridDim.x * blockDim.x)
+		y[i] = (double)x[i];
+}
+
+/* eta rows from D (em_alg.c:650-702) */
+__global__ void k_eta_from_D(const double *D, double *eta_t, long long I, int K,
+	int do_proj, double lb)
+{
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < I;
+		i += (long long)gridDim.x * blockDim.x) {
+		double s = 0.0;
+		for (int k = 0; k < K; k++)
+			s += D[(size_t)i * K + k];
+		double *row = eta_t + (size_t)i * K;
+		for (int k = 0; k < K; k++)
+			row[k] = D[(size_t)i * K + k] / s;
+		if (do_proj)
+			project_row(row, K, lb);
 	}
 }
 

@@ -1,0 +1,186 @@
+/*
+ * init_model.c -- random initialisation of the parameters (reference
+ * rnd_init.c:54-110, 192-357, 456-482).
+ *
+ * The reference draws from glibc rand() -- one shared stream over all
+ * initialisations and all K (multiclust.c:516-531, never reseeded unless -r) --
+ * and parity needs the same stream, so the draws are made here on the host in
+ * the reference's order.  What is done with them runs on the device:
+ *   admixture: one cluster per allele copy -> hard-assignment counts and the
+ *              M-step (mc_init_admixture);
+ *   mixture:   K random centre individuals, nearest-centre partition, smoothed
+ *              counts; the O(I*L) counting is done here on the 8-bit codes and
+ *              the resulting parameters are uploaded (mc_set_params).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "multiclust.h"
+
+#define GPU(call) gpu_check(mod, (call), #call)
+
+/* rnd_init.c:456-482: k = rand() % K for every copy, missing ones included */
+static int random_initialize_admixture(options *opt, data *dat, model *mod)
+{
+	const size_t n = (size_t)dat->I * dat->L * dat->ploidy;
+	uint8_t *z = malloc(n ? n : 1);
+
+	(void)opt;
+	if (!z)
+		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "allele partition\n");
+	for (size_t x = 0; x < n; x++)
+		z[x] = (uint8_t)((int)rand() % mod->K);
+	GPU(mc_init_admixture(mod->gpu, mod->tindex, z));
+	free(z);
+	return NO_ERROR;
+}
+
+/* L1 distance between the allele-count vectors of two individuals at all loci
+ * (rnd_init.c:238-247), computed from the codes: at one locus it is
+ * sum_j |n_a(j) - n_b(j)| over the alleles either of them carries */
+static double count_distance(const data *dat, int a, int b)
+{
+	const int P = dat->ploidy, L = dat->L;
+	const uint8_t *ca = dat->codes + (size_t)a * L * P;
+	const uint8_t *cb = dat->codes + (size_t)b * L * P;
+	double d = 0;
+
+	for (int l = 0; l < L; l++, ca += P, cb += P) {
+		for (int x = 0; x < P; x++) {
+			int first = 1, na = 0, nb = 0;
+			if (ca[x] == MC_CODE_MISSING)
+				continue;
+			for (int y = 0; y < x; y++)
+				if (ca[y] == ca[x])
+					first = 0;
+			if (!first)
+				continue;
+			for (int y = 0; y < P; y++) {
+				na += ca[y] == ca[x];
+				nb += cb[y] == ca[x];
+			}
+			d += abs(na - nb);
+		}
+		for (int x = 0; x < P; x++) {	/* alleles only b carries */
+			int first = 1, nb = 0, in_a = 0;
+			if (cb[x] == MC_CODE_MISSING)
+				continue;
+			for (int y = 0; y < x; y++)
+				if (cb[y] == cb[x])
+					first = 0;
+			for (int y = 0; y < P; y++) {
+				in_a |= ca[y] == cb[x];
+				nb += cb[y] == cb[x];
+			}
+			if (first && !in_a)
+				d += nb;
+		}
+	}
+	return d;
+}
+
+/* rnd_init.c:192-339 */
+static int random_initialize_mixture(options *opt, data *dat, model *mod)
+{
+	const int K = mod->K, I = dat->I, L = dat->L, P = dat->ploidy;
+	const int64_t T = mod->T;
+	int *center = malloc(sizeof *center * (size_t)K);
+	double *eta = calloc((size_t)K, sizeof *eta);
+	double *p = calloc((size_t)K * (T ? T : 1), sizeof *p);
+	int *part = dat->I_K;
+
+	(void)opt;
+	if (!center || !eta || !p)
+		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "initial parameters\n");
+
+	if (K == 1) {
+		for (int i = 0; i < I; i++)
+			part[i] = 0;
+	} else {
+		/* K distinct random centres, re-drawing on collision (205-217) */
+		for (int k = 0; k < K; k++) {
+			int again;
+			center[k] = (int)(rand() % I);
+			do {
+				again = 0;
+				for (int j = 0; j < k; j++)
+					if (center[k] == center[j]) {
+						center[k] = (int)(rand() % I);
+						again = 1;
+						break;
+					}
+			} while (again);
+		}
+		/* nearest centre, strictly smaller distance wins (220-258) */
+		for (int i = 0; i < I; i++) {
+			double best = INFINITY;
+			part[i] = 0;
+			if (i == center[0])
+				continue;
+			for (int k = 0; k < K; k++) {
+				double d;
+				if (i == center[k]) {
+					part[i] = k;
+					break;
+				}
+				d = count_distance(dat, i, center[k]);
+				if (d < best) {
+					part[i] = k;
+					best = d;
+				}
+			}
+		}
+	}
+
+	/* eta_k = (1 + n_k) / (I + K)  (274-293) */
+	for (int k = 0; k < K; k++)
+		eta[k] = 1;
+	for (int i = 0; i < I; i++)
+		eta[part[i]]++;
+	for (int k = 0; k < K; k++)
+		eta[k] /= I + K;
+
+	/* p_klj proportional to 1 + (K - k) S_klj with S_klj the allele count of
+	 * cluster k: the reference's accumulation sits inside its k loop
+	 * (296-318), so row k is reset at pass k and then receives its members'
+	 * counts on passes k..K-1.  Counts are integers: the closed form is
+	 * bit-identical to the repeated additions. */
+	for (int i = 0; i < I; i++) {
+		const uint8_t *c = dat->codes + (size_t)i * L * P;
+		double *row = p + (size_t)part[i] * T;
+		for (int l = 0; l < L; l++)
+			for (int a = 0; a < P; a++)
+				if (c[l * P + a] != MC_CODE_MISSING)
+					row[dat->allele_off[l] + c[l * P + a]] += 1;
+	}
+	for (int k = 0; k < K; k++)
+		for (int l = 0; l < L; l++) {
+			double *row = p + (size_t)k * T + dat->allele_off[l];
+			double sum = 0.0;
+			for (int m = 0; m < dat->uniquealleles[l]; m++) {
+				row[m] = 1.0 + (K - k) * row[m];
+				sum += row[m];
+			}
+			for (int m = 0; m < dat->uniquealleles[l]; m++)
+				row[m] /= sum;
+		}
+	GPU(mc_set_params(mod->gpu, mod->tindex, eta, p));
+	free(center);
+	free(eta);
+	free(p);
+	return NO_ERROR;
+}
+
+/* reference rnd_init.c:54-89 */
+int initialize_model(options *opt, data *dat, model *mod)
+{
+	mod->n_iter = 0;
+	mod->logL = -INFINITY;
+	mod->converged = 0;
+	if (opt->accel_scheme)
+		mod->pindex = mod->tindex = mod->findex = 0;
+	if (opt->admixture)
+		return random_initialize_admixture(opt, dat, mod);
+	return random_initialize_mixture(opt, dat, mod);
+}

@@ -1,0 +1,120 @@
+"""End-to-end parity of the product binary (multiclust_b200/host/multiclust:
+C host + libmc_cuda.so) with the golden vectors written by the unmodified
+reference: same generated STRUCTURE text, same command line (plus --trace /
+--dump for full precision), compared per fit:
+  - initial parameters after initialize_model (same rand() stream)   1e-12
+  - every log likelihood handed to stop()                  1e-9 relative
+  - final parameters and posterior sums                    1e-7 absolute
+  - n_iter, converged, iter_stop, pindex                   exact
+and the seven result-file kinds against the same numbers at %f."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import ROOT, ensure_mc_gen, golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+CLI = os.path.join(ROOT, "multiclust_b200", "host", "multiclust")
+LL_RTOL = 1e-9
+PAR_ATOL = 1e-7
+
+
+def run_cli(tmp_path, g, extra=()):
+    from oracle import orc
+    gen = g["meta"]["gen"]
+    stru = str(tmp_path / "d.stru")
+    subprocess.check_call([ensure_mc_gen(), "--I", str(gen["I"]), "--L", str(gen["L"]),
+                           "--K", str(gen["K"]), "--jmax", str(gen["jmax"]),
+                           "--miss", str(gen["miss"]), "--P", str(gen["P"]), "--stru", stru])
+    out = tmp_path / "out"
+    out.mkdir()
+    trace = str(tmp_path / "trace.txt")
+    pre = str(tmp_path / "dump")
+    cmd = [CLI, "-f", stru] + g["meta"]["cmd"].split() + [
+        "-d", str(out), "--trace", trace, "--dump", pre] + list(extra)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ll, fit, cur = {}, {}, None
+    for line in open(trace):
+        w = line.split()
+        if w[0] == "init":
+            cur = (int(w[1]), int(w[2]))
+            ll[cur] = []
+        elif w[0] == "ll":
+            ll[cur].append(float(w[3]))
+        elif w[0] == "fit":
+            d = {}
+            for kv in w[3:]:
+                k, v = kv.split("=")
+                d[k] = float(v) if k == "logL" else int(v)
+            fit[(int(w[1]), int(w[2]))] = d
+    states = {}
+    for key in fit:
+        for tag in ("start", "final"):
+            states[key + (tag,)] = orc.read_state("%s.K%d.init%d.%s.bin" % (pre, key[0], key[1], tag))
+    return r, ll, fit, states, out
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cli_matches_reference(tmp_path, name):
+    g = load_golden(name)
+    r, ll, fit, states, out = run_cli(tmp_path, g)
+    assert len(fit) == len(g["meta"]["fits"])
+    for rec in g["meta"]["fits"]:
+        K, init = rec["K"], rec["init"]
+        key = "K%d_i%d_" % (K, init)
+        st = states[(K, init, "start")]
+        assert np.max(np.abs(st["eta"] - g[key + "start_eta"])) < 1e-12
+        assert np.max(np.abs(st["p"] - g[key + "start_p"])) < 1e-12
+        ref_ll = g[key + "ll"]
+        got = np.array(ll[(K, init)])
+        assert got.size == ref_ll.size, "number of EM steps"
+        assert np.all(np.abs(got - ref_ll) <= LL_RTOL * np.abs(ref_ll))
+        f = fit[(K, init)]
+        assert abs(f["logL"] - rec["logL"]) <= LL_RTOL * abs(rec["logL"])
+        for field in ("n_iter", "converged", "iter_stop", "pindex"):
+            assert f[field] == rec[field], field
+        fi = states[(K, init, "final")]
+        assert np.max(np.abs(fi["eta"] - g[key + "final_eta"])) < PAR_ATOL
+        assert np.max(np.abs(fi["p"] - g[key + "final_p"])) < PAR_ATOL
+        assert np.max(np.abs(fi["posterior"] - g[key + "final_post"])) < PAR_ATOL * 10
+
+
+def test_result_files(tmp_path):
+    """names and contents of the result files of an admixture and a mixture fit"""
+    for name, kind in (("admix_em", "admix"), ("mix_em", "mix")):
+        g = load_golden(name)
+        sub = tmp_path / name
+        sub.mkdir()
+        r, ll, fit, states, out = run_cli(sub, g)
+        K = g["meta"]["fits"][0]["K"]
+        # the best of the fits is what is left on disk
+        best = max(g["meta"]["fits"], key=lambda f: f["logL"])
+        key = "K%d_i%d_" % (K, best["init"])
+        files = sorted(os.listdir(out))
+        base = "d.stru"
+        expect = ["%s.%s.K=%d.out.txt" % (base, kind, K), "%s.%s.K=%d.pklm.txt" % (base, kind, K)]
+        if kind == "admix":
+            expect += ["%s.admix.K=%d.etaik.txt" % (base, K), "%s_admix_popq_%d.popq" % (base, K),
+                       "%s_admix_indivq_%d.indivq" % (base, K)]
+        else:
+            expect += ["%s.mix.K=%d.etak.txt" % (base, K), "%s_mix_popq.popq" % base,
+                       "%s.mix.K=%d.indivq" % (base, K)]
+        assert files == sorted(expect)
+        txt = open(out / expect[0]).read().split("\n")
+        assert txt[0].startswith("logL = %f" % best["logL"])
+        rows = [l.split("\t") for l in open(out / expect[1]).read().strip().split("\n")[1:]]
+        p = np.array([float(x[3]) for x in rows])
+        assert np.max(np.abs(p - g[key + "final_p"])) < 1e-6
+        # per-initialisation line on stdout (multiclust.c:618-627)
+        assert "K = %d, initialization = 0: %f" % (K, g["meta"]["fits"][0]["logL"]) in r.stdout
+
+
+def test_dash_C_is_dash_T(tmp_path):
+    g = load_golden("admix_em")
+    g["meta"]["cmd"] = g["meta"]["cmd"].replace("-T", "-C")
+    r, ll, fit, states, out = run_cli(tmp_path, g)
+    assert fit[(3, 0)]["n_iter"] == g["meta"]["fits"][0]["n_iter"]
