@@ -5,7 +5,11 @@ reference: same generated STRUCTURE text, same command line (plus --trace /
   - initial parameters after initialize_model (same rand() stream)   1e-12
   - every log likelihood handed to stop()                  1e-9 relative
   - final parameters and posterior sums                    1e-7 absolute
-  - n_iter, converged, iter_stop, pindex                   exact
+  - n_iter, converged, iter_stop                           exact
+(the slot index pindex is not compared: whenever SQUAREM's step length is
+clipped to -1 the extrapolated point equals the plain EM point F(F(x)) up to
+rounding, accel_em.c:236-237, so accept/reject -- and with it which of two
+numerically identical slots is kept -- is decided by the last bit)
 and the seven result-file kinds against the same numbers at %f."""
 import os
 import subprocess
@@ -75,7 +79,7 @@ def test_cli_matches_reference(tmp_path, name):
         assert np.all(np.abs(got - ref_ll) <= LL_RTOL * np.abs(ref_ll))
         f = fit[(K, init)]
         assert abs(f["logL"] - rec["logL"]) <= LL_RTOL * abs(rec["logL"])
-        for field in ("n_iter", "converged", "iter_stop", "pindex"):
+        for field in ("n_iter", "converged", "iter_stop"):
             assert f[field] == rec[field], field
         fi = states[(K, init, "final")]
         assert np.max(np.abs(fi["eta"] - g[key + "final_eta"])) < PAR_ATOL
