@@ -246,8 +246,13 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    # one torch stream carries the context's kernels, the NCCL all-gather and
+    # the timing events (the legacy default stream has handle 0, which
+    # mc_set_stream reads as "use the context's own stream")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx = Context(local)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.set_stream(stream.cuda_stream)
     sp = SynthParams(seed=SEED, K=a.K, jmax=a.jmax, miss_bp=a.miss_bp, ploidy=a.ploidy)
     # rank r owns individuals [r*I, (r+1)*I) of the global synthetic population
     ctx.set_data_synth(a.I, a.L, sp, i_first=rank * a.I)
@@ -268,23 +273,14 @@ def main():
         p0 = pt.cpu().numpy()
     ctx.set_params(0, eta0, p0)
 
+    from multiclust_b200.sharding import sharded_em_step
     gathered = None
     if world > 1:
-        xptr, xn = ctx.exchange_buffer()
-        gathered = torch.empty(world * xn, dtype=torch.float64, device="cuda")
-
-        class _Arr:
-            __cuda_array_interface__ = {"shape": (xn,), "typestr": "<f8",
-                                        "data": (xptr, False), "version": 3}
-        xbuf = torch.as_tensor(_Arr(), device="cuda")
+        gathered = torch.empty(world * ctx.exchange_buffer()[1], dtype=torch.float64,
+                               device="cuda")
 
     def one_step():
-        if world == 1:
-            return ctx.em_step(0, 0)
-        ctx.em_step_local(0, 0)
-        dist.all_gather_into_tensor(gathered, xbuf)
-        ctx.exchange_sum(gathered.data_ptr(), world)
-        return ctx.em_step_finish(0)
+        return sharded_em_step(ctx, dist, world, 0, 0, gathered)
 
     def barrier():
         if world > 1:
@@ -342,22 +338,9 @@ def main():
         ctx2.set_data(J, codes_p)
         ctx2.alloc_model(a.K, admixture=1, q=0, eta_lb=lb, p_lb=lb)
         ctx2.set_params(0, eta_h, p_h)
-        if world == 1:
-            for _ in range(a.steps):
-                ctx2.em_step(0, 0)
-        else:
-            x2ptr, _ = ctx2.exchange_buffer()
-
-            class _Arr2:
-                __cuda_array_interface__ = {"shape": (xn,), "typestr": "<f8",
-                                            "data": (x2ptr, False), "version": 3}
-            xbuf2 = torch.as_tensor(_Arr2(), device="cuda")
-            ctx2.set_stream(torch.cuda.current_stream().cuda_stream)
-            for _ in range(a.steps):
-                ctx2.em_step_local(0, 0)
-                dist.all_gather_into_tensor(gathered, xbuf2)
-                ctx2.exchange_sum(gathered.data_ptr(), world)
-                ctx2.em_step_finish(0)
+        ctx2.set_stream(stream.cuda_stream)
+        for _ in range(a.steps):
+            sharded_em_step(ctx2, dist, world, 0, 0, gathered)
         ctx2.lib.mc_get_params(ctx2.h, 0, ctypes.c_void_p(eta_o.ctypes.data),
                                ctypes.c_void_p(p_o.ctypes.data))
         ctx2.lib.mc_get_posterior(ctx2.h, ctypes.c_void_p(post_o.ctypes.data))

@@ -228,6 +228,22 @@ class Context:
                  "mc_em_step_finish")
         return ll.value
 
+    # the shard interface of multiclust_b200/sharding.py
+    def exchange_tensor(self):
+        """the exchange buffer viewed as a torch CUDA tensor (no copy)"""
+        import torch
+        ptr, n = self.exchange_buffer()
+        if getattr(self, "_xt", None) is None or self._xt_key != (ptr, n):
+            class _Arr:
+                __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8",
+                                            "data": (ptr, False), "version": 3}
+            self._xt = torch.as_tensor(_Arr(), device="cuda")
+            self._xt_key = (ptr, n)
+        return self._xt
+
+    def sum_gathered(self, gathered, world):
+        self.exchange_sum(gathered.data_ptr(), world)
+
     def exchange_sum(self, gathered_ptr, n_ranks):
         self._ck(self.lib.mc_exchange_sum(self.h, C.c_void_p(gathered_ptr), n_ranks),
                  "mc_exchange_sum")

@@ -519,6 +519,82 @@ void orc_m_step(orc_fit *f)
 		m_step_mixture(f);
 }
 
+/* ---- sharded fits (test support): the sums a rank contributes ---- */
+
+void orc_get_sums(const orc_fit *f, double *N, double *S)
+{
+	const int K = f->K, T = f->T;
+	int i, k, m;
+
+	if (f->o.admixture) {
+		memcpy(N, f->N, sizeof(double) * (size_t)K * T);
+		for (k = 0; k < K; k++) {
+			S[k] = 0;
+			for (i = 0; i < f->I; i++)
+				S[k] += f->D[(size_t)i * K + k];
+		}
+		return;
+	}
+	for (k = 0; k < K; k++) {
+		S[k] = 0;
+		for (i = 0; i < f->I; i++)
+			S[k] += f->vik[(size_t)i * K + k];
+		for (m = 0; m < T; m++) {
+			double s = 0;
+			for (i = 0; i < f->I; i++) {
+				int c = f->cnt[(size_t)i * T + m];
+				if (c)
+					s += f->vik[(size_t)i * K + k] * c;
+			}
+			N[(size_t)k * T + m] = s;
+		}
+	}
+}
+
+void orc_m_step_from_sums(orc_fit *f, const double *N, const double *S)
+{
+	const int K = f->K, T = f->T;
+	double *eta = f->eta[f->tindex], *p = f->p[f->tindex];
+	double temp;
+	int k, l, m;
+
+	if (f->o.admixture && !f->o.eta_constrained) {
+		/* eta rows are local to the shard: the regular M-step forms them;
+		 * only p needs the global sums */
+		memcpy(f->N, N, sizeof(double) * (size_t)K * T);
+		m_step_admixture(f);
+		return;
+	}
+	if (f->o.admixture) {
+		memcpy(f->N, N, sizeof(double) * (size_t)K * T);
+		memcpy(f->Dk, S, sizeof(double) * (size_t)K);
+		m_step_admixture(f);
+		return;
+	}
+	temp = 0;
+	for (k = 0; k < K; k++) {
+		eta[k] = S[k];
+		temp += eta[k];
+	}
+	for (k = 0; k < K; k++)
+		eta[k] /= temp;
+	if (f->o.do_projection)
+		orc_project(eta, K, f->eta_lb);
+	for (k = 0; k < K; k++)
+		for (l = 0; l < f->L; l++) {
+			double *row = p + (size_t)k * T + f->off[l];
+			temp = 0.0;
+			for (m = 0; m < f->J[l]; m++) {
+				row[m] = f->p_lb + N[(size_t)k * T + f->off[l] + m];
+				temp += row[m];
+			}
+			for (m = 0; m < f->J[l]; m++)
+				row[m] /= temp;
+			if (f->o.do_projection)
+				orc_project(row, f->J[l], f->p_lb);
+		}
+}
+
 /* ------------------------------------------------------ em_alg.c:101-207 */
 
 static int converged(orc_fit *f, double ll)

@@ -68,6 +68,14 @@ int orc_accelerated_em_step(orc_fit *f);
 void orc_project(double *x, int n, double floor_);	/* michelot_project */
 void orc_em(orc_fit *f);			/* em() */
 
+/* sufficient statistics left by orc_e_step, for tests of individual-sharded
+ * fits: [K*T allele-count sums | K pooled-eta sums] (admixture: N and Dk;
+ * mixture: sum_i v_ik c_ilj without the pseudo-count and sum_i v_ik) */
+void orc_get_sums(const orc_fit *f, double *N, double *S);
+/* M-step from externally summed statistics (the exchange step of a sharded
+ * fit): overwrites the allele-count / pooled sums, keeps the local D_ik */
+void orc_m_step_from_sums(orc_fit *f, const double *N, const double *S);
+
 /* state */
 void orc_set_indices(orc_fit *f, int pindex, int findex, int tindex);
 void orc_get_state(const orc_fit *f, double *logL, int *n_iter, int *converged,

@@ -70,6 +70,8 @@ def lib():
         L.orc_get_state.argtypes = [C.c_void_p, dp, ip, ip, ip, ip, ip, ip]
         L.orc_get_posterior.argtypes = [C.c_void_p, dp]
         L.orc_get_trace.argtypes = [C.c_void_p, dp]
+        L.orc_get_sums.argtypes = [C.c_void_p, dp, dp]
+        L.orc_m_step_from_sums.argtypes = [C.c_void_p, dp, dp]
         L.orc_reset_trace.argtypes = [C.c_void_p]
         for name in ("orc_aic", "orc_bic"):
             getattr(L, name).restype = C.c_double
@@ -176,6 +178,17 @@ class Fit:
         out = np.empty(self.I * self.K)
         lib().orc_get_posterior(self.h, _dp(out))
         return out.reshape(self.I, self.K)
+
+    def sums(self):
+        N = np.empty(self.K * self.T)
+        S = np.empty(self.K)
+        lib().orc_get_sums(self.h, _dp(N), _dp(S))
+        return N, S
+
+    def m_step_from_sums(self, N, S):
+        N = np.ascontiguousarray(N, dtype=np.float64)
+        S = np.ascontiguousarray(S, dtype=np.float64)
+        lib().orc_m_step_from_sums(self.h, _dp(N), _dp(S))
 
     def trace(self):
         n = lib().orc_trace_len(self.h)
