@@ -41,7 +41,8 @@ class PlanInfo(C.Structure):
                 ("n_tiles", C.c_int32), ("n_chunks", C.c_int32),
                 ("n_units", C.c_int32), ("grid", C.c_int32),
                 ("block", C.c_int32), ("indiv_per_block", C.c_int32),
-                ("ploidy_padded", C.c_int32), ("smem_bytes", C.c_int64),
+                ("ploidy_padded", C.c_int32), ("two_pass", C.c_int32),
+                ("reserved", C.c_int32), ("smem_bytes", C.c_int64),
                 ("algorithmic_bytes_em", C.c_int64),
                 ("algorithmic_bytes_ll", C.c_int64)]
 
