@@ -31,8 +31,13 @@
 #include <stdint.h>
 
 #define A2_IT 256		/* individuals per tile (8-bit index in the lists) */
-#define A2_THREADS 512
+#ifndef A2_THREADS
+#define A2_THREADS 256
+#endif
 #define A2_H (A2_THREADS / A2_IT)	/* threads sharing an individual in pass 1 */
+#ifndef A2_CTAS_PER_SM
+#define A2_CTAS_PER_SM 2	/* two CTAs per SM: one's pass 1 (FP64) overlaps the other's pass 2 (LDS) */
+#endif
 
 struct Admix2Args {
 	int K, KR;			/* KR = K rounded up to even */
@@ -57,7 +62,7 @@ struct Admix2Args {
 	const double *p, *eta;
 	long long eta_stride;
 	/* outputs */
-	double *Apart;			/* [n_lchunks][Ipad][K] */
+	double *Apart;			/* [n_lchunks * A2_H][Ipad][K] */
 	double *Npart;			/* [n_ichunks][K*T] */
 	double *llpart;			/* [n_units] */
 };
@@ -77,8 +82,8 @@ __global__ void k_build_csr(const unsigned char *nat, unsigned char *csr,
 		const long long r = x / A2_THREADS;
 		const int lt = (int)(r % n_ltiles);
 		const long long it = r / n_ltiles;
-		const long long i = it * A2_IT + t / A2_H;
-		const int h = t % A2_H;
+		const long long i = it * A2_IT + t % A2_IT;
+		const int h = t / A2_IT;
 		unsigned char b[8];
 		for (int q = 0; q < 8; q++) {
 			const int l = lt * LT + h * LH + q / PP, a = q % PP;
@@ -183,13 +188,14 @@ __device__ __forceinline__ void a2_cp_async_wait()
 
 /* MODE 0: E+M step, MODE 1: log likelihood only */
 template <int KP, int PP, int MODE>
-__global__ void __launch_bounds__(A2_THREADS, 1) admix2_kernel(const Admix2Args a)
+__global__ void __launch_bounds__(A2_THREADS, A2_CTAS_PER_SM) admix2_kernel(const Admix2Args a)
 {
 	constexpr int KR = 2 * KP;
 	constexpr bool EM = (MODE == 0);
 	extern __shared__ double smem[];
 	const int t = threadIdx.x, lane = t & 31;
-	const int ii = t / A2_H, h = t % A2_H;
+	/* pass 1: a warp is 32 consecutive individuals at the SAME loci */
+	const int ii = t % A2_IT, h = t / A2_IT;
 	const int LT = a.LT, LH = a.LH;
 
 	/* shared memory carve-up (doubles first, then 16-bit tables) */
@@ -352,7 +358,35 @@ __global__ void __launch_bounds__(A2_THREADS, 1) admix2_kernel(const Admix2Args 
 					const int ce = cst_s[col + 1];
 					ll2 = info >> 8;
 					j2 = info & 0xff;
-					for (int x = cst_s[col] + seg; x < ce; x += S) {
+					int x = cst_s[col] + seg;
+					/* two entries per trip: their loads are issued together */
+					for (; x + S < ce; x += 2 * S) {
+						const unsigned e0 = csc_s[x], e1 = csc_s[x + S];
+						const int i0 = e0 & 0xff, i1 = e1 & 0xff;
+						const double w0 = w_s[(size_t)(ll2 * PP + ((e0 >> 8) & 0xf)) * A2_IT + i0]
+							* (double)((e0 >> 12) + 1);
+						const double w1 = w_s[(size_t)(ll2 * PP + ((e1 >> 8) & 0xf)) * A2_IT + i1]
+							* (double)((e1 >> 12) + 1);
+						const double2 *r0 = reinterpret_cast<const double2 *>(eta_s + (size_t)i0 * KR);
+						const double2 *r1 = reinterpret_cast<const double2 *>(eta_s + (size_t)i1 * KR);
+						double2 v0[KP], v1[KP];
+#pragma unroll
+						for (int kp = 0; kp < KP; kp++) {
+							v0[kp] = r0[kp];
+							v1[kp] = r1[kp];
+						}
+#pragma unroll
+						for (int kp = 0; kp < KP; kp++) {
+							g[2 * kp] = fma(v0[kp].x, w0, g[2 * kp]);
+							g[2 * kp + 1] = fma(v0[kp].y, w0, g[2 * kp + 1]);
+						}
+#pragma unroll
+						for (int kp = 0; kp < KP; kp++) {
+							g[2 * kp] = fma(v1[kp].x, w1, g[2 * kp]);
+							g[2 * kp + 1] = fma(v1[kp].y, w1, g[2 * kp + 1]);
+						}
+					}
+					if (x < ce) {
 						const unsigned ent = csc_s[x];
 						const int ei = ent & 0xff, ea = (ent >> 8) & 0xf;
 						const double wv = w_s[(size_t)(ll2 * PP + ea) * A2_IT + ei]
@@ -388,20 +422,13 @@ __global__ void __launch_bounds__(A2_THREADS, 1) admix2_kernel(const Admix2Args 
 				}
 			}
 			if (EM) {
-				/* A_i of this chunk of loci: fold the A2_H pass-1 threads of
-				 * the individual (adjacent lanes), one of them writes */
+				/* A_i of this chunk of loci; the A2_H pass-1 threads of an
+				 * individual own separate slots, k_admix_eta adds them */
+				double *dst = a.Apart + ((size_t)(c * A2_H + h) * a.Ipad + i) * a.K;
 #pragma unroll
-				for (int m = 1; m < A2_H; m <<= 1)
-#pragma unroll
-					for (int k = 0; k < KR; k++)
-						A[k] += shfl_xor_f64(A[k], m);
-				if (h == 0) {
-					double *dst = a.Apart + ((size_t)c * a.Ipad + i) * a.K;
-#pragma unroll
-					for (int k = 0; k < KR; k++)
-						if (k < a.K)
-							dst[k] = A[k];
-				}
+				for (int k = 0; k < KR; k++)
+					if (k < a.K)
+						dst[k] = A[k];
 			}
 		}
 

@@ -520,9 +520,11 @@ static int make_plan2(mc_ctx *c)
 		+ A2_THREADS / 32) * sizeof(double)
 		+ ((size_t)cap + (size_t)(ncolmax + 1 + 7) / 8 * 8) * sizeof(unsigned short)
 		+ (size_t)LT * sizeof(int) + 64;
-	if (fixed + (size_t)max_tile_rows * KR * sizeof(double) > SMEM_LIMIT)
+	/* per CTA; A2_CTAS_PER_SM of them share the SM (1 KB each is reserved) */
+	const size_t smem_cap = (size_t)(228 * 1024) / A2_CTAS_PER_SM - 1024 - 64;
+	if (fixed + (size_t)max_tile_rows * KR * sizeof(double) > smem_cap)
 		return MC_OK;
-	const long long budget_rows = (long long)((SMEM_LIMIT - fixed) / (KR * sizeof(double)));
+	const long long budget_rows = (long long)((smem_cap - fixed) / (KR * sizeof(double)));
 	const long long total_rows = c->T;
 	int n_lchunks = (int)((total_rows + budget_rows - 1) / budget_rows);
 	std::vector<int> lc_first;
@@ -555,7 +557,7 @@ static int make_plan2(mc_ctx *c)
 	/* chunks of individual tiles: balance the persistent grid */
 	int n_ichunks = 1;
 	{
-		const long long sms = c->num_sms;
+		const long long sms = (long long)c->num_sms * A2_CTAS_PER_SM;
 		double best_eff = -1;
 		const long long cmax = std::min<long long>(n_itiles,
 			std::max<long long>(1, (6 * sms + n_lchunks - 1) / n_lchunks));
@@ -580,7 +582,7 @@ static int make_plan2(mc_ctx *c)
 	a.max_tile_rows = max_tile_rows; a.cap = cap;
 	c->KP2 = KP;
 	c->smem2 = fixed + (size_t)max_chunk_rows * KR * sizeof(double);
-	c->grid2 = std::min(a.n_units, c->num_sms);
+	c->grid2 = std::min(a.n_units, c->num_sms * A2_CTAS_PER_SM);
 
 	std::vector<unsigned short> colinfo((size_t)n_ltiles * ncolmax, 0);
 	for (int lt = 0; lt < n_ltiles; lt++)
@@ -605,7 +607,7 @@ static int make_plan2(mc_ctx *c)
 	a.lt_first = c->d2_lt_first; a.lt_ncol = c->d2_lt_ncol; a.lt_S = c->d2_lt_S;
 	a.colinfo = c->d2_colinfo; a.lc_first = c->d2_lc_first; a.off = c->d_off;
 	a.csr = c->d2_csr; a.csc = c->d2_csc; a.colstart = c->d2_colstart;
-	if ((rc = alloc_outputs(c, n_lchunks, n_ichunks, a.n_units, a.Ipad))) return rc;
+	if ((rc = alloc_outputs(c, n_lchunks * A2_H, n_ichunks, a.n_units, a.Ipad))) return rc;
 	a.Apart = c->d_Apart; a.Npart = c->d_Npart; a.llpart = c->d_llpart;
 	CK(cudaStreamSynchronize(c->stream));
 	c->use2 = true;
