@@ -380,7 +380,9 @@ def main():
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "peak_source": peak_src, "kernel": "tile_kernel<MODE_ADMIX_EM>",
+                "peak_source": peak_src,
+                "kernel": "admix2_kernel<MODE_EM> (two-pass)" if plan.get("two_pass")
+                else "tile_kernel<MODE_ADMIX_EM>",
                 "kernel_ms": k_ms, "kernel_launches_timed": nk,
                 "algorithmic_bytes_per_launch": alg,
                 "kernel_share_of_step": (k_ms / ms_per_step) if nk else None}
@@ -404,9 +406,9 @@ def main():
                                        "individuals)" % a.I,
                    "l2": "inputs (%.2f GB of genotype codes per GPU) exceed the 126 MB L2; no flush"
                          % (a.I * a.L * a.ploidy / 1e9),
-                   "plan": {k: plan[k] for k in ("k_split", "k_per_lane", "warps", "groups",
-                                                 "n_tiles", "n_chunks", "grid", "block",
-                                                 "smem_bytes")}},
+                   "plan": {k: plan[k] for k in ("two_pass", "k_split", "k_per_lane", "warps",
+                                                 "groups", "n_tiles", "n_chunks", "grid",
+                                                 "block", "smem_bytes")}},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
         "logL_first": lls[0], "logL_last": lls[-1],

@@ -61,6 +61,9 @@ void mc_destroy(mc_ctx *ctx);
  * torch stream); NULL restores the context's own stream. */
 int mc_set_stream(mc_ctx *ctx, void *cuda_stream);
 int mc_sync(mc_ctx *ctx);
+/* the CUDA ordinal and the cudaStream_t launches currently go to */
+int mc_ctx_device(const mc_ctx *ctx);
+void *mc_ctx_stream(const mc_ctx *ctx);
 
 /* ---- data: replaces dat->IL / ILM / uniquealleles as the path reads them
  *      (multiclust.h:223-250, read_file.c:633-663) ------------------------ */
@@ -97,6 +100,10 @@ int mc_get_params(mc_ctx *ctx, int slot, double *eta, double *p);
  * at locus l (set, not incremented: two copies of one allele drawn to the same
  * k count once) and runs the M-step (with projections) into `slot`. */
 int mc_init_admixture(mc_ctx *ctx, int slot, const uint8_t *z);
+/* the same split for an individual-sharded fit: counts of this context's
+ * individuals (eta rows of `slot` are final, the allele counts are left in
+ * the exchange buffer); sum over ranks, then mc_em_step_finish(slot) */
+int mc_init_admixture_local(mc_ctx *ctx, int slot, const uint8_t *z);
 
 /* ---- the hot path ------------------------------------------------------ */
 
@@ -110,6 +117,11 @@ int mc_em_step(mc_ctx *ctx, int from, int to, double *ll);
 
 /* log_likelihood() (log_likelihood.c:56-62, 96-232); touches no posterior. */
 int mc_loglik(mc_ctx *ctx, int slot, double *ll);
+
+/* Log likelihood left on the device by the last mc_em_step_finish / mc_loglik
+ * call that was given ll == NULL (lets one host thread keep several devices
+ * busy: launch everywhere first, read afterwards).  Synchronises the stream. */
+int mc_read_ll(mc_ctx *ctx, double *ll);
 
 /* Posterior sums of the last E-step: D_ik = sum_{l,j} d_iklj (admixture, what
  * write_file.c:359-381,446-459,525-543 reduce diklm to) or v_ik (mixture). */

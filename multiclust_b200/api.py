@@ -13,9 +13,9 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 # every symbol include/mc_cuda.h declares (tests check the library exports all)
 SYMBOLS = [
     "mc_last_error", "mc_abi_version", "mc_create", "mc_destroy",
-    "mc_set_stream", "mc_sync", "mc_set_data", "mc_set_data_synth",
+    "mc_set_stream", "mc_sync", "mc_ctx_device", "mc_ctx_stream", "mc_set_data", "mc_set_data_synth",
     "mc_get_dims", "mc_get_J", "mc_get_codes", "mc_alloc_model", "mc_eta_len",
-    "mc_set_params", "mc_get_params", "mc_init_admixture", "mc_em_step", "mc_loglik",
+    "mc_set_params", "mc_get_params", "mc_init_admixture", "mc_init_admixture_local", "mc_em_step", "mc_loglik", "mc_read_ll",
     "mc_get_posterior", "mc_partition", "mc_delta", "mc_step_dots",
     "mc_qn_dots", "mc_accel_update", "mc_qn_update", "mc_project",
     "mc_copy_slot", "mc_em_step_local", "mc_exchange_buffer",
@@ -75,6 +75,9 @@ def load_library():
     L.mc_destroy.restype = None
     L.mc_set_stream.argtypes = [vp, vp]
     L.mc_sync.argtypes = [vp]
+    L.mc_ctx_device.argtypes = [vp]
+    L.mc_ctx_stream.argtypes = [vp]
+    L.mc_ctx_stream.restype = vp
     L.mc_set_data.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, vp, vp]
     L.mc_set_data_synth.argtypes = [vp, C.c_int64, C.c_int32,
                                     C.POINTER(SynthParams), C.c_int64]
@@ -88,8 +91,10 @@ def load_library():
     L.mc_set_params.argtypes = [vp, C.c_int, vp, vp]
     L.mc_get_params.argtypes = [vp, C.c_int, vp, vp]
     L.mc_init_admixture.argtypes = [vp, C.c_int, vp]
+    L.mc_init_admixture_local.argtypes = [vp, C.c_int, vp]
     L.mc_em_step.argtypes = [vp, C.c_int, C.c_int, dp]
     L.mc_loglik.argtypes = [vp, C.c_int, dp]
+    L.mc_read_ll.argtypes = [vp, dp]
     L.mc_get_posterior.argtypes = [vp, vp]
     L.mc_partition.argtypes = [vp, vp, vp]
     L.mc_delta.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]

@@ -40,13 +40,28 @@ def _run(cmd):
 
 def build_cuda(force=False, extra=()):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != "mc_comm.cu"]
     srcs += [os.path.join(INC, f) for f in os.listdir(INC)]
     if not force and _newer(LIB, srcs):
         return LIB
     _run([nvcc] + NVCC_FLAGS + list(extra)
          + ["-o", LIB, os.path.join(CSRC, "mc_cuda.cu")])
     return LIB
+
+
+COMM = os.path.join(PKG, "libmc_comm.so")
+
+
+def build_comm(force=False):
+    """libmc_comm.so: the NCCL exchange used by the C host with --gpus N"""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    src = os.path.join(CSRC, "mc_comm.cu")
+    deps = [src, LIB] + [os.path.join(INC, f) for f in os.listdir(INC)]
+    if not force and _newer(COMM, deps):
+        return COMM
+    _run([nvcc] + NVCC_FLAGS + ["-o", COMM, src, "-L" + PKG, "-lmc_cuda",
+                                "-Xlinker", "-rpath," + PKG, "-lnccl"])
+    return COMM
 
 
 def build_host(force=False):
@@ -62,16 +77,17 @@ def build_host(force=False):
     if cli_src:
         exe = os.path.join(HOST, "multiclust")
         deps = cli_src + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".h")]
-        deps += [os.path.join(INC, f) for f in os.listdir(INC)] + [LIB]
+        deps += [os.path.join(INC, f) for f in os.listdir(INC)] + [LIB, COMM]
         if force or not _newer(exe, deps):
             _run([cc] + HOST_CFLAGS + ["-o", exe] + cli_src
-                 + ["-L" + PKG, "-lmc_cuda", "-Wl,-rpath," + PKG, "-lm"])
+                 + ["-L" + PKG, "-lmc_comm", "-lmc_cuda", "-Wl,-rpath," + PKG, "-lm"])
         out.append(exe)
     return out
 
 
 def build_all(force=False):
     build_cuda(force)
+    build_comm(force)
     build_host(force)
 
 

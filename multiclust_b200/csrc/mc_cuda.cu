@@ -225,6 +225,9 @@ extern "C" int mc_set_stream(mc_ctx *c, void *s)
 	return MC_OK;
 }
 
+extern "C" int mc_ctx_device(const mc_ctx *c) { return c ? c->device : -1; }
+extern "C" void *mc_ctx_stream(const mc_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
 extern "C" int mc_sync(mc_ctx *c)
 {
 	if (!c)
@@ -1071,6 +1074,16 @@ extern "C" int mc_em_step_finish(mc_ctx *c, int to, double *ll)
 /* admixture initialiser: hard assignment + M-step (rnd_init.c:349-357) */
 extern "C" int mc_init_admixture(mc_ctx *c, int slot, const uint8_t *z)
 {
+	int rc = mc_init_admixture_local(c, slot, z);
+	if (rc)
+		return rc;
+	rc = mc_em_step_finish(c, slot, nullptr);
+	CK(cudaStreamSynchronize(c->stream));
+	return rc;
+}
+
+extern "C" int mc_init_admixture_local(mc_ctx *c, int slot, const uint8_t *z)
+{
 	NEED_MODEL();
 	CHECK_SLOT(slot);
 	if (!z)
@@ -1091,7 +1104,7 @@ extern "C" int mc_init_admixture(mc_ctx *c, int slot, const uint8_t *z)
 	LAUNCH_CHECK("k_init_counts");
 	k_u32_to_f64<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(d_N, xb_N(c), c->np);
 	LAUNCH_CHECK("k_u32_to_f64");
-	int rc;
+	int rc = MC_OK;
 	if (c->per_indiv) {
 		k_eta_from_D<<<grid_for(c, c->I, 128), 128, 0, c->stream>>>(c->d_post,
 			c->d_eta[slot], c->I, c->K, c->do_proj, c->eta_lb);
@@ -1099,11 +1112,10 @@ extern "C" int mc_init_admixture(mc_ctx *c, int slot, const uint8_t *z)
 	} else {
 		if ((rc = reduce_columns(c, c->d_post, c->I, c->K, xb_S(c)))) return rc;
 	}
-	rc = mc_em_step_finish(c, slot, nullptr);
 	CK(cudaStreamSynchronize(c->stream));
 	cudaFree(d_z);
 	cudaFree(d_N);
-	return rc;
+	return MC_OK;
 }
 
 extern "C" int mc_em_step(mc_ctx *c, int from, int to, double *ll)
@@ -1143,6 +1155,16 @@ extern "C" int mc_loglik(mc_ctx *c, int slot, double *ll)
 		CK(cudaMemcpyAsync(ll, xb_ll(c), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
 	}
+	return MC_OK;
+}
+
+extern "C" int mc_read_ll(mc_ctx *c, double *ll)
+{
+	NEED_MODEL();
+	if (!ll)
+		return fail(c, MC_ERR_ARG, "mc_read_ll: null pointer");
+	CK(cudaMemcpyAsync(ll, xb_ll(c), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
 	return MC_OK;
 }
 

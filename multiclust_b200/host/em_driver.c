@@ -23,6 +23,22 @@ void gpu_check(model *mod, int rc, const char *what)
 	exit(GPU_ERROR);
 }
 #define GPU(call) gpu_check(mod, (call), #call)
+/* the same call on every device of an individual-sharded fit (--gpus); the
+ * calls only launch work, so the devices run concurrently */
+#define GPUS(r, call) for (int r = 0; r < mod->n_gpus; r++) gpu_check(mod, (call), #call)
+
+static void comm_exchange(model *mod)
+{
+	if (mc_comm_exchange(mod->comm) != MC_OK) {
+		mmessage(ERROR_MSG, GPU_ERROR, "%s\n", mc_comm_last_error(mod->comm));
+		exit(GPU_ERROR);
+	}
+}
+
+static int eta_is_sharded(const options *opt)
+{
+	return opt->admixture && !opt->eta_constrained;
+}
 
 /* reference em_alg.c:163-182 */
 int converged(options *opt, model *mod, double loglik)
@@ -98,7 +114,16 @@ int em_step(options *opt, data *dat, model *mod)
 	double ll = 0;
 
 	(void)dat;
-	GPU(mc_em_step(mod->gpu, mod->findex, mod->tindex, &ll));
+	if (mod->n_gpus == 1) {
+		GPU(mc_em_step(mod->gpu, mod->findex, mod->tindex, &ll));
+	} else {
+		/* local E-step on every device, one NCCL all-gather + rank-order
+		 * sum of the sufficient statistics, identical finish everywhere */
+		GPUS(r, mc_em_step_local(mod->gpus[r], mod->findex, mod->tindex));
+		comm_exchange(mod);
+		GPUS(r, mc_em_step_finish(mod->gpus[r], mod->tindex, NULL));
+		GPU(mc_read_ll(mod->gpu, &ll));
+	}
 	return stop(opt, mod, ll);
 }
 
@@ -109,7 +134,16 @@ double log_likelihood(options *opt, data *dat, model *mod, int which)
 
 	(void)opt;
 	(void)dat;
-	GPU(mc_loglik(mod->gpu, which, &ll));
+	if (mod->n_gpus == 1) {
+		GPU(mc_loglik(mod->gpu, which, &ll));
+		return ll;
+	}
+	GPUS(r, mc_loglik(mod->gpus[r], which, NULL));
+	for (int r = 0; r < mod->n_gpus; r++) {	/* rank order: deterministic */
+		double part = 0;
+		GPU(mc_read_ll(mod->gpus[r], &part));
+		ll += part;
+	}
 	return ll;
 }
 
@@ -133,7 +167,7 @@ int em_2_steps(model *mod, data *dat, options *opt)
 	for (int j = 0; j < 2; j++) {
 		if (em_step(opt, dat, mod))
 			return 1;
-		GPU(mc_delta(mod->gpu, j, mod->delta_index, mod->tindex, mod->findex));
+		GPUS(r, mc_delta(mod->gpus[r], j, mod->delta_index, mod->tindex, mod->findex));
 		mod->findex = mod->tindex;
 		mod->tindex = (mod->findex + 1) % 3;
 		if (mod->tindex == mod->pindex)
@@ -147,9 +181,20 @@ int em_2_steps(model *mod, data *dat, options *opt)
  * two parts (eta, p) and are added in the reference's order (eta first) */
 static double step_size(options *opt, model *mod)
 {
-	double e[3], p[3], utu, utvu, vutvu, s;
+	double e[3] = { 0, 0, 0 }, p[3], utu, utvu, vutvu, s;
 
-	GPU(mc_step_dots(mod->gpu, mod->delta_index, e, p));
+	/* p is replicated: device 0's sums; eta rows are sharded: add the parts
+	 * of all devices in rank order (a pooled eta is replicated too) */
+	for (int r = 0; r < mod->n_gpus; r++) {
+		double er[3], pr[3];
+		GPU(mc_step_dots(mod->gpus[r], mod->delta_index, er, pr));
+		for (int x = 0; x < 3; x++) {
+			if (r == 0)
+				p[x] = pr[x];
+			if (r == 0 || eta_is_sharded(opt))
+				e[x] += er[x];
+		}
+	}
 	utu = e[0] + p[0];
 	utvu = e[1] + p[1];
 	vutvu = e[2] + p[2];
@@ -183,7 +228,7 @@ static double accelerated_update(options *opt, data *dat, model *mod, double s)
 	double ll;
 
 	mod->delta_index = mod->delta_index ? mod->delta_index - 1 : opt->q - 1;
-	GPU(mc_accel_update(mod->gpu, opt->accel_scheme == QN, mod->tindex,
+	GPUS(r, mc_accel_update(mod->gpus[r], opt->accel_scheme == QN, mod->tindex,
 		mod->pindex, mod->delta_index, s));
 	ll = log_likelihood(opt, dat, mod, mod->tindex);
 	mod->delta_index = (mod->delta_index + 1) % opt->q;
@@ -196,14 +241,26 @@ static double qn_accelerated_update(options *opt, data *dat, model *mod)
 	const int q = opt->q;
 	const int vindex = mod->delta_index ? mod->delta_index - 1 : q - 1;
 	const int uindex = vindex ? vindex - 1 : q - 1;
-	double *A = mod->A, *Ai = mod->Ainv, e[2], p[2], det;
+	double *A = mod->A, *Ai = mod->Ainv, e[2], p[2] = { 0, 0 }, det;
 	int q1 = mod->delta_index, q2, j = 0, n;
 
 	do {
 		q2 = mod->delta_index;
 		n = 0;
 		do {
-			GPU(mc_qn_dots(mod->gpu, q1, q2, e, p));
+			e[0] = e[1] = 0;
+			for (int r = 0; r < mod->n_gpus; r++) {
+				double er[2], pr[2];
+				GPU(mc_qn_dots(mod->gpus[r], q1, q2, er, pr));
+				if (r == 0) {
+					p[0] = pr[0];
+					p[1] = pr[1];
+				}
+				if (r == 0 || eta_is_sharded(opt)) {
+					e[0] += er[0];
+					e[1] += er[1];
+				}
+			}
 			mod->cutu[n] = e[0] + p[0];
 			A[j * q + n] = (e[0] + p[0]) - (e[1] + p[1]);
 			n++;
@@ -237,7 +294,7 @@ static double qn_accelerated_update(options *opt, data *dat, model *mod)
 		Ai[7] = (A[1] * A[6] - A[0] * A[7]) / det;
 		Ai[8] = (A[0] * A[4] - A[1] * A[3]) / det;
 	}
-	GPU(mc_qn_update(mod->gpu, mod->tindex, mod->pindex, uindex,
+	GPUS(r, mc_qn_update(mod->gpus[r], mod->tindex, mod->pindex, uindex,
 		mod->delta_index, Ai, mod->cutu));
 	return log_likelihood(opt, dat, mod, mod->tindex);
 }

@@ -31,7 +31,20 @@ static int random_initialize_admixture(options *opt, data *dat, model *mod)
 		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "allele partition\n");
 	for (size_t x = 0; x < n; x++)
 		z[x] = (uint8_t)((int)rand() % mod->K);
-	GPU(mc_init_admixture(mod->gpu, mod->tindex, z));
+	if (mod->n_gpus == 1) {
+		GPU(mc_init_admixture(mod->gpu, mod->tindex, z));
+	} else {
+		/* each device counts its rows of z; the allele counts are summed
+		 * over devices before p is normalised */
+		for (int r = 0; r < mod->n_gpus; r++)
+			GPU(mc_init_admixture_local(mod->gpus[r], mod->tindex,
+				z + (size_t)mod->row_first[r] * dat->L * dat->ploidy));
+		if (mc_comm_exchange(mod->comm) != MC_OK)
+			return mmessage(ERROR_MSG, GPU_ERROR, "%s\n",
+				mc_comm_last_error(mod->comm));
+		for (int r = 0; r < mod->n_gpus; r++)
+			GPU(mc_em_step_finish(mod->gpus[r], mod->tindex, NULL));
+	}
 	free(z);
 	return NO_ERROR;
 }
@@ -165,7 +178,8 @@ static int random_initialize_mixture(options *opt, data *dat, model *mod)
 			for (int m = 0; m < dat->uniquealleles[l]; m++)
 				row[m] /= sum;
 		}
-	GPU(mc_set_params(mod->gpu, mod->tindex, eta, p));
+	for (int r = 0; r < mod->n_gpus; r++)	/* eta_k and p are replicated */
+		GPU(mc_set_params(mod->gpus[r], mod->tindex, eta, p));
 	free(center);
 	free(eta);
 	free(p);

@@ -153,6 +153,9 @@ void free_model_data(model *mod, options *opt)
 	(void)opt;
 	free(mod->count_K);
 	free(mod->eta_host); free(mod->p_host); free(mod->post_host);
+	if (mod->comm)
+		mc_comm_destroy(mod->comm);
+	mod->comm = NULL;
 	mod->count_K = NULL;
 	mod->eta_host = mod->p_host = mod->post_host = NULL;
 }
@@ -163,8 +166,11 @@ void free_model(model *mod, options *opt)
 		return;
 	free_model_data(mod, opt);
 	free(mod->A); free(mod->Ainv); free(mod->cutu);
-	if (mod->gpu)
-		mc_destroy(mod->gpu);
+	for (int r = 0; r < mod->n_gpus; r++)
+		if (mod->gpus[r])
+			mc_destroy(mod->gpus[r]);
+	free(mod->gpus);
+	free(mod->row_first);
 	if (mod->trace)
 		fclose(mod->trace);
 	free(mod);
@@ -198,7 +204,8 @@ void fprint_usage(FILE *fp, const char *cmd)
 "  -v <level>    verbosity (4: one line per iteration); -w n <r>  timing repeats\n"
 "  -M            print only the maximum log likelihood\n"
 "device\n"
-"  --device <d>  CUDA device ordinal (default 0)\n"
+"  --device <d>  first CUDA device ordinal (default 0)\n"
+"  --gpus <n>    shard the individuals of one fit over n devices (NCCL exchange)\n"
 "  --trace <f>   write every log likelihood at full precision to <f>\n"
 "  --dump <pre>  binary parameters before / after every fit to <pre>.K*.init*.bin\n"
 "  --parse-only <f>  read and recode the data, write it as MCB1 to <f>, stop\n", cmd);
@@ -502,12 +509,18 @@ int allocate_model_for_k(options *opt, model *mod, data *dat)
 	mod->count_K = calloc((size_t)mod->K, sizeof *mod->count_K);
 	if (!mod->count_K)
 		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "cluster sizes\n");
-	rc = mc_alloc_model(mod->gpu, mod->K, opt->admixture, opt->eta_constrained,
-		opt->accel_scheme ? opt->q : 0, opt->eta_lower_bound,
-		opt->p_lower_bound, opt->do_projection);
-	if (rc)
-		return mmessage(ERROR_MSG, GPU_ERROR, "%s\n", mc_last_error(mod->gpu));
-	mc_eta_len(mod->gpu, &mod->eta_len);
+	for (int r = 0; r < mod->n_gpus; r++) {
+		rc = mc_alloc_model(mod->gpus[r], mod->K, opt->admixture,
+			opt->eta_constrained, opt->accel_scheme ? opt->q : 0,
+			opt->eta_lower_bound, opt->p_lower_bound, opt->do_projection);
+		if (rc)
+			return mmessage(ERROR_MSG, GPU_ERROR, "%s\n",
+				mc_last_error(mod->gpus[r]));
+	}
+	if (mod->n_gpus > 1 && mc_comm_create(&mod->comm, mod->gpus, mod->n_gpus))
+		return mmessage(ERROR_MSG, GPU_ERROR, "%s\n", mc_comm_last_error(NULL));
+	mod->eta_len = (opt->admixture && !opt->eta_constrained)
+		? (int64_t)dat->I * mod->K : mod->K;
 	/* parameter count: phantom slots included (multiclust.c:1268-1276) */
 	mod->no_parameters = (!opt->admixture || opt->eta_constrained)
 		? mod->K - 1 : dat->I * (mod->K - 1);
@@ -534,8 +547,7 @@ static int dump_state(options *opt, data *dat, model *mod, int init, const char 
 	if (!eta || !p || !post || !(fp = fopen(name, "wb")))
 		return message(stderr, __FILE__, __func__, __LINE__, ERROR_MSG,
 			FILE_OPEN_ERROR, name);
-	gpu_check(mod, mc_get_params(mod->gpu, slot, eta, p), "mc_get_params");
-	gpu_check(mod, mc_get_posterior(mod->gpu, post), "mc_get_posterior");
+	gather_state(opt, dat, mod, slot, eta, p, post);
 	hdr[0] = mod->K; hdr[1] = dat->I; hdr[2] = (int32_t)mod->T;
 	hdr[3] = opt->admixture && !opt->eta_constrained;
 	hdr[4] = opt->admixture; hdr[5] = mod->n_iter;

@@ -23,6 +23,7 @@
 #include <time.h>
 
 #include "mc_cuda.h"
+#include "mc_comm.h"
 
 /* error codes: same numbering as reference message.h:17-42 */
 enum {
@@ -137,7 +138,12 @@ struct _model {
 	double seconds_run;
 	int aic_K, bic_K;
 	/* device side */
-	mc_ctx *gpu;			/* context holding data + parameters */
+	mc_ctx *gpu;			/* = gpus[0] */
+	mc_ctx **gpus;			/* --gpus: one context per device, individuals
+					 * [row_first[r], row_first[r+1]) on device r */
+	int n_gpus;
+	int *row_first;
+	mc_comm *comm;			/* NCCL exchange (n_gpus > 1) */
 	int64_t T;			/* sum of allele slots */
 	int64_t eta_len;		/* I*K or K */
 	/* host copies fetched for the writers */
@@ -178,6 +184,8 @@ double aic(model *mod);
 double bic(data *dat, model *mod);
 
 /* ---- output (reference write_file.c) ---- */
+int gather_state(options *opt, data *dat, model *mod, int slot, double *eta,
+	double *p, double *post);
 int fetch_results(options *opt, data *dat, model *mod);
 int write_file_detail(options *opt, data *dat, model *mod);
 void partition_admixture(data *dat, model *mod);

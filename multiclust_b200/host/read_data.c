@@ -344,16 +344,34 @@ int read_file(options *opt, data *dat)
 	return NO_ERROR;
 }
 
-/* hand the recoded genotypes to the device */
+/* hand the recoded genotypes to the device(s): with --gpus N device r gets
+ * the individuals [r*I/N, (r+1)*I/N) and the allele slots of the whole sample */
 int upload_data(options *opt, data *dat, model *mod)
 {
+	const int n = opt->n_gpus;
 	int rc;
 
-	if ((rc = mc_create(&mod->gpu, opt->device)))
-		return mmessage(ERROR_MSG, GPU_ERROR, "%s\n", mc_last_error(NULL));
-	if ((rc = mc_set_data(mod->gpu, dat->I, dat->L, dat->ploidy,
-		dat->uniquealleles, dat->codes)))
-		return mmessage(ERROR_MSG, GPU_ERROR, "%s\n", mc_last_error(mod->gpu));
+	mod->n_gpus = n;
+	mod->gpus = calloc((size_t)n, sizeof *mod->gpus);
+	mod->row_first = calloc((size_t)n + 1, sizeof *mod->row_first);
+	if (!mod->gpus || !mod->row_first)
+		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "device table\n");
+	if (dat->I < n)
+		return mmessage(ERROR_MSG, INVALID_USER_SETUP, "--gpus %d exceeds the "
+			"number of individuals (%d)\n", n, dat->I);
+	for (int r = 0; r <= n; r++)
+		mod->row_first[r] = (int)((long long)dat->I * r / n);
+	for (int r = 0; r < n; r++) {
+		const int rows = mod->row_first[r + 1] - mod->row_first[r];
+		if ((rc = mc_create(&mod->gpus[r], opt->device + r)))
+			return mmessage(ERROR_MSG, GPU_ERROR, "%s\n", mc_last_error(NULL));
+		if ((rc = mc_set_data(mod->gpus[r], rows, dat->L, dat->ploidy,
+			dat->uniquealleles, dat->codes
+			+ (size_t)mod->row_first[r] * dat->L * dat->ploidy)))
+			return mmessage(ERROR_MSG, GPU_ERROR, "%s\n",
+				mc_last_error(mod->gpus[r]));
+	}
+	mod->gpu = mod->gpus[0];
 	mod->T = dat->allele_off[dat->L];
 	return NO_ERROR;
 }

@@ -15,6 +15,23 @@
 
 #define GPU(call) gpu_check(mod, (call), #call)
 
+/* parameters of `slot` and posterior sums from all devices: p (and a pooled
+ * eta) from device 0, the eta / posterior rows of each device's individuals */
+int gather_state(options *opt, data *dat, model *mod, int slot, double *eta,
+	double *p, double *post)
+{
+	const int sharded = opt->admixture && !opt->eta_constrained;
+
+	(void)dat;
+	for (int r = 0; r < mod->n_gpus; r++) {
+		const size_t row = (size_t)mod->row_first[r] * mod->K;
+		GPU(mc_get_params(mod->gpus[r], slot,
+			sharded ? eta + row : (r == 0 ? eta : NULL), r == 0 ? p : NULL));
+		GPU(mc_get_posterior(mod->gpus[r], post + row));
+	}
+	return NO_ERROR;
+}
+
 /* parameters of slot pindex and the posterior sums of the last E-step */
 int fetch_results(options *opt, data *dat, model *mod)
 {
@@ -27,9 +44,8 @@ int fetch_results(options *opt, data *dat, model *mod)
 	mod->post_host = malloc(sizeof(double) * (size_t)dat->I * mod->K);
 	if (!mod->eta_host || !mod->p_host || !mod->post_host)
 		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "result buffers\n");
-	GPU(mc_get_params(mod->gpu, mod->pindex, mod->eta_host, mod->p_host));
-	GPU(mc_get_posterior(mod->gpu, mod->post_host));
-	return NO_ERROR;
+	return gather_state(opt, dat, mod, mod->pindex, mod->eta_host, mod->p_host,
+		mod->post_host);
 }
 
 /* "<path>/<file>" or the -o prefix, followed by a formatted tail */
@@ -55,7 +71,16 @@ static FILE *open_result(options *opt, char *name, size_t len, const char *tail)
  * (write_file.c:369-375, 590-598); done on the device */
 static void partition(data *dat, model *mod)
 {
-	GPU(mc_partition(mod->gpu, dat->I_K, mod->count_K));
+	int *cnt = calloc((size_t)mod->K, sizeof *cnt);
+
+	for (int k = 0; k < mod->K; k++)
+		mod->count_K[k] = 0;
+	for (int r = 0; r < mod->n_gpus; r++) {
+		GPU(mc_partition(mod->gpus[r], dat->I_K + mod->row_first[r], cnt));
+		for (int k = 0; k < mod->K; k++)
+			mod->count_K[k] += cnt[k];
+	}
+	free(cnt);
 }
 
 void partition_admixture(data *dat, model *mod)

@@ -122,3 +122,36 @@ def test_dash_C_is_dash_T(tmp_path):
     g["meta"]["cmd"] = g["meta"]["cmd"].replace("-T", "-C")
     r, ll, fit, states, out = run_cli(tmp_path, g)
     assert fit[(3, 0)]["n_iter"] == g["meta"]["fits"][0]["n_iter"]
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("name", ["admix_em", "admix_s3", "admix_s5", "admix_c_em", "mix_em",
+                                  "mix_s1", "admix_k10", "admix_tetra"])
+def test_cli_two_gpus_matches_reference(tmp_path, name):
+    """--gpus 2: individuals sharded over two devices, NCCL exchange of the
+    sufficient statistics (libmc_comm.so); same parity bars as one device"""
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    g = load_golden(name)
+    r, ll, fit, states, out = run_cli(tmp_path, g, extra=["--gpus", "2"])
+    for rec in g["meta"]["fits"]:
+        K, init = rec["K"], rec["init"]
+        key = "K%d_i%d_" % (K, init)
+        st = states[(K, init, "start")]
+        assert np.max(np.abs(st["eta"] - g[key + "start_eta"])) < 1e-12
+        assert np.max(np.abs(st["p"] - g[key + "start_p"])) < 1e-12
+        ref_ll = g[key + "ll"]
+        got = np.array(ll[(K, init)])
+        assert got.size == ref_ll.size
+        assert np.all(np.abs(got - ref_ll) <= LL_RTOL * np.abs(ref_ll))
+        fi = states[(K, init, "final")]
+        assert np.max(np.abs(fi["eta"] - g[key + "final_eta"])) < PAR_ATOL
+        assert np.max(np.abs(fi["p"] - g[key + "final_p"])) < PAR_ATOL
+        assert np.max(np.abs(fi["posterior"] - g[key + "final_post"])) < PAR_ATOL * 10
