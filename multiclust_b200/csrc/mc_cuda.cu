@@ -997,10 +997,12 @@ extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 		/* eta side: D_ik = eta_ik * A_ik needs only this context's
 		 * individuals; the streaming kernel is done with slot `from`, so
 		 * from == to (in-place EM) is safe */
-		k_admix_eta<<<grid_for(c, c->I, 128), 128, 0, c->stream>>>(c->d_Apart,
+		const int er = eta_rows(K);
+		k_admix_eta<<<(unsigned)std::min<long long>((c->I + er - 1) / er,
+			(long long)c->num_sms * 16), 256, sizeof(double) * er * K, c->stream>>>(c->d_Apart,
 			c->act_tiles, c->act_Ipad, c->I, K, c->d_eta[from],
 			c->per_indiv ? K : 0, c->d_eta[to], c->d_post, c->per_indiv,
-			c->do_proj, c->eta_lb);
+			c->do_proj, c->eta_lb, er);
 		LAUNCH_CHECK("k_admix_eta");
 		if (!c->per_indiv)	/* pooled eta: S_k = sum_i D_ik */
 			if ((rc = reduce_columns(c, c->d_post, c->I, K, xb_S(c)))) return rc;

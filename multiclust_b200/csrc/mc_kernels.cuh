@@ -567,28 +567,45 @@ __global__ void k_project_eta(double *eta, long long rows, int K, double lb)
 /* admixture M-step, eta side (em_alg.c:650-702): A_ik = sum over tiles,
  * D_ik = eta_ik A_ik, eta_ik = D_ik / sum_k D_ik, projection             */
 
+/* individuals per block of k_admix_eta: 32, fewer when K is large */
+static inline int eta_rows(int K) { return K <= 128 ? 32 : (4096 / K > 0 ? 4096 / K : 1); }
+
 __global__ void k_admix_eta(const double *Apart, int n_tiles, long long Ipad,
 	long long I, int K, const double *eta_f, long long eta_stride,
-	double *eta_t, double *D, int per_indiv, int do_proj, double lb)
+	double *eta_t, double *D, int per_indiv, int do_proj, double lb, int ETA_ROWS)
 {
-	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < I;
-		i += (long long)gridDim.x * blockDim.x) {
-		double s = 0.0;
-		for (int k = 0; k < K; k++) {
+	/* one thread per (individual, k) adds the per-tile partial sums: a warp
+	 * reads contiguous runs of Apart; then one thread per individual
+	 * normalises and projects its row */
+	extern __shared__ double rows[];	/* [ETA_ROWS][K] */
+	const int n = ETA_ROWS * K;
+	for (long long i0 = (long long)blockIdx.x * ETA_ROWS; i0 < I;
+		i0 += (long long)gridDim.x * ETA_ROWS) {
+		for (int x = threadIdx.x; x < n; x += blockDim.x) {
+			const long long i = i0 + x / K;
+			if (i >= I)
+				continue;
+			const int k = x % K;
 			double acc = 0.0;
 			for (int t = 0; t < n_tiles; t++)
-				acc += Apart[((size_t)t * Ipad + i) * K + k];
+				acc += Apart[((size_t)t * Ipad + i0) * K + x];
 			const double d = eta_f[(size_t)i * eta_stride + k] * acc;
 			D[(size_t)i * K + k] = d;
-			s += d;
+			rows[x] = d;
 		}
-		if (per_indiv) {
-			double *row = eta_t + (size_t)i * K;
+		__syncthreads();
+		if (per_indiv && threadIdx.x < ETA_ROWS && i0 + threadIdx.x < I) {
+			const double *r = rows + threadIdx.x * K;
+			double *row = eta_t + (size_t)(i0 + threadIdx.x) * K;
+			double s = 0.0;
 			for (int k = 0; k < K; k++)
-				row[k] = D[(size_t)i * K + k] / s;
+				s += r[k];
+			for (int k = 0; k < K; k++)
+				row[k] = r[k] / s;
 			if (do_proj)
 				project_row(row, K, lb);
 		}
+		__syncthreads();
 	}
 }
 
