@@ -80,7 +80,7 @@ def build_host(force=False):
         deps += [os.path.join(INC, f) for f in os.listdir(INC)] + [LIB, COMM]
         if force or not _newer(exe, deps):
             _run([cc] + HOST_CFLAGS + ["-o", exe] + cli_src
-                 + ["-L" + PKG, "-lmc_comm", "-lmc_cuda", "-Wl,-rpath," + PKG, "-lm"])
+                 + ["-L" + PKG, "-lmc_comm", "-lmc_cuda", "-Wl,-rpath," + PKG, "-lm", "-lpthread"])
         out.append(exe)
     return out
 

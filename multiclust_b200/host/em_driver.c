@@ -85,11 +85,21 @@ int stop(options *opt, model *mod, double loglik)
 		fflush(mod->trace);
 	}
 	if (isnan(loglik)) {
+		if (mod->no_exit) {	/* a worker of the sharded multi-start mode */
+			mod->aborted = 1;
+			return mod->stopped = 1;
+		}
 		mmessage(ERROR_MSG, CUSTOM_ERROR, "nan\n");
 		exit(0);
 	}
 	mod->stopped = stop_condition(opt, mod, loglik);
 	if (loglik < mod->logL && !mod->stopped) {
+		if (mod->no_exit) {
+			mod->aborted = 2;
+			mod->abort_ll = loglik;
+			mod->abort_prev = mod->logL;
+			return mod->stopped = 1;
+		}
 		mmessage(ERROR_MSG, CUSTOM_ERROR, "log likelihood decrease (%f < %f; %e)\n",
 			loglik, mod->logL, (loglik - mod->logL) / loglik);
 		exit(0);

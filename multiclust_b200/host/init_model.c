@@ -5,7 +5,7 @@
  * The reference draws from glibc rand() -- one shared stream over all
  * initialisations and all K (multiclust.c:516-531, never reseeded unless -r) --
  * and parity needs the same stream, so the draws are made here on the host in
- * the reference's order.  What is done with them runs on the device:
+ * the reference's order, from the bit-identical generator of mc_rand.h.  What is done with them runs on the device:
  *   admixture: one cluster per allele copy -> hard-assignment counts and the
  *              M-step (mc_init_admixture);
  *   mixture:   K random centre individuals, nearest-centre partition, smoothed
@@ -30,7 +30,7 @@ static int random_initialize_admixture(options *opt, data *dat, model *mod)
 	if (!z)
 		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "allele partition\n");
 	for (size_t x = 0; x < n; x++)
-		z[x] = (uint8_t)((int)rand() % mod->K);
+		z[x] = (uint8_t)(mcr_next(mod->rng) % mod->K);
 	if (mod->n_gpus == 1) {
 		GPU(mc_init_admixture(mod->gpu, mod->tindex, z));
 	} else {
@@ -101,10 +101,10 @@ static int random_initialize_mixture(options *opt, data *dat, model *mod)
 	int *center = malloc(sizeof *center * (size_t)K);
 	double *eta = calloc((size_t)K, sizeof *eta);
 	double *p = calloc((size_t)K * (T ? T : 1), sizeof *p);
-	int *part = dat->I_K;
+	int *part = malloc(sizeof *part * (size_t)I);
 
 	(void)opt;
-	if (!center || !eta || !p)
+	if (!center || !eta || !p || !part)
 		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "initial parameters\n");
 
 	if (K == 1) {
@@ -114,12 +114,12 @@ static int random_initialize_mixture(options *opt, data *dat, model *mod)
 		/* K distinct random centres, re-drawing on collision (205-217) */
 		for (int k = 0; k < K; k++) {
 			int again;
-			center[k] = (int)(rand() % I);
+			center[k] = mcr_next(mod->rng) % I;
 			do {
 				again = 0;
 				for (int j = 0; j < k; j++)
 					if (center[k] == center[j]) {
-						center[k] = (int)(rand() % I);
+						center[k] = mcr_next(mod->rng) % I;
 						again = 1;
 						break;
 					}
@@ -183,6 +183,7 @@ static int random_initialize_mixture(options *opt, data *dat, model *mod)
 	free(center);
 	free(eta);
 	free(p);
+	free(part);
 	return NO_ERROR;
 }
 

@@ -24,6 +24,10 @@
 #include "mc_format.h"
 #include "multiclust.h"
 
+/* the initialisers' random stream: glibc's rand() state after no srand()
+ * call equals srand(1) */
+static mcr_state g_rng;
+
 static const char *accel_abbrev[NUM_ACCELERATION_METHODS] = { "EM", "S1", "S2", "S3", "Q" };
 static const char *accel_names[NUM_ACCELERATION_METHODS] = {
 	"No acceleration", "SQUAREM version 1", "SQUAREM version 2",
@@ -125,6 +129,8 @@ int make_model(model **out)
 		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "model object\n");
 	mod->K = 1;
 	mod->max_logL = -INFINITY;
+	mcr_seed(&g_rng, 1);
+	mod->rng = &g_rng;
 	*out = mod;
 	return NO_ERROR;
 }
@@ -206,6 +212,7 @@ void fprint_usage(FILE *fp, const char *cmd)
 "device\n"
 "  --device <d>  first CUDA device ordinal (default 0)\n"
 "  --gpus <n>    shard the individuals of one fit over n devices (NCCL exchange)\n"
+"  --shard-fits  with --gpus: deal whole fits (K, initialisation) to the devices\n"
 "  --trace <f>   write every log likelihood at full precision to <f>\n"
 "  --dump <pre>  binary parameters before / after every fit to <pre>.K*.init*.bin\n"
 "  --parse-only <f>  read and recode the data, write it as MCB1 to <f>, stop\n", cmd);
@@ -401,9 +408,13 @@ int parse_options(options *opt, data *dat, int argc, const char **argv)
 			if (read_int_arg(argc, argv, ++i, 0, &tmp))
 				goto bad_arg;
 			opt->seed = (unsigned int)tmp;
-			srand(opt->seed);
+			mcr_seed(&g_rng, opt->seed);	/* srand(seed), multiclust.c:1595 */
 			break;
 		case 's':
+			if (!strncmp(name, "sh", 2)) {	/* --shard-fits */
+				opt->shard_fits = 1;
+				break;
+			}
 			if (!strncmp(name, "si", 2))
 				return unsupported(argv[i], "data simulation");
 			if (read_int_arg(argc, argv, ++i, 0, &opt->accel_scheme))
@@ -561,6 +572,106 @@ static int dump_state(options *opt, data *dat, model *mod, int init, const char 
 	return NO_ERROR;
 }
 
+/* bookkeeping of one finished fit (reference multiclust.c:534-627): counters,
+ * best-so-far test, result files, the per-initialisation stdout line.
+ * `write_best` writes the files of the current fit (it is called only when the
+ * fit improves on everything seen so far, all K included) */
+static int record_fit(options *opt, data *dat, model *mod, int i, int bootstrap,
+	int (*write_best)(options *, data *, model *, void *), void *ctx)
+{
+	int err;
+
+	if (mod->converged)
+		mod->ever_converged = 1;
+	if (mod->converged || (!mod->n_init && mod->time_stop)) {
+		mod->n_total_iter += mod->n_iter;
+		if (mod->n_max_iter < mod->n_iter)
+			mod->n_max_iter = mod->n_iter;
+		mod->n_init++;
+	}
+	if (mod->converged && converged(opt, mod, mod->first_max_logL)) {
+		mod->n_maxll_times++;
+	} else if (mod->converged && mod->logL > mod->first_max_logL) {
+		mod->n_maxll_times = 1;
+		mod->first_max_logL = mod->logL;
+		mod->n_maxll_init = mod->n_init;
+	}
+	if (mod->trace)
+		fprintf(mod->trace, "fit %d %d logL=%.17g converged=%d stopped=%d "
+			"iter_stop=%d n_iter=%d pindex=%d\n", mod->K, i, mod->logL,
+			mod->converged, mod->stopped, mod->iter_stop, mod->n_iter,
+			mod->pindex);
+	if (mod->logL > mod->max_logL) {
+		mod->max_logL = mod->logL;
+		mod->aic = aic(mod);
+		mod->bic = bic(dat, mod);
+		if (!bootstrap && opt->write_files && (err = write_best(opt, dat, mod, ctx)))
+			return err;
+	}
+	if (!bootstrap && opt->verbosity > QUIET && opt->write_files)
+		fprintf(stdout, "K = %d, initialization = %d: %f (%s) in %3d "
+			"iterations, %02d:%02d:%02d (%f; %d), seed: %u\n",
+			mod->K, i, mod->logL,
+			mod->converged ? "converged" : "not converged",
+			mod->n_iter, (int)(mod->seconds_run / 3600),
+			(int)((((int)mod->seconds_run) % 3600) / 60),
+			(((int)mod->seconds_run) % 60), mod->max_logL,
+			mod->n_maxll_times, opt->seed);
+	return NO_ERROR;
+}
+
+/* the result files of a fit whose state is in mod->eta_host / p_host /
+ * post_host, dat->I_K and mod->count_K (write_file.c:203-732) */
+static int write_result_files(options *opt, data *dat, model *mod)
+{
+	int err;
+
+	if (opt->admixture) {
+		if ((err = write_file_detail(opt, dat, mod))
+			|| (err = popq_admix(opt, dat, mod))
+			|| (err = indivq_admix(opt, dat, mod)))
+			return err;
+	} else {
+		if ((err = write_file_detail(opt, dat, mod))
+			|| (err = popq_mix(opt, dat, mod))
+			|| (err = indivq_mix(opt, dat, mod)))
+			return err;
+	}
+	return NO_ERROR;
+}
+
+/* sequential mode: the fit's state is still on the device */
+static int write_best_from_device(options *opt, data *dat, model *mod, void *ctx)
+{
+	int err;
+
+	(void)ctx;
+	if ((err = fetch_results(opt, dat, mod)))
+		return err;
+	if (opt->admixture)
+		partition_admixture(dat, mod);
+	else
+		partition_mixture(dat, mod);
+	return write_result_files(opt, dat, mod);
+}
+
+int record_fit_public(options *opt, data *dat, model *mod, int i,
+	int (*write_best)(options *, data *, model *, void *), void *ctx)
+{
+	return record_fit(opt, dat, mod, i, 0, write_best, ctx);
+}
+
+int write_result_files_public(options *opt, data *dat, model *mod)
+{
+	return write_result_files(opt, dat, mod);
+}
+
+int dump_state_public(options *opt, data *dat, model *mod, int init, const char *tag,
+	int slot)
+{
+	return dump_state(opt, dat, mod, init, tag, slot);
+}
+
 /* reference multiclust.c:471-660 */
 int maximize_likelihood(options *opt, data *dat, model *mod, int bootstrap)
 {
@@ -591,58 +702,8 @@ int maximize_likelihood(options *opt, data *dat, model *mod, int bootstrap)
 		if (opt->dump_prefix && (err = dump_state(opt, dat, mod, i, "final", mod->pindex)))
 			return err;
 
-		if (mod->converged)
-			mod->ever_converged = 1;
-		if (mod->converged || (!mod->n_init && mod->time_stop)) {
-			mod->n_total_iter += mod->n_iter;
-			if (mod->n_max_iter < mod->n_iter)
-				mod->n_max_iter = mod->n_iter;
-			mod->n_init++;
-		}
-		if (mod->converged && converged(opt, mod, mod->first_max_logL)) {
-			mod->n_maxll_times++;
-		} else if (mod->converged && mod->logL > mod->first_max_logL) {
-			mod->n_maxll_times = 1;
-			mod->first_max_logL = mod->logL;
-			mod->n_maxll_init = mod->n_init;
-		}
-		if (mod->trace)
-			fprintf(mod->trace, "fit %d %d logL=%.17g converged=%d stopped=%d "
-				"iter_stop=%d n_iter=%d pindex=%d\n", mod->K, i, mod->logL,
-				mod->converged, mod->stopped, mod->iter_stop, mod->n_iter,
-				mod->pindex);
-
-		if (mod->logL > mod->max_logL) {
-			mod->max_logL = mod->logL;
-			mod->aic = aic(mod);
-			mod->bic = bic(dat, mod);
-			if (!bootstrap && opt->write_files) {
-				if ((err = fetch_results(opt, dat, mod)))
-					return err;
-				if (opt->admixture) {
-					partition_admixture(dat, mod);
-					if ((err = write_file_detail(opt, dat, mod))
-						|| (err = popq_admix(opt, dat, mod))
-						|| (err = indivq_admix(opt, dat, mod)))
-						return err;
-				} else {
-					partition_mixture(dat, mod);
-					if ((err = write_file_detail(opt, dat, mod))
-						|| (err = popq_mix(opt, dat, mod))
-						|| (err = indivq_mix(opt, dat, mod)))
-						return err;
-				}
-			}
-		}
-		if (!bootstrap && opt->verbosity > QUIET && opt->write_files)
-			fprintf(stdout, "K = %d, initialization = %d: %f (%s) in %3d "
-				"iterations, %02d:%02d:%02d (%f; %d), seed: %u\n",
-				mod->K, i, mod->logL,
-				mod->converged ? "converged" : "not converged",
-				mod->n_iter, (int)(mod->seconds_run / 3600),
-				(int)((((int)mod->seconds_run) % 3600) / 60),
-				(((int)mod->seconds_run) % 60), mod->max_logL,
-				mod->n_maxll_times, opt->seed);
+		if ((err = record_fit(opt, dat, mod, i, bootstrap, write_best_from_device, NULL)))
+			return err;
 		if (mod->K == 1)
 			break;
 		if (mod->time_stop)
@@ -781,6 +842,12 @@ int main(int argc, const char **argv)
 	if (opt->trace_file && !(mod->trace = fopen(opt->trace_file, "w"))) {
 		err = message(stderr, __FILE__, __func__, __LINE__, ERROR_MSG,
 			FILE_OPEN_ERROR, opt->trace_file);
+		goto done;
+	}
+	if (opt->shard_fits && opt->n_gpus > 1) {
+		err = estimate_model_sharded(opt, dat, mod);
+		if (!err && opt->parallel)
+			printf("%f\n", mod->max_logL);
 		goto done;
 	}
 	if ((err = upload_data(opt, dat, mod)))

@@ -24,6 +24,7 @@
 
 #include "mc_cuda.h"
 #include "mc_comm.h"
+#include "mc_rand.h"
 
 /* error codes: same numbering as reference message.h:17-42 */
 enum {
@@ -93,6 +94,9 @@ struct _options {
 	const char *trace_file;		/* --trace: every log likelihood, %.17g */
 	const char *dump_prefix;	/* --dump: binary parameters per fit */
 	const char *parse_only;		/* --parse-only: MCB1 file to write */
+	int shard_fits;			/* --shard-fits: with --gpus N, deal whole fits
+					 * (K, initialisation) to the devices instead of
+					 * sharding the individuals of one fit */
 };
 
 struct _indiv {
@@ -149,6 +153,11 @@ struct _model {
 	/* host copies fetched for the writers */
 	double *eta_host, *p_host, *post_host;
 	FILE *trace;			/* --trace */
+	mcr_state *rng;			/* the rand() stream of the initialisers */
+	int no_exit;			/* 1: record the reference's exit(0) conditions in
+					 * `aborted` (1 NaN, 2 decrease) instead of exiting */
+	int aborted;
+	double abort_ll, abort_prev;
 };
 
 /* ---- objects (reference multiclust.c:902-1380) ---- */
@@ -165,6 +174,13 @@ int allocate_model_for_k(options *opt, model *mod, data *dat);
 int estimate_model(options *opt, data *dat, model *mod, int bootstrap);
 int maximize_likelihood(options *opt, data *dat, model *mod, int bootstrap);
 void print_model_state(options *opt, data *dat, model *mod, int diff, int newline);
+/* --gpus N --shard-fits: whole fits dealt to the devices (shard_fits.c) */
+int estimate_model_sharded(options *opt, data *dat, model *mod);
+int record_fit_public(options *opt, data *dat, model *mod, int i,
+	int (*write_best)(options *, data *, model *, void *), void *ctx);
+int write_result_files_public(options *opt, data *dat, model *mod);
+int dump_state_public(options *opt, data *dat, model *mod, int init, const char *tag,
+	int slot);
 void fprint_usage(FILE *fp, const char *cmd);
 
 /* ---- input (reference read_file.c) ---- */

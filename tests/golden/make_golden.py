@@ -65,6 +65,10 @@ CASES = [
     # K sweep with several initialisations: one shared rand() stream
     ("admix_sweep", dict(I=30, L=20, K=3, jmax=4, miss=200, P=2),
      "-a -1 2 -2 4 -T 6 -E 1e-30 -n 2"),
+    # mixture sweep from K=1 (one fit only, multiclust.c:630-631) on few
+    # individuals, so the centre draws collide and are re-drawn (rnd_init.c:205-217)
+    ("mix_sweep", dict(I=12, L=30, K=3, jmax=4, miss=200, P=2),
+     "-1 1 -2 6 -n 3"),
 ]
 
 
@@ -171,7 +175,10 @@ def main():
     orc.build()
     from multiclust_b200 import build as mcbuild
     mcbuild.build_host()
+    only = set(sys.argv[1:])  # optional: names of the cases to (re)generate
     for name, gen, cmd in CASES:
+        if only and name not in only:
+            continue
         meta = make_case(name, gen, cmd, HERE)
         if not meta["fits"]:
             sys.exit("%s: the reference aborted (exit(0) on a log likelihood "

@@ -155,3 +155,44 @@ def test_cli_two_gpus_matches_reference(tmp_path, name):
         assert np.max(np.abs(fi["eta"] - g[key + "final_eta"])) < PAR_ATOL
         assert np.max(np.abs(fi["p"] - g[key + "final_p"])) < PAR_ATOL
         assert np.max(np.abs(fi["posterior"] - g[key + "final_post"])) < PAR_ATOL * 10
+
+
+@pytest.mark.parametrize("name", ["admix_sweep", "mix_sweep", "admix_s1", "mix_em", "admix_c_em"])
+def test_cli_shard_fits_matches_reference(tmp_path, name):
+    """--gpus 2 --shard-fits: whole fits (K, initialisation) dealt to two
+    devices (host/shard_fits.c).  Every fit starts from the reference's rand()
+    stream position, so initial parameters, traces and final parameters equal
+    the sequential reference's; stdout lines and result files equal those of
+    the one-device run of this program."""
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    g = load_golden(name)
+    a = tmp_path / "sharded"
+    b = tmp_path / "sequential"
+    a.mkdir(), b.mkdir()
+    r, ll, fit, states, out = run_cli(a, g, extra=["--gpus", "2", "--shard-fits"])
+    assert len(fit) == len(g["meta"]["fits"])
+    for rec in g["meta"]["fits"]:
+        K, init = rec["K"], rec["init"]
+        key = "K%d_i%d_" % (K, init)
+        st = states[(K, init, "start")]
+        assert np.max(np.abs(st["eta"] - g[key + "start_eta"])) < 1e-12
+        assert np.max(np.abs(st["p"] - g[key + "start_p"])) < 1e-12
+        ref_ll = g[key + "ll"]
+        got = np.array(ll[(K, init)])
+        assert got.size == ref_ll.size
+        assert np.all(np.abs(got - ref_ll) <= LL_RTOL * np.abs(ref_ll))
+        f = fit[(K, init)]
+        for field in ("n_iter", "converged", "iter_stop"):
+            assert f[field] == rec[field], field
+        fi = states[(K, init, "final")]
+        assert np.max(np.abs(fi["eta"] - g[key + "final_eta"])) < PAR_ATOL
+        assert np.max(np.abs(fi["p"] - g[key + "final_p"])) < PAR_ATOL
+    r1, ll1, fit1, states1, out1 = run_cli(b, g)
+    # the replayed bookkeeping: same lines in the same order (times blanked)
+    import re
+    blank = lambda s: re.sub(r"\d\d:\d\d:\d\d", "hh:mm:ss", s).replace(str(a), "").replace(str(b), "")
+    assert blank(r.stdout) == blank(r1.stdout)
+    assert sorted(os.listdir(out)) == sorted(os.listdir(out1))
+    for fn in os.listdir(out):
+        assert open(out / fn).read() == open(out1 / fn).read(), fn
