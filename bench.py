@@ -381,7 +381,9 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_source": peak_src,
-                "kernel": "admix2_kernel<MODE_EM> (two-pass)" if plan.get("two_pass")
+                "kernel": "admix3_kernel<MODE_EM> (two-pass, rotation gather)"
+                if plan.get("two_pass") == 2
+                else "admix2_kernel<MODE_EM> (two-pass)" if plan.get("two_pass")
                 else "tile_kernel<MODE_ADMIX_EM>",
                 "kernel_ms": k_ms, "kernel_launches_timed": nk,
                 "algorithmic_bytes_per_launch": alg,

@@ -1,0 +1,484 @@
+/*
+ * mc_admix3.cuh -- two-pass admixture kernel, third mapping: 512 individuals
+ * per tile, bank-conflict-free gathers by construction.
+ *
+ * The fused E+M step of the admixture model (em_alg.c:325-433, 604-725) is,
+ * per allele copy (i, l, a) with allele j:
+ *     tmp = sum_k eta_ik p_klj,  w = c / tmp,  ll += c log tmp,
+ *     A_ik += p_klj w   (-> D_ik = eta_ik A_ik,  the eta update)
+ *     G_klj += eta_ik w (-> N_klj = p_klj G_klj, the p update)
+ * Measured on B200 (tools/lds_probe3.cu, tools/shfl_probe.cu): the SM delivers
+ * 128 B/clk from shared memory whatever the access width, multi-lane broadcast
+ * does not make a 64-bit load cheaper, SHFL shares the same data path, and
+ * FP64 issues 64 FMAs/clk.  Every copy needs one K-vector gathered per pass
+ * (2 x 8K bytes against 3K FMAs), so the path is bound by the shared-memory
+ * pipe and the kernel is built around wavefront counts:
+ *   pass 1  thread <-> individual (eta_i, A_i in registers for the whole sweep
+ *           over the CTA's loci); p is staged k-major, p_s[k][row], so the 32
+ *           lanes of a warp -- 32 individuals at the SAME locus -- read one
+ *           8-byte word each from <= J_l consecutive words: 2 wavefronts per
+ *           LDS.64, the minimum.  w goes to shared memory, w_s[copy][i].
+ *   pass 2  thread <-> (allele column, segment); a column gets a number of
+ *           lanes proportional to its allele count, its sorted entry list is
+ *           dealt round-robin to them.  eta rows live in shared memory padded
+ *           to 128 bytes = 8 pieces of 16 bytes; lane m reads piece (m + s) % 8
+ *           in step s, so the 8 lanes of every quarter warp always touch 8
+ *           different bank groups whichever rows they read: 4 wavefronts per
+ *           LDS.128, the minimum, for ANY entry-to-lane assignment.  The
+ *           accumulators are held in rotated order (static register indices)
+ *           and un-rotated when the lane writes its partial sums.
+ *   fold    the lanes' partial sums go through a shared scratch; thread
+ *           (column, piece) adds the column's partials in lane order and
+ *           updates the CTA's accumulator B_s: no atomics, fixed order.
+ * Three barriers per (512 individuals x 8 copies) tile.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define A3_THREADS 512
+#define A3_IT 512		/* individuals per tile = pass-1 threads */
+#define A3_IDLE 1023u		/* lane map: no column */
+
+struct Admix3Args {
+	int K;
+	int n_itiles, n_ltiles, n_lchunks, n_ichunks, n_units;
+	long long I, Ipad, T;
+	int L, ncolmax, max_chunk_rows, PR;	/* PR: pitch of p_s rows (doubles) */
+	/* per locus tile (static) */
+	const int *lt_ncol;		/* [n_ltiles] real allele columns */
+	const unsigned short *colinfo;	/* [n_ltiles][ncolmax] locus_in_tile << 8 | allele */
+	const unsigned *lanemap;	/* [n_ltiles][A3_THREADS] pass-2 lane: col | seg << 10 |
+					 * lanes << 19 | locus_in_tile << 29 */
+	const uint2 *foldmap;		/* [n_ltiles][A3_THREADS] fold thread: x = first lane |
+					 * lanes << 16 (0: idle), y = row in chunk | piece << 24 */
+	const int *lc_first;		/* [n_lchunks + 1] first locus tile of each chunk */
+	const int *off;			/* [L + 1] prefix sums of J */
+	/* data */
+	const unsigned char *codes;	/* [n_itiles][n_ltiles][A3_THREADS][8] */
+	const unsigned short *csc;	/* [n_itiles][n_ltiles][cap] sorted entries */
+	const unsigned short *colstart;	/* [n_itiles][n_ltiles][csw], csw = ncolmax + 1
+					 * rounded up to a multiple of 8 */
+	int cap;			/* entries per tile: A3_IT * 8 */
+	/* parameters */
+	const double *p, *eta;
+	long long eta_stride;
+	/* outputs */
+	double *Apart;			/* [n_lchunks][Ipad][K] */
+	double *Npart;			/* [n_ichunks][K*T] */
+	double *llpart;			/* [n_units] */
+};
+
+/* ---------------------------------------------------------------------- */
+/* one-time layout builders                                                 */
+
+/* natural [I][L][P] codes -> 8 bytes per (tile, individual): LT = 8 / PP loci
+ * x PP copies, thread-major inside a tile */
+__global__ void k3_build_codes(const unsigned char *nat, unsigned char *codes,
+	long long I, int L, int P, int PP, int n_itiles, int n_ltiles)
+{
+	const int LT = 8 / PP;
+	const long long n = (long long)n_itiles * n_ltiles * A3_THREADS;
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		const int t = (int)(x % A3_THREADS);
+		const long long r = x / A3_THREADS;
+		const int lt = (int)(r % n_ltiles);
+		const long long i = (r / n_ltiles) * A3_IT + t;
+		unsigned char b[8];
+		for (int q = 0; q < 8; q++) {
+			const int l = lt * LT + q / PP, a = q % PP;
+			b[q] = (i < I && l < L && a < P) ? nat[((size_t)i * L + l) * P + a] : 255;
+		}
+		*reinterpret_cast<uint2 *>(codes + (size_t)x * 8) = *reinterpret_cast<uint2 *>(b);
+	}
+}
+
+/* allele-sorted entry lists of one (itile, ltile): for every real allele column
+ * in `colinfo` order, the individuals carrying it in ascending order, one entry
+ * per (individual, allele): i | first copy << 9 | (count - 1) << 12 */
+__global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
+	int ncolmax, int cap, const int *lt_ncol, const unsigned short *colinfo,
+	unsigned short *csc, unsigned short *colstart)
+{
+	extern __shared__ unsigned char sm3[];
+	unsigned char *cd = sm3;				/* [A3_IT][8] */
+	int *cnt = reinterpret_cast<int *>(sm3 + (size_t)A3_IT * 8);
+	const int lt = blockIdx.x % n_ltiles;
+	const int ncol = lt_ncol[lt];
+	const unsigned short *ci = colinfo + (size_t)lt * ncolmax;
+	unsigned short *out = csc + (size_t)blockIdx.x * cap;
+	const int csw = ((ncolmax + 1 + 7) / 8) * 8;
+	unsigned short *cs = colstart + (size_t)blockIdx.x * csw;
+	const uint2 *src = reinterpret_cast<const uint2 *>(codes) + (size_t)blockIdx.x * A3_THREADS;
+
+	for (int x = threadIdx.x; x < A3_IT; x += blockDim.x)
+		reinterpret_cast<uint2 *>(cd)[x] = src[x];
+	__syncthreads();
+	for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+		const int ll = ci[c] >> 8, j = ci[c] & 0xff;
+		int n = 0;
+		for (int ii = 0; ii < A3_IT; ii++) {
+			bool has = false;
+			for (int a = 0; a < PP; a++)
+				has |= cd[ii * 8 + ll * PP + a] == j;
+			n += has;
+		}
+		cnt[c] = n;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int acc = 0;
+		for (int c = 0; c < ncol; c++) {
+			const int n = cnt[c];
+			cnt[c] = acc;
+			cs[c] = (unsigned short)acc;
+			acc += n;
+		}
+		for (int c = ncol; c < csw; c++)
+			cs[c] = (unsigned short)acc;
+	}
+	__syncthreads();
+	for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+		const int ll = ci[c] >> 8, j = ci[c] & 0xff;
+		int pos = cnt[c];
+		for (int ii = 0; ii < A3_IT; ii++) {
+			int n = 0, first = 0;
+			for (int a = PP - 1; a >= 0; a--)
+				if (cd[ii * 8 + ll * PP + a] == j) {
+					n++;
+					first = a;
+				}
+			if (n)
+				out[pos++] = (unsigned short)(ii | first << 9 | (n - 1) << 12);
+		}
+	}
+}
+
+/* ---------------------------------------------------------------------- */
+
+__device__ __forceinline__ void a3_cp_async16(void *smem_dst, const void *gsrc)
+{
+	const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void a3_cp_async8(void *smem_dst, const void *gsrc)
+{
+	const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void a3_cp_async_wait()
+{
+	asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+/* pieces of 16 bytes per eta row in shared memory */
+template <int KP> struct A3Row { static constexpr int NP = KP <= 4 ? 4 : 8; };
+
+/* bytes of dynamic shared memory; the host planner uses the same formula */
+static inline size_t a3_smem_bytes(int KP, bool em, int max_chunk_rows, int PR,
+	int ncolmax, int cap)
+{
+	const int KR = 2 * KP, NP = KP <= 4 ? 4 : 8;
+	size_t d = (size_t)KR * PR + 16;
+	if (em)
+		d += (size_t)max_chunk_rows * KR + (size_t)A3_IT * NP * 2 + 8 * (size_t)A3_IT
+			+ (size_t)A3_THREADS * KR;
+	return d * sizeof(double)
+		+ ((em ? (size_t)cap : 0) + (size_t)(ncolmax + 1 + 7) / 8 * 8) * sizeof(unsigned short)
+		+ 16 * sizeof(int);
+}
+
+/* lane map word: col | seg << 10 | lanes << 19 | locus_in_tile << 29 */
+#define A3_LM_COL(x) ((x) & 1023u)
+#define A3_LM_SEG(x) (((x) >> 10) & 511u)
+#define A3_LM_S(x) (((x) >> 19) & 1023u)
+#define A3_LM_LOC(x) ((x) >> 29)
+
+/* MODE 0: E+M step, MODE 1: log likelihood only */
+template <int KP, int PP, int MODE>
+__global__ void __launch_bounds__(A3_THREADS, 1) admix3_kernel(const Admix3Args a)
+{
+	constexpr int KR = 2 * KP;
+	constexpr int NP = A3Row<KP>::NP;
+	constexpr int LT = 8 / PP;
+	constexpr bool EM = (MODE == 0);
+	extern __shared__ double smem[];
+	const int t = threadIdx.x, lane = t & 31, m = t & (NP - 1);
+	const int PR = a.PR;
+	const int csw = ((a.ncolmax + 1 + 7) / 8) * 8;	/* colstart row, 16-byte multiple */
+
+	double *B_s = smem;						/* [max_chunk_rows][KR] */
+	double *p_s = B_s + (EM ? (size_t)a.max_chunk_rows * KR : 0);	/* [KR][PR] */
+	double *eta_s = p_s + (size_t)KR * PR;				/* [A3_IT][2 NP] */
+	double *w_s = eta_s + (EM ? (size_t)A3_IT * NP * 2 : 0);	/* [8][A3_IT] */
+	double *part_s = w_s + (EM ? 8 * (size_t)A3_IT : 0);		/* [A3_THREADS][KR] */
+	double *red = part_s + (EM ? (size_t)A3_THREADS * KR : 0);	/* [16] */
+	unsigned short *csc_s = reinterpret_cast<unsigned short *>(red + 16);	/* [cap] */
+	unsigned short *cst_s = csc_s + (EM ? a.cap : 0);		/* [csw] */
+	int *rb_s = reinterpret_cast<int *>(cst_s + csw);		/* [2][8] row bases */
+
+	for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+		const int c = u % a.n_lchunks, r = u / a.n_lchunks;
+		const int lt0 = a.lc_first[c], lt1 = a.lc_first[c + 1];
+		const long long it0 = (long long)a.n_itiles * r / a.n_ichunks;
+		const long long it1 = (long long)a.n_itiles * (r + 1) / a.n_ichunks;
+		const int l0 = lt0 * LT;
+		const int lend = lt1 * LT < a.L ? lt1 * LT : a.L;
+		const int row0 = a.off[l0];
+		const int chunk_rows = a.off[lend] - row0;
+		double prod = 1.0, ll_slow = 0.0;
+		long long esum = 0;
+		double e[KR], A[EM ? KR : 1];
+
+		__syncthreads();
+		if (EM)
+			for (int x = t; x < chunk_rows * KR; x += A3_THREADS)
+				B_s[x] = 0.0;
+
+		/* what the NEXT tile needs, fetched one tile ahead: the thread's
+		 * 8 allele codes and its pass-2 / fold assignments in registers,
+		 * the p rows and the entry lists by cp.async */
+		uint2 cw_n = make_uint2(0xffffffffu, 0xffffffffu), fm_n = make_uint2(0u, 0u);
+		unsigned lm_n = A3_IDLE;
+		auto fetch_regs = [&](long long it, int lt) {
+			const size_t tix = (size_t)it * a.n_ltiles + lt;
+			cw_n = __ldg(reinterpret_cast<const uint2 *>(a.codes) + tix * A3_THREADS + t);
+			if (EM) {
+				lm_n = __ldg(a.lanemap + (size_t)lt * A3_THREADS + t);
+				fm_n = __ldg(a.foldmap + (size_t)lt * A3_THREADS + t);
+			}
+		};
+		auto stage_p = [&](int lt, int buf) {
+			const int lf = lt * LT;
+			const int lnext = lf + LT < a.L ? lf + LT : a.L;
+			const int trow0 = a.off[lf];
+			const int tile_rows = a.off[lnext] - trow0;
+			for (int x = t; x < tile_rows * KR; x += A3_THREADS) {
+				const int k = x / tile_rows, row = x - k * tile_rows;
+				if (k < a.K)
+					a3_cp_async8(p_s + (size_t)k * PR + row,
+						a.p + (size_t)k * a.T + trow0 + row);
+				else
+					p_s[(size_t)k * PR + row] = 0.0;
+			}
+			if (t < LT)
+				rb_s[buf * 8 + t] = lf + t < a.L ? a.off[lf + t] - trow0 : 0;
+		};
+		auto stage_lists = [&](long long it, int lt) {
+			const size_t tix = (size_t)it * a.n_ltiles + lt;
+			if (t * 8 < a.cap)
+				a3_cp_async16(csc_s + t * 8, a.csc + tix * a.cap + t * 8);
+			if (t * 8 < csw)
+				a3_cp_async16(cst_s + t * 8, a.colstart + tix * csw + t * 8);
+		};
+
+		fetch_regs(it0, lt0);
+		stage_p(lt0, 0);
+		if (EM)
+			stage_lists(it0, lt0);
+		int buf = 0;
+
+		for (long long it = it0; it < it1; it++) {
+			const long long i = it * A3_IT + t;
+			const long long ic = i < a.I ? i : a.I - 1;
+
+#pragma unroll
+			for (int k = 0; k < KR; k++)
+				e[k] = k < a.K ? __ldg(a.eta + (size_t)ic * a.eta_stride + k) : 0.0;
+			if (EM) {
+#pragma unroll
+				for (int k = 0; k < KR; k++)
+					A[k] = 0.0;
+				/* every reader of the previous tile's eta rows is past the
+				 * barrier that follows pass 2 */
+				double2 *dst = reinterpret_cast<double2 *>(eta_s + (size_t)t * NP * 2);
+#pragma unroll
+				for (int pc = 0; pc < NP; pc++)
+					dst[pc] = pc < KP ? make_double2(e[2 * pc], e[2 * pc + 1])
+						: make_double2(0.0, 0.0);
+			}
+
+			for (int lt = lt0; lt < lt1; lt++, buf ^= 1) {
+				const uint2 cw = cw_n, fm = fm_n;
+				const unsigned lm = lm_n;
+				const bool last = lt + 1 == lt1;
+				const long long itn = last ? it + 1 : it;
+				const int ltn = last ? lt0 : lt + 1;
+				const bool more = itn < it1;
+				const int *rb = rb_s + buf * 8;
+
+				if (more)
+					fetch_regs(itn, ltn);
+				a3_cp_async_wait();
+				__syncthreads();
+
+				/* ---- pass 1: tmp, w, A, log likelihood ---- */
+				double pr[2][KR];
+				bool valid[2];
+				auto load_row = [&](int q, int z) {
+					const unsigned code = ((q < 4 ? cw.x : cw.y) >> ((q & 3) * 8)) & 0xffu;
+					valid[z] = code != 255u;
+					/* a missing copy reads the locus's first row: same
+					 * bank window as the lanes that carry an allele */
+					const int row = rb[q / PP] + (valid[z] ? (int)code : 0);
+#pragma unroll
+					for (int k = 0; k < KR; k++)
+						pr[z][k] = p_s[(size_t)k * PR + row];
+				};
+				load_row(0, 0);
+				double tprev = 1.0;
+#pragma unroll
+				for (int q = 0; q < 8; q++) {
+					const int z = q & 1;
+					if (q + 1 < 8)
+						load_row(q + 1, z ^ 1);
+					double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+					for (int kp = 0; kp < KP; kp++) {
+						s0 = fma(e[2 * kp], pr[z][2 * kp], s0);
+						s1 = fma(e[2 * kp + 1], pr[z][2 * kp + 1], s1);
+					}
+					const double tmp = valid[z] ? s0 + s1 : 1.0;
+					if (EM) {
+						const double wgt = valid[z] ? mc_rcp(tmp) : 0.0;
+#pragma unroll
+						for (int k = 0; k < KR; k++)
+							A[k] = fma(pr[z][k], wgt, A[k]);
+						w_s[(size_t)q * A3_IT + t] = wgt;
+					}
+					if (z == 0) {
+						tprev = tmp;
+					} else {
+						/* log of a product of mantissas, exponents summed as
+						 * integers: one log per unit instead of per copy */
+						const int h0 = __double2hiint(tprev), h1 = __double2hiint(tmp);
+						const unsigned bad = ((unsigned)(h0 - 0x00100000) >= 0x7fe00000u)
+							| ((unsigned)(h1 - 0x00100000) >= 0x7fe00000u);
+						if (!bad) {
+							prod *= __hiloint2double((h0 & 0x000fffff) | 0x3ff00000,
+								__double2loint(tprev));
+							prod *= __hiloint2double((h1 & 0x000fffff) | 0x3ff00000,
+								__double2loint(tmp));
+							const int hp = __double2hiint(prod);
+							esum += (h0 >> 20) + (h1 >> 20) + (hp >> 20) - 3 * 1023;
+							prod = __hiloint2double((hp & 0x000fffff) | 0x3ff00000,
+								__double2loint(prod));
+						} else {
+							ll_slow += log(tprev) + log(tmp);
+						}
+					}
+				}
+				__syncthreads();
+				/* p_s is free: the next tile's p rows travel during pass 2 */
+				if (more)
+					stage_p(ltn, buf ^ 1);
+				if (!EM)
+					continue;
+
+				/* ---- pass 2: G_lj += eta_i w over the lane's entries ---- */
+				double g[2 * NP];
+#pragma unroll
+				for (int k = 0; k < 2 * NP; k++)
+					g[k] = 0.0;
+				if (A3_LM_COL(lm) != A3_IDLE) {
+					const int S = (int)A3_LM_S(lm);
+					const unsigned col = A3_LM_COL(lm);
+					const double *wb = w_s + (size_t)(A3_LM_LOC(lm) * PP) * A3_IT;
+					const int ce = cst_s[col + 1];
+					int x = cst_s[col] + (int)A3_LM_SEG(lm);
+					const char *eb = reinterpret_cast<const char *>(eta_s);
+					/* ids and weights are fetched one trip ahead */
+					unsigned ent = x < ce ? csc_s[x] : 0u;
+					double w = x < ce ? wb[((ent >> 9) & 7) * A3_IT + (ent & 511)]
+						* (double)((ent >> 12) + 1) : 0.0;
+					while (x < ce) {
+						const char *row = eb + (size_t)(ent & 511) * (NP * 16);
+						const double wc = w;
+						x += S;
+						ent = x < ce ? csc_s[x] : 0u;
+						double2 v[NP];
+#pragma unroll
+						for (int s = 0; s < NP; s++)
+							v[s] = *reinterpret_cast<const double2 *>(
+								row + (((m + s) & (NP - 1)) << 4));
+						w = x < ce ? wb[((ent >> 9) & 7) * A3_IT + (ent & 511)]
+							* (double)((ent >> 12) + 1) : 0.0;
+#pragma unroll
+						for (int s = 0; s < NP; s++) {
+							g[2 * s] = fma(v[s].x, wc, g[2 * s]);
+							g[2 * s + 1] = fma(v[s].y, wc, g[2 * s + 1]);
+						}
+					}
+				}
+				/* the lane's partial sums, un-rotated */
+#pragma unroll
+				for (int s = 0; s < NP; s++) {
+					const int pc = (m + s) & (NP - 1);
+					if (pc < KP)
+						*reinterpret_cast<double2 *>(part_s + (size_t)t * KR + 2 * pc)
+							= make_double2(g[2 * s], g[2 * s + 1]);
+				}
+				__syncthreads();
+				if (more)
+					stage_lists(itn, ltn);
+
+				/* ---- fold: thread <-> (column, piece), lanes in order ---- */
+				{
+					const int S = (int)(fm.x >> 16);
+					if (S) {
+						const int lane0 = fm.x & 0xffffu, pc = fm.y >> 24;
+						double2 acc = make_double2(0.0, 0.0);
+						for (int s = 0; s < S; s++) {
+							const double2 v = *reinterpret_cast<const double2 *>(
+								part_s + (size_t)(lane0 + s) * KR + 2 * pc);
+							acc.x += v.x;
+							acc.y += v.y;
+						}
+						double2 *dst = reinterpret_cast<double2 *>(B_s
+							+ (size_t)(fm.y & 0xffffffu) * KR + 2 * pc);
+						double2 v = *dst;
+						v.x += acc.x;
+						v.y += acc.y;
+						*dst = v;
+					}
+				}
+			}
+			if (EM) {
+				double *dst = a.Apart + ((size_t)c * a.Ipad + i) * a.K;
+#pragma unroll
+				for (int k = 0; k < KR; k++)
+					if (k < a.K)
+						dst[k] = A[k];
+			}
+		}
+		a3_cp_async_wait();
+
+		/* ---- flush the chunk's allele sums: N_klj = p_klj G_klj ---- */
+		if (EM) {
+			__syncthreads();
+			double *Np = a.Npart + (size_t)r * a.K * a.T;
+			for (int x = t; x < chunk_rows * a.K; x += A3_THREADS) {
+				const int k = x / chunk_rows, row = x - k * chunk_rows;
+				const size_t gx = (size_t)k * a.T + row0 + row;
+				Np[gx] = B_s[(size_t)row * KR + k] * __ldg(a.p + gx);
+			}
+		}
+		/* ---- log likelihood of the unit ---- */
+		double ll = log(prod) + (double)esum * 0.693147180559945309417232121458 + ll_slow;
+#pragma unroll
+		for (int mm = 16; mm >= 1; mm >>= 1)
+			ll += shfl_xor_f64(ll, mm);
+		__syncthreads();
+		if (lane == 0)
+			red[t >> 5] = ll;
+		__syncthreads();
+		if (t == 0) {
+			double sum = 0.0;
+			for (int wv = 0; wv < A3_THREADS / 32; wv++)
+				sum += red[wv];
+			a.llpart[u] = sum;
+		}
+	}
+}

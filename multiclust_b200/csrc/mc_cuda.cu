@@ -19,6 +19,7 @@
 #include "mc_cuda.h"
 #include "mc_kernels.cuh"
 #include "mc_admix2.cuh"
+#include "mc_admix3.cuh"
 
 #define KH_MAX 6
 #define SMEM_LIMIT (227 * 1024)
@@ -75,6 +76,16 @@ struct mc_ctx {
 		*d2_lc_first = nullptr;
 	unsigned short *d2_colinfo = nullptr, *d2_csc = nullptr, *d2_colstart = nullptr;
 	unsigned char *d2_csr = nullptr;
+	/* rotation two-pass plan (mc_admix3.cuh); used when `use3` */
+	bool use3 = false;
+	Admix3Args a3;
+	int KP3 = 0, grid3 = 0;
+	size_t smem3 = 0, smem3_ll = 0;
+	int *d3_lt_ncol = nullptr, *d3_lc_first = nullptr;
+	unsigned short *d3_colinfo = nullptr, *d3_csc = nullptr, *d3_colstart = nullptr;
+	unsigned *d3_lanemap = nullptr;
+	uint2 *d3_foldmap = nullptr;
+	unsigned char *d3_codes = nullptr;
 	/* sizes of the partial-sum buffers of the active plan */
 	int act_tiles = 0, act_chunks = 0, act_units = 0;
 	long long act_Ipad = 0;
@@ -175,6 +186,10 @@ static void free_plan(mc_ctx *c)
 	dfree(c->d2_lc_first); dfree(c->d2_colinfo); dfree(c->d2_csc);
 	dfree(c->d2_colstart); dfree(c->d2_csr);
 	c->use2 = false;
+	dfree(c->d3_lt_ncol); dfree(c->d3_lc_first); dfree(c->d3_colinfo);
+	dfree(c->d3_csc); dfree(c->d3_colstart); dfree(c->d3_foldmap);
+	dfree(c->d3_lanemap); dfree(c->d3_codes);
+	c->use3 = false;
 }
 
 static void free_model(mc_ctx *c)
@@ -671,9 +686,293 @@ static int launch_admix2(mc_ctx *c, int ll_only, const double *p, const double *
 }
 
 
+
+/* ------------------------------------------ rotation two-pass plan (admix3) */
+
+/* returns MC_OK with c->use3 set when the kernel of mc_admix3.cuh applies */
+static int make_plan3(mc_ctx *c)
+{
+	c->use3 = false;
+	if (!c->admixture || c->PP > 8 || c->K > 16 || c->T < 1)
+		return MC_OK;
+	if (const char *ev = getenv("MC_KERNEL"))
+		if (atoi(ev) == 1 || atoi(ev) == 2)
+			return MC_OK;	/* tuning knob: force an older kernel */
+	const int K = c->K, KP = (K + 1) / 2, KR = 2 * KP, PP = c->PP, L = c->L;
+	const int LT = 8 / PP;
+	const int n_ltiles = (L + LT - 1) / LT;
+	const long long n_itiles = (c->I + A3_IT - 1) / A3_IT;
+	const int cap = A3_IT * 8;
+	if (n_itiles * n_ltiles > 0x7fffffffLL)
+		return MC_OK;
+
+	/* allele counts: column order and lanes per column */
+	unsigned *d_hist = nullptr;
+	std::vector<unsigned> hist((size_t)c->T);
+	CK(cudaMalloc(&d_hist, sizeof(unsigned) * (size_t)c->T));
+	CK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * (size_t)c->T, c->stream));
+	k_allele_hist<<<grid_for(c, c->I * (long long)L, 256), 256, 0, c->stream>>>(
+		c->d_nat, c->I, L, c->P, c->d_off, d_hist);
+	LAUNCH_CHECK("k_allele_hist");
+	CK(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned) * (size_t)c->T,
+		cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	cudaFree(d_hist);
+
+	std::vector<int> lt_ncol((size_t)n_ltiles), lt_rows((size_t)n_ltiles);
+	std::vector<std::vector<std::pair<unsigned, unsigned short>>> cols((size_t)n_ltiles);
+	int ncolmax = 1, max_tile_rows = 1;
+	for (int lt = 0; lt < n_ltiles; lt++) {
+		const int lf = lt * LT, le = std::min(L, lf + LT);
+		lt_rows[lt] = c->off[le] - c->off[lf];
+		max_tile_rows = std::max(max_tile_rows, lt_rows[lt]);
+		auto &v = cols[lt];
+		for (int l = lf; l < le; l++)
+			for (int j = 0; j < c->J[l]; j++)
+				if (hist[(size_t)c->off[l] + j])
+					v.push_back({ hist[(size_t)c->off[l] + j],
+						(unsigned short)((l - lf) << 8 | j) });
+		std::stable_sort(v.begin(), v.end(),
+			[](const std::pair<unsigned, unsigned short> &x,
+			   const std::pair<unsigned, unsigned short> &y) { return x.first > y.first; });
+		lt_ncol[lt] = (int)v.size();
+		ncolmax = std::max(ncolmax, (int)v.size());
+	}
+	if (ncolmax > A3_THREADS || ncolmax >= (int)A3_IDLE)
+		return MC_OK;	/* more allele columns in a tile than lanes */
+
+	/* lanes per column in proportion to the allele counts (largest
+	 * remainder on count / lanes), lanes handed out in column order */
+	if ((long long)ncolmax * KP > A3_THREADS)
+		return MC_OK;	/* the fold maps one (column, piece) to a thread */
+	std::vector<unsigned short> colinfo((size_t)n_ltiles * ncolmax, 0);
+	std::vector<unsigned> lanemap((size_t)n_ltiles * A3_THREADS, A3_IDLE);
+	std::vector<uint2> foldmap((size_t)n_ltiles * A3_THREADS, make_uint2(0u, 0u));
+	for (int lt = 0; lt < n_ltiles; lt++) {
+		const auto &v = cols[lt];
+		const int ncol = (int)v.size();
+		if (!ncol)
+			continue;
+		double total = 0;
+		for (auto &e : v)
+			total += e.first;
+		std::vector<int> S((size_t)ncol);
+		int used = 0;
+		for (int x = 0; x < ncol; x++) {
+			S[x] = std::max(1, (int)floor(v[x].first * (double)A3_THREADS / total));
+			used += S[x];
+		}
+		while (used > A3_THREADS) {	/* only through the max(1, .) floor */
+			int b = 0;
+			for (int x = 1; x < ncol; x++)
+				if (S[x] > 1 && (S[b] <= 1 || v[x].first / (double)S[x] < v[b].first / (double)S[b]))
+					b = x;
+			S[b]--; used--;
+		}
+		while (used < A3_THREADS) {
+			int b = 0;
+			for (int x = 1; x < ncol; x++)
+				if (v[x].first / (double)S[x] > v[b].first / (double)S[b])
+					b = x;
+			S[b]++; used++;
+		}
+		int lane0 = 0;
+		for (int x = 0; x < ncol; x++) {
+			const unsigned loc = v[x].second >> 8;
+			colinfo[(size_t)lt * ncolmax + x] = v[x].second;
+			for (int sgm = 0; sgm < S[x]; sgm++)
+				lanemap[(size_t)lt * A3_THREADS + lane0 + sgm] = (unsigned)x
+					| (unsigned)sgm << 10 | (unsigned)S[x] << 19 | loc << 29;
+			/* the row inside the locus chunk is added once the chunks are known */
+			for (int pc = 0; pc < KP; pc++)
+				foldmap[(size_t)lt * A3_THREADS + (size_t)x * KP + pc] = make_uint2(
+					(unsigned)lane0 | (unsigned)S[x] << 16,
+					(unsigned)(c->off[lt * LT + (int)loc] + (v[x].second & 0xff))
+					| (unsigned)pc << 24);
+			lane0 += S[x];
+		}
+	}
+
+	/* shared memory: fixed part, the rest holds the chunk's accumulators */
+	const int PR = (max_tile_rows + 1) & ~1;
+	const size_t fixed = a3_smem_bytes(KP, true, 0, PR, ncolmax, cap) + 64;
+	const size_t smem_cap = (size_t)(227 * 1024) - 1024;
+	if (fixed + (size_t)max_tile_rows * KR * sizeof(double) > smem_cap)
+		return MC_OK;
+	const long long budget_rows = (long long)((smem_cap - fixed) / (KR * sizeof(double)));
+	const long long total_rows = c->T;
+	const long long sms = c->num_sms;
+	const int nl_min = (int)((total_rows + budget_rows - 1) / budget_rows);
+
+	/* locus chunks x individual chunks: fill the persistent grid evenly; more
+	 * locus chunks cost A_ik partial sums, more individual chunks cost N sums */
+	auto split_loci = [&](int want, std::vector<int> &first, int &max_rows) {
+		int n = want;
+		for (;;) {
+			const double target = (double)total_rows / n;
+			first.assign(1, 0);
+			long long rows = 0;
+			bool ok = true;
+			max_rows = 1;
+			for (int lt = 0; lt < n_ltiles; lt++) {
+				if (rows > 0 && (rows + lt_rows[lt] > budget_rows
+					|| (rows + lt_rows[lt] / 2.0 > target && (int)first.size() < n))) {
+					first.push_back(lt);
+					rows = 0;
+				}
+				rows += lt_rows[lt];
+				if (rows > budget_rows)
+					ok = false;
+				max_rows = std::max<long long>(max_rows, rows);
+			}
+			first.push_back(n_ltiles);
+			if (ok)
+				break;
+			n++;
+		}
+	};
+	std::vector<int> lc_first;
+	int max_chunk_rows = 1, n_ichunks = 1;
+	{
+		double best_eff = -1;
+		std::vector<int> first;
+		int mr = 1, last_n = -1;
+		const int nl_max = (int)std::min<long long>(n_ltiles, std::max<long long>(nl_min, 2 * sms));
+		for (int want = nl_min; want <= nl_max; want++) {
+			split_loci(want, first, mr);
+			const int nl = (int)first.size() - 1;	/* what the split really gives */
+			if (nl == last_n)
+				continue;
+			last_n = nl;
+			const long long cmax = std::min<long long>(n_itiles,
+				std::max<long long>(1, (4 * sms + nl - 1) / nl));
+			for (long long cc = 1; cc <= cmax; cc++) {
+				const long long units = cc * nl;
+				const long long rounds = (units + sms - 1) / sms;
+				const double eff = (double)units / (double)(rounds * sms)
+					- 0.02 * (double)nl / (double)std::max(nl_min, 1)
+					- 0.004 * (double)cc - 0.002 * (double)rounds;
+				if (eff > best_eff + 1e-12) {
+					best_eff = eff;
+					lc_first = first;
+					max_chunk_rows = mr;
+					n_ichunks = (int)cc;
+				}
+			}
+		}
+	}
+	const int n_lchunks = (int)lc_first.size() - 1;
+
+	if (c->T >= (1 << 24))
+		return MC_OK;
+	for (int ch = 0; ch + 1 < (int)lc_first.size(); ch++) {
+		const unsigned row0 = (unsigned)c->off[std::min(L, lc_first[ch] * LT)];
+		for (int lt = lc_first[ch]; lt < lc_first[ch + 1]; lt++)
+			for (int f = 0; f < lt_ncol[lt] * KP; f++)
+				foldmap[(size_t)lt * A3_THREADS + f].y -= row0;
+	}
+
+	Admix3Args &a = c->a3;
+	memset(&a, 0, sizeof a);
+	a.K = K;
+	a.n_itiles = (int)n_itiles; a.n_ltiles = n_ltiles; a.n_lchunks = n_lchunks;
+	a.n_ichunks = n_ichunks; a.n_units = n_lchunks * n_ichunks;
+	a.I = c->I; a.Ipad = n_itiles * A3_IT; a.T = c->T; a.L = L;
+	a.ncolmax = ncolmax; a.max_chunk_rows = max_chunk_rows; a.PR = PR; a.cap = cap;
+	c->KP3 = KP;
+	c->smem3 = a3_smem_bytes(KP, true, max_chunk_rows, PR, ncolmax, cap);
+	c->smem3_ll = a3_smem_bytes(KP, false, max_chunk_rows, PR, ncolmax, cap);
+	c->grid3 = (int)std::min<long long>(a.n_units, sms);
+
+	int rc;
+	if ((rc = upload(c, c->d3_lt_ncol, lt_ncol))) return rc;
+	if ((rc = upload(c, c->d3_lc_first, lc_first))) return rc;
+	if ((rc = upload(c, c->d3_colinfo, colinfo))) return rc;
+	if ((rc = upload(c, c->d3_foldmap, foldmap))) return rc;
+	if ((rc = upload(c, c->d3_lanemap, lanemap))) return rc;
+	const size_t ntile = (size_t)n_itiles * n_ltiles;
+	CK(cudaMalloc(&c->d3_codes, ntile * A3_THREADS * 8));
+	CK(cudaMalloc(&c->d3_csc, ntile * cap * sizeof(unsigned short)));
+	CK(cudaMalloc(&c->d3_colstart, ntile * (size_t)((ncolmax + 1 + 7) / 8 * 8) * sizeof(unsigned short)));
+	k3_build_codes<<<grid_for(c, (long long)ntile * A3_THREADS, 256), 256, 0, c->stream>>>(
+		c->d_nat, c->d3_codes, c->I, L, c->P, PP, (int)n_itiles, n_ltiles);
+	LAUNCH_CHECK("k3_build_codes");
+	const size_t bsm = (size_t)A3_IT * 8 + sizeof(int) * (size_t)ncolmax;
+	k3_build_csc<<<(unsigned)ntile, 128, bsm, c->stream>>>(c->d3_codes, PP, n_ltiles,
+		ncolmax, cap, c->d3_lt_ncol, c->d3_colinfo, c->d3_csc, c->d3_colstart);
+	LAUNCH_CHECK("k3_build_csc");
+	a.lt_ncol = c->d3_lt_ncol; a.colinfo = c->d3_colinfo; a.foldmap = c->d3_foldmap;
+	a.lanemap = c->d3_lanemap; a.lc_first = c->d3_lc_first; a.off = c->d_off;
+	a.codes = c->d3_codes; a.csc = c->d3_csc; a.colstart = c->d3_colstart;
+	if ((rc = alloc_outputs(c, n_lchunks, n_ichunks, a.n_units, a.Ipad))) return rc;
+	a.Apart = c->d_Apart; a.Npart = c->d_Npart; a.llpart = c->d_llpart;
+	CK(cudaStreamSynchronize(c->stream));
+	c->use3 = true;
+	return MC_OK;
+}
+
+typedef void (*admix3_fn)(const Admix3Args);
+
+template <int KP, int MODE> static admix3_fn pick3_pp(int PP)
+{
+	switch (PP) {
+	case 1: return admix3_kernel<KP, 1, MODE>;
+	case 2: return admix3_kernel<KP, 2, MODE>;
+	case 4: return admix3_kernel<KP, 4, MODE>;
+	case 8: return admix3_kernel<KP, 8, MODE>;
+	}
+	return nullptr;
+}
+
+template <int MODE> static admix3_fn pick3(int KP, int PP)
+{
+	switch (KP) {
+	case 1: return pick3_pp<1, MODE>(PP);
+	case 2: return pick3_pp<2, MODE>(PP);
+	case 3: return pick3_pp<3, MODE>(PP);
+	case 4: return pick3_pp<4, MODE>(PP);
+	case 5: return pick3_pp<5, MODE>(PP);
+	case 6: return pick3_pp<6, MODE>(PP);
+	case 7: return pick3_pp<7, MODE>(PP);
+	case 8: return pick3_pp<8, MODE>(PP);
+	}
+	return nullptr;
+}
+
+static int launch_admix3(mc_ctx *c, int ll_only, const double *p, const double *eta,
+	long long eta_stride)
+{
+	admix3_fn fn = ll_only ? pick3<1>(c->KP3, c->PP) : pick3<0>(c->KP3, c->PP);
+	if (!fn)
+		return fail(c, MC_ERR_UNSUPPORTED, "no admix3 kernel for K=%d P=%d", c->K, c->P);
+	Admix3Args a = c->a3;
+	a.p = p; a.eta = eta; a.eta_stride = eta_stride;
+	const size_t smem = ll_only ? c->smem3_ll : c->smem3;
+	CK(cudaFuncSetAttribute((const void *)fn,
+		cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	if (c->profile) {
+		CK(cudaEventCreate(&e0));
+		CK(cudaEventCreate(&e1));
+		CK(cudaEventRecord(e0, c->stream));
+	}
+	fn<<<c->grid3, A3_THREADS, smem, c->stream>>>(a);
+	LAUNCH_CHECK("admix3_kernel");
+	if (c->profile) {
+		CK(cudaEventRecord(e1, c->stream));
+		c->prof_events.push_back({ e0, e1 });
+	}
+	return MC_OK;
+}
+
 static int make_plan(mc_ctx *c)
 {
 	const int K = c->K;
+	{
+		const int rc3 = make_plan3(c);
+		if (rc3 || c->use3)
+			return rc3;
+	}
 	{
 		const int rc2 = make_plan2(c);
 		if (rc2 || c->use2)
@@ -985,7 +1284,9 @@ extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 	const int K = c->K;
 	int rc;
 	if (c->admixture) {
-		rc = c->use2
+		rc = c->use3
+			? launch_admix3(c, 0, c->d_p[from], c->d_eta[from], c->per_indiv ? K : 0)
+			: c->use2
 			? launch_admix2(c, 0, c->d_p[from], c->d_eta[from], c->per_indiv ? K : 0)
 			: launch_tile(c, MODE_ADMIX_EM, c->d_p[from], c->d_eta[from],
 				c->per_indiv ? K : 0);
@@ -1134,7 +1435,9 @@ extern "C" int mc_loglik(mc_ctx *c, int slot, double *ll)
 	CHECK_SLOT(slot);
 	int rc;
 	if (c->admixture) {
-		rc = c->use2
+		rc = c->use3
+			? launch_admix3(c, 1, c->d_p[slot], c->d_eta[slot], c->per_indiv ? c->K : 0)
+			: c->use2
 			? launch_admix2(c, 1, c->d_p[slot], c->d_eta[slot], c->per_indiv ? c->K : 0)
 			: launch_tile(c, MODE_ADMIX_LL, c->d_p[slot], c->d_eta[slot],
 				c->per_indiv ? c->K : 0);
@@ -1361,6 +1664,14 @@ extern "C" int mc_get_plan(const mc_ctx *c, mc_plan_info *o)
 		o->n_tiles = c->a2.n_lchunks; o->n_chunks = c->a2.n_ichunks;
 		o->n_units = c->a2.n_units; o->grid = c->grid2; o->block = A2_THREADS;
 		o->indiv_per_block = A2_IT; o->smem_bytes = (int64_t)c->smem2;
+	}
+	if (c->use3) {	/* rotation two-pass kernel */
+		o->two_pass = 2;
+		o->k_split = 1; o->k_per_lane = 2 * c->KP3;
+		o->loci_per_warp = 8 / c->PP; o->warps = A3_THREADS / 32; o->groups = 1;
+		o->n_tiles = c->a3.n_lchunks; o->n_chunks = c->a3.n_ichunks;
+		o->n_units = c->a3.n_units; o->grid = c->grid3; o->block = A3_THREADS;
+		o->indiv_per_block = A3_IT; o->smem_bytes = (int64_t)c->smem3;
 	}
 	const int64_t g = c->I * (int64_t)c->L * c->P;
 	o->algorithmic_bytes_em = g + 16 * c->I * (int64_t)c->K + 16 * (int64_t)c->K * c->T;
