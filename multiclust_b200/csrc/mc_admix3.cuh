@@ -21,7 +21,7 @@
  *   pass 2  thread <-> (allele column, segment); a column gets a number of
  *           lanes proportional to its allele count, its sorted entry list is
  *           dealt round-robin to them.  eta rows live in shared memory padded
- *           to 128 bytes = 8 pieces of 16 bytes; lane m reads piece (m + s) % 8
+ *           to 128 bytes = 8 pieces of 16 bytes; lane m reads piece m ^ s
  *           in step s, so the 8 lanes of every quarter warp always touch 8
  *           different bank groups whichever rows they read: 4 wavefronts per
  *           LDS.128, the minimum, for ANY entry-to-lane assignment.  The
@@ -37,8 +37,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef A3_THREADS
 #define A3_THREADS 512
-#define A3_IT 512		/* individuals per tile = pass-1 threads */
+#endif
+#define A3_IT A3_THREADS	/* individuals per tile = pass-1 threads */
+#ifndef A3_CTAS_PER_SM
+#define A3_CTAS_PER_SM (512 / A3_THREADS)	/* CTAs sharing an SM (and its shared memory) */
+#endif
 #define A3_IDLE 1023u		/* lane map: no column */
 
 struct Admix3Args {
@@ -51,7 +56,7 @@ struct Admix3Args {
 	const unsigned short *colinfo;	/* [n_ltiles][ncolmax] locus_in_tile << 8 | allele */
 	const unsigned *lanemap;	/* [n_ltiles][A3_THREADS] pass-2 lane: col | seg << 10 |
 					 * lanes << 19 | locus_in_tile << 29 */
-	const uint2 *foldmap;		/* [n_ltiles][A3_THREADS] fold thread: x = first lane |
+	const uint2 *foldmap;		/* [n_ltiles][nfi][A3_THREADS] fold thread: x = first lane |
 					 * lanes << 16 (0: idle), y = row in chunk | piece << 24 */
 	const int *lc_first;		/* [n_lchunks + 1] first locus tile of each chunk */
 	const int *off;			/* [L + 1] prefix sums of J */
@@ -61,6 +66,7 @@ struct Admix3Args {
 	const unsigned short *colstart;	/* [n_itiles][n_ltiles][csw], csw = ncolmax + 1
 					 * rounded up to a multiple of 8 */
 	int cap;			/* entries per tile: A3_IT * 8 */
+	int nfi;			/* fold items per thread: ceil(4 * ncolmax * KP / A3_THREADS) */
 	/* parameters */
 	const double *p, *eta;
 	long long eta_stride;
@@ -168,9 +174,33 @@ __device__ __forceinline__ void a3_cp_async8(void *smem_dst, const void *gsrc)
 	const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(s), "l"(gsrc));
 }
-__device__ __forceinline__ void a3_cp_async_wait()
+__device__ __forceinline__ void a3_cp_async_commit()
 {
-	asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void a3_cp_async_wait()
+{
+	asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
+
+/* shared-memory loads from 32-bit addresses */
+__device__ __forceinline__ double2 a3_lds_f64x2(unsigned addr)
+{
+	double2 v;
+	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ double a3_lds_f64(unsigned addr)
+{
+	double v;
+	asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ unsigned a3_lds_u16(unsigned addr)
+{
+	unsigned short v;
+	asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+	return v;
 }
 
 /* pieces of 16 bytes per eta row in shared memory */
@@ -198,26 +228,30 @@ static inline size_t a3_smem_bytes(int KP, bool em, int max_chunk_rows, int PR,
 
 /* MODE 0: E+M step, MODE 1: log likelihood only */
 template <int KP, int PP, int MODE>
-__global__ void __launch_bounds__(A3_THREADS, 1) admix3_kernel(const Admix3Args a)
+__global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(const Admix3Args a)
 {
 	constexpr int KR = 2 * KP;
 	constexpr int NP = A3Row<KP>::NP;
 	constexpr int LT = 8 / PP;
 	constexpr bool EM = (MODE == 0);
-	extern __shared__ double smem[];
+	extern __shared__ __align__(128) double smem3d[];
 	const int t = threadIdx.x, lane = t & 31, m = t & (NP - 1);
 	const int PR = a.PR;
 	const int csw = ((a.ncolmax + 1 + 7) / 8) * 8;	/* colstart row, 16-byte multiple */
 
-	double *B_s = smem;						/* [max_chunk_rows][KR] */
-	double *p_s = B_s + (EM ? (size_t)a.max_chunk_rows * KR : 0);	/* [KR][PR] */
-	double *eta_s = p_s + (size_t)KR * PR;				/* [A3_IT][2 NP] */
+	/* eta rows first: the xor rotation needs them aligned to their size */
+	double *eta_s = smem3d;						/* [A3_IT][2 NP] */
 	double *w_s = eta_s + (EM ? (size_t)A3_IT * NP * 2 : 0);	/* [8][A3_IT] */
 	double *part_s = w_s + (EM ? 8 * (size_t)A3_IT : 0);		/* [A3_THREADS][KR] */
-	double *red = part_s + (EM ? (size_t)A3_THREADS * KR : 0);	/* [16] */
+	double *B_s = part_s + (EM ? (size_t)A3_THREADS * KR : 0);	/* [max_chunk_rows][KR] */
+	double *p_s = B_s + (EM ? (size_t)a.max_chunk_rows * KR : 0);	/* [KR][PR] */
+	double *red = p_s + (size_t)KR * PR;				/* [16] */
 	unsigned short *csc_s = reinterpret_cast<unsigned short *>(red + 16);	/* [cap] */
 	unsigned short *cst_s = csc_s + (EM ? a.cap : 0);		/* [csw] */
 	int *rb_s = reinterpret_cast<int *>(cst_s + csw);		/* [2][8] row bases */
+	const unsigned eta_sa = (unsigned)__cvta_generic_to_shared(eta_s);
+	const unsigned w_sa = (unsigned)__cvta_generic_to_shared(w_s);
+	const unsigned csc_sa = (unsigned)__cvta_generic_to_shared(csc_s);
 
 	for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
 		const int c = u % a.n_lchunks, r = u / a.n_lchunks;
@@ -247,7 +281,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) admix3_kernel(const Admix3Args 
 			cw_n = __ldg(reinterpret_cast<const uint2 *>(a.codes) + tix * A3_THREADS + t);
 			if (EM) {
 				lm_n = __ldg(a.lanemap + (size_t)lt * A3_THREADS + t);
-				fm_n = __ldg(a.foldmap + (size_t)lt * A3_THREADS + t);
+				fm_n = __ldg(a.foldmap + (size_t)lt * a.nfi * A3_THREADS + t);
 			}
 		};
 		auto stage_p = [&](int lt, int buf) {
@@ -265,6 +299,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) admix3_kernel(const Admix3Args 
 			}
 			if (t < LT)
 				rb_s[buf * 8 + t] = lf + t < a.L ? a.off[lf + t] - trow0 : 0;
+			a3_cp_async_commit();
 		};
 		auto stage_lists = [&](long long it, int lt) {
 			const size_t tix = (size_t)it * a.n_ltiles + lt;
@@ -272,6 +307,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) admix3_kernel(const Admix3Args 
 				a3_cp_async16(csc_s + t * 8, a.csc + tix * a.cap + t * 8);
 			if (t * 8 < csw)
 				a3_cp_async16(cst_s + t * 8, a.colstart + tix * csw + t * 8);
+			a3_cp_async_commit();
 		};
 
 		fetch_regs(it0, lt0);
@@ -311,7 +347,12 @@ __global__ void __launch_bounds__(A3_THREADS, 1) admix3_kernel(const Admix3Args 
 
 				if (more)
 					fetch_regs(itn, ltn);
-				a3_cp_async_wait();
+				/* the p rows must have landed; the entry lists (the younger
+				 * group) are only needed after pass 1 */
+				if (EM)
+					a3_cp_async_wait<1>();
+				else
+					a3_cp_async_wait<0>();
 				__syncthreads();
 
 				/* ---- pass 1: tmp, w, A, log likelihood ---- */
@@ -370,10 +411,14 @@ __global__ void __launch_bounds__(A3_THREADS, 1) admix3_kernel(const Admix3Args 
 						}
 					}
 				}
+				if (EM)
+					a3_cp_async_wait<0>();
 				__syncthreads();
 				/* p_s is free: the next tile's p rows travel during pass 2 */
 				if (more)
 					stage_p(ltn, buf ^ 1);
+				else
+					a3_cp_async_commit();	/* keeps the group count in step */
 				if (!EM)
 					continue;
 
@@ -383,28 +428,27 @@ __global__ void __launch_bounds__(A3_THREADS, 1) admix3_kernel(const Admix3Args 
 				for (int k = 0; k < 2 * NP; k++)
 					g[k] = 0.0;
 				if (A3_LM_COL(lm) != A3_IDLE) {
-					const int S = (int)A3_LM_S(lm);
+					const int S2 = (int)A3_LM_S(lm) * 2;	/* list stride, bytes */
 					const unsigned col = A3_LM_COL(lm);
-					const double *wb = w_s + (size_t)(A3_LM_LOC(lm) * PP) * A3_IT;
-					const int ce = cst_s[col + 1];
-					int x = cst_s[col] + (int)A3_LM_SEG(lm);
-					const char *eb = reinterpret_cast<const char *>(eta_s);
+					const unsigned wb = w_sa + A3_LM_LOC(lm) * (PP * A3_IT * 8);
+					const unsigned xe = csc_sa + 2u * cst_s[col + 1];
+					unsigned x = csc_sa + 2u * (cst_s[col] + A3_LM_SEG(lm));
 					/* ids and weights are fetched one trip ahead */
-					unsigned ent = x < ce ? csc_s[x] : 0u;
-					double w = x < ce ? wb[((ent >> 9) & 7) * A3_IT + (ent & 511)]
-						* (double)((ent >> 12) + 1) : 0.0;
-					while (x < ce) {
-						const char *row = eb + (size_t)(ent & 511) * (NP * 16);
+					unsigned ent = x < xe ? a3_lds_u16(x) : 0u;
+					double w = x < xe ? a3_lds_f64(wb + ((ent >> 9) & 7) * (A3_IT * 8)
+						+ (ent & (A3_IT - 1)) * 8) * (double)((ent >> 12) + 1) : 0.0;
+					while (x < xe) {
+						/* piece m ^ s of the row in step s */
+						const unsigned rm = eta_sa + (ent & (A3_IT - 1)) * (NP * 16) + (m << 4);
 						const double wc = w;
-						x += S;
-						ent = x < ce ? csc_s[x] : 0u;
+						x += S2;
+						ent = x < xe ? a3_lds_u16(x) : 0u;
 						double2 v[NP];
 #pragma unroll
 						for (int s = 0; s < NP; s++)
-							v[s] = *reinterpret_cast<const double2 *>(
-								row + (((m + s) & (NP - 1)) << 4));
-						w = x < ce ? wb[((ent >> 9) & 7) * A3_IT + (ent & 511)]
-							* (double)((ent >> 12) + 1) : 0.0;
+							v[s] = a3_lds_f64x2(rm ^ (s << 4));
+						w = x < xe ? a3_lds_f64(wb + ((ent >> 9) & 7) * (A3_IT * 8)
+							+ (ent & (A3_IT - 1)) * 8) * (double)((ent >> 12) + 1) : 0.0;
 #pragma unroll
 						for (int s = 0; s < NP; s++) {
 							g[2 * s] = fma(v[s].x, wc, g[2 * s]);
@@ -415,7 +459,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) admix3_kernel(const Admix3Args 
 				/* the lane's partial sums, un-rotated */
 #pragma unroll
 				for (int s = 0; s < NP; s++) {
-					const int pc = (m + s) & (NP - 1);
+					const int pc = m ^ s;
 					if (pc < KP)
 						*reinterpret_cast<double2 *>(part_s + (size_t)t * KR + 2 * pc)
 							= make_double2(g[2 * s], g[2 * s + 1]);
@@ -423,21 +467,32 @@ __global__ void __launch_bounds__(A3_THREADS, 1) admix3_kernel(const Admix3Args 
 				__syncthreads();
 				if (more)
 					stage_lists(itn, ltn);
+				else
+					a3_cp_async_commit();
 
-				/* ---- fold: thread <-> (column, piece), lanes in order ---- */
-				{
-					const int S = (int)(fm.x >> 16);
-					if (S) {
-						const int lane0 = fm.x & 0xffffu, pc = fm.y >> 24;
-						double2 acc = make_double2(0.0, 0.0);
-						for (int s = 0; s < S; s++) {
-							const double2 v = *reinterpret_cast<const double2 *>(
-								part_s + (size_t)(lane0 + s) * KR + 2 * pc);
-							acc.x += v.x;
-							acc.y += v.y;
-						}
+				/* ---- fold: 4 adjacent threads <-> (column, piece); each adds
+				 * every 4th partial, two shuffle steps, one of them updates
+				 * the CTA's accumulator (idle items carry 0 lanes) ---- */
+				for (int fi = 0; fi < a.nfi; fi++) {
+					const uint2 fmi = fi == 0 ? fm : __ldg(a.foldmap
+						+ ((size_t)lt * a.nfi + fi) * A3_THREADS + t);
+					const int S = (int)(fmi.x >> 16);
+					const int lane0 = fmi.x & 0xffffu, pc = fmi.y >> 24;
+					const double2 *src = reinterpret_cast<const double2 *>(
+						part_s + (size_t)lane0 * KR + 2 * pc);
+					double2 acc = make_double2(0.0, 0.0);
+					for (int sx = t & 3; sx < S; sx += 4) {
+						const double2 v0 = src[(size_t)sx * KP];
+						acc.x += v0.x;
+						acc.y += v0.y;
+					}
+					acc.x += shfl_xor_f64(acc.x, 1);
+					acc.y += shfl_xor_f64(acc.y, 1);
+					acc.x += shfl_xor_f64(acc.x, 2);
+					acc.y += shfl_xor_f64(acc.y, 2);
+					if (S && (t & 3) == 0) {
 						double2 *dst = reinterpret_cast<double2 *>(B_s
-							+ (size_t)(fm.y & 0xffffffu) * KR + 2 * pc);
+							+ (size_t)(fmi.y & 0xffffffu) * KR + 2 * pc);
 						double2 v = *dst;
 						v.x += acc.x;
 						v.y += acc.y;
@@ -453,7 +508,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) admix3_kernel(const Admix3Args 
 						dst[k] = A[k];
 			}
 		}
-		a3_cp_async_wait();
+		a3_cp_async_wait<0>();
 
 		/* ---- flush the chunk's allele sums: N_klj = p_klj G_klj ---- */
 		if (EM) {

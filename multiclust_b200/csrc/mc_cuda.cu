@@ -743,11 +743,11 @@ static int make_plan3(mc_ctx *c)
 
 	/* lanes per column in proportion to the allele counts (largest
 	 * remainder on count / lanes), lanes handed out in column order */
-	if ((long long)ncolmax * KP > A3_THREADS)
-		return MC_OK;	/* the fold maps one (column, piece) to a thread */
+	const int nfi = (4 * ncolmax * KP + A3_THREADS - 1) / A3_THREADS;
+	const size_t fstride = (size_t)nfi * A3_THREADS;
 	std::vector<unsigned short> colinfo((size_t)n_ltiles * ncolmax, 0);
 	std::vector<unsigned> lanemap((size_t)n_ltiles * A3_THREADS, A3_IDLE);
-	std::vector<uint2> foldmap((size_t)n_ltiles * A3_THREADS, make_uint2(0u, 0u));
+	std::vector<uint2> foldmap((size_t)n_ltiles * fstride, make_uint2(0u, 0u));
 	for (int lt = 0; lt < n_ltiles; lt++) {
 		const auto &v = cols[lt];
 		const int ncol = (int)v.size();
@@ -785,10 +785,11 @@ static int make_plan3(mc_ctx *c)
 					| (unsigned)sgm << 10 | (unsigned)S[x] << 19 | loc << 29;
 			/* the row inside the locus chunk is added once the chunks are known */
 			for (int pc = 0; pc < KP; pc++)
-				foldmap[(size_t)lt * A3_THREADS + (size_t)x * KP + pc] = make_uint2(
-					(unsigned)lane0 | (unsigned)S[x] << 16,
-					(unsigned)(c->off[lt * LT + (int)loc] + (v[x].second & 0xff))
-					| (unsigned)pc << 24);
+				for (int sub = 0; sub < 4; sub++)	/* 4 adjacent fold threads */
+					foldmap[(size_t)lt * fstride + ((size_t)x * KP + pc) * 4 + sub]
+						= make_uint2((unsigned)lane0 | (unsigned)S[x] << 16,
+						(unsigned)(c->off[lt * LT + (int)loc] + (v[x].second & 0xff))
+						| (unsigned)pc << 24);
 			lane0 += S[x];
 		}
 	}
@@ -796,12 +797,12 @@ static int make_plan3(mc_ctx *c)
 	/* shared memory: fixed part, the rest holds the chunk's accumulators */
 	const int PR = (max_tile_rows + 1) & ~1;
 	const size_t fixed = a3_smem_bytes(KP, true, 0, PR, ncolmax, cap) + 64;
-	const size_t smem_cap = (size_t)(227 * 1024) - 1024;
+	const size_t smem_cap = (size_t)(228 * 1024) / A3_CTAS_PER_SM - 1024 - 64;
 	if (fixed + (size_t)max_tile_rows * KR * sizeof(double) > smem_cap)
 		return MC_OK;
 	const long long budget_rows = (long long)((smem_cap - fixed) / (KR * sizeof(double)));
 	const long long total_rows = c->T;
-	const long long sms = c->num_sms;
+	const long long sms = (long long)c->num_sms * A3_CTAS_PER_SM;
 	const int nl_min = (int)((total_rows + budget_rows - 1) / budget_rows);
 
 	/* locus chunks x individual chunks: fill the persistent grid evenly; more
@@ -868,8 +869,8 @@ static int make_plan3(mc_ctx *c)
 	for (int ch = 0; ch + 1 < (int)lc_first.size(); ch++) {
 		const unsigned row0 = (unsigned)c->off[std::min(L, lc_first[ch] * LT)];
 		for (int lt = lc_first[ch]; lt < lc_first[ch + 1]; lt++)
-			for (int f = 0; f < lt_ncol[lt] * KP; f++)
-				foldmap[(size_t)lt * A3_THREADS + f].y -= row0;
+			for (int f = 0; f < lt_ncol[lt] * KP * 4; f++)
+				foldmap[(size_t)lt * fstride + f].y -= row0;
 	}
 
 	Admix3Args &a = c->a3;
@@ -879,10 +880,12 @@ static int make_plan3(mc_ctx *c)
 	a.n_ichunks = n_ichunks; a.n_units = n_lchunks * n_ichunks;
 	a.I = c->I; a.Ipad = n_itiles * A3_IT; a.T = c->T; a.L = L;
 	a.ncolmax = ncolmax; a.max_chunk_rows = max_chunk_rows; a.PR = PR; a.cap = cap;
+	a.nfi = nfi;
 	c->KP3 = KP;
 	c->smem3 = a3_smem_bytes(KP, true, max_chunk_rows, PR, ncolmax, cap);
 	c->smem3_ll = a3_smem_bytes(KP, false, max_chunk_rows, PR, ncolmax, cap);
 	c->grid3 = (int)std::min<long long>(a.n_units, sms);
+	(void)fstride;
 
 	int rc;
 	if ((rc = upload(c, c->d3_lt_ncol, lt_ncol))) return rc;
