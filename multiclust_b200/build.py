@@ -20,6 +20,7 @@ HOST = os.path.join(PKG, "host")
 LIB = os.path.join(PKG, "libmc_cuda.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+              "-diag-suppress", "128",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-Wall", "-I" + INC, "-I" + CSRC]
 HOST_CFLAGS = ["-std=c17", "-O2", "-Wall", "-Wextra", "-D_GNU_SOURCE",

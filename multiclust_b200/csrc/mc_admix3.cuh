@@ -1,6 +1,7 @@
 /*
- * mc_admix3.cuh -- two-pass admixture kernel, third mapping: 512 individuals
- * per tile, bank-conflict-free gathers by construction.
+ * mc_admix3.cuh -- two-pass admixture kernel, third mapping: A3_IT individuals
+ * per tile (one per thread), gathers laid out for the minimum number of
+ * shared-memory wavefronts.
  *
  * The fused E+M step of the admixture model (em_alg.c:325-433, 604-725) is,
  * per allele copy (i, l, a) with allele j:
@@ -19,18 +20,21 @@
  *           8-byte word each from <= J_l consecutive words: 2 wavefronts per
  *           LDS.64, the minimum.  w goes to shared memory, w_s[copy][i].
  *   pass 2  thread <-> (allele column, segment); a column gets a number of
- *           lanes proportional to its allele count, its sorted entry list is
- *           dealt round-robin to them.  eta rows live in shared memory padded
- *           to 128 bytes = 8 pieces of 16 bytes; lane m reads piece m ^ s
- *           in step s, so the 8 lanes of every quarter warp always touch 8
- *           different bank groups whichever rows they read: 4 wavefronts per
- *           LDS.128, the minimum, for ANY entry-to-lane assignment.  The
- *           accumulators are held in rotated order (static register indices)
- *           and un-rotated when the lane writes its partial sums.
+ *           lanes proportional to its allele count.  The eta rows live in
+ *           shared memory with a pitch of an odd number of 16-byte pieces, so
+ *           the rows of individuals with different i % 8 start in different
+ *           bank groups, and the entry lists are built (k3_build_csc, once per
+ *           data set) so that lane t mostly reads individuals with
+ *           i % 8 == t % 8: the 8 lanes of a quarter warp then touch 8
+ *           different bank groups, 4 wavefronts per LDS.128, the minimum.
+ *           (A first version padded the rows to 8 pieces and rotated the
+ *           piece order per lane -- conflict-free for any assignment but 8
+ *           loads for 5 useful pieces at K = 10.)
  *   fold    the lanes' partial sums go through a shared scratch; thread
  *           (column, piece) adds the column's partials in lane order and
  *           updates the CTA's accumulator B_s: no atomics, fixed order.
- * Three barriers per (512 individuals x 8 copies) tile.
+ * Three barriers per (A3_IT individuals x 8 copies) tile; two CTAs per SM so
+ * that one's pass 1 (FP64) overlaps the other's pass 2 (shared-memory pipe).
  */
 #pragma once
 
@@ -38,7 +42,7 @@
 #include <stdint.h>
 
 #ifndef A3_THREADS
-#define A3_THREADS 512
+#define A3_THREADS 256		/* measured at C3: 256 x 2 CTAs/SM 26.7 ms, 512 x 1 30.3 ms */
 #endif
 #define A3_IT A3_THREADS	/* individuals per tile = pass-1 threads */
 #ifndef A3_CTAS_PER_SM
@@ -57,7 +61,8 @@ struct Admix3Args {
 	const unsigned *lanemap;	/* [n_ltiles][A3_THREADS] pass-2 lane: col | seg << 10 |
 					 * lanes << 19 | locus_in_tile << 29 */
 	const uint2 *foldmap;		/* [n_ltiles][nfi][A3_THREADS] fold thread: x = first lane |
-					 * lanes << 16 (0: idle), y = row in chunk | piece << 24 */
+					 * lanes << 16 (0: idle), y = row in chunk | piece << 24 |
+					 * log2(threads of the group) << 28 */
 	const int *lc_first;		/* [n_lchunks + 1] first locus tile of each chunk */
 	const int *off;			/* [L + 1] prefix sums of J */
 	/* data */
@@ -66,7 +71,7 @@ struct Admix3Args {
 	const unsigned short *colstart;	/* [n_itiles][n_ltiles][csw], csw = ncolmax + 1
 					 * rounded up to a multiple of 8 */
 	int cap;			/* entries per tile: A3_IT * 8 */
-	int nfi;			/* fold items per thread: ceil(4 * ncolmax * KP / A3_THREADS) */
+	int nfi;			/* fold items per thread */
 	/* parameters */
 	const double *p, *eta;
 	long long eta_stride;
@@ -101,12 +106,17 @@ __global__ void k3_build_codes(const unsigned char *nat, unsigned char *codes,
 	}
 }
 
-/* allele-sorted entry lists of one (itile, ltile): for every real allele column
- * in `colinfo` order, the individuals carrying it in ascending order, one entry
- * per (individual, allele): i | first copy << 9 | (count - 1) << 12 */
+/* entry lists of one (itile, ltile): for every real allele column in `colinfo`
+ * order, one entry per (individual, allele) carrying it:
+ *     i | first copy << 9 | (count - 1) << 12.
+ * The column owns S consecutive pass-2 lanes (colmeta: first lane | S << 16);
+ * lane seg reads the entries at start + s * S + seg, s = 0, 1, ...  The eta rows
+ * of 8 individuals with different i % 8 lie in different bank groups, so an
+ * entry is dealt to a lane with (lane % 8) == (i % 8) wherever such a lane still
+ * has room; the rest fill the remaining positions in ascending order of i. */
 __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 	int ncolmax, int cap, const int *lt_ncol, const unsigned short *colinfo,
-	unsigned short *csc, unsigned short *colstart)
+	const unsigned *colmeta, unsigned short *csc, unsigned short *colstart)
 {
 	extern __shared__ unsigned char sm3[];
 	unsigned char *cd = sm3;				/* [A3_IT][8] */
@@ -114,6 +124,7 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 	const int lt = blockIdx.x % n_ltiles;
 	const int ncol = lt_ncol[lt];
 	const unsigned short *ci = colinfo + (size_t)lt * ncolmax;
+	const unsigned *cm = colmeta + (size_t)lt * ncolmax;
 	unsigned short *out = csc + (size_t)blockIdx.x * cap;
 	const int csw = ((ncolmax + 1 + 7) / 8) * 8;
 	unsigned short *cs = colstart + (size_t)blockIdx.x * csw;
@@ -138,7 +149,6 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 		int acc = 0;
 		for (int c = 0; c < ncol; c++) {
 			const int n = cnt[c];
-			cnt[c] = acc;
 			cs[c] = (unsigned short)acc;
 			acc += n;
 		}
@@ -148,16 +158,56 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 	__syncthreads();
 	for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
 		const int ll = ci[c] >> 8, j = ci[c] & 0xff;
-		int pos = cnt[c];
-		for (int ii = 0; ii < A3_IT; ii++) {
-			int n = 0, first = 0;
-			for (int a = PP - 1; a >= 0; a--)
-				if (cd[ii * 8 + ll * PP + a] == j) {
-					n++;
-					first = a;
+		const int n = cnt[c], start = cs[c];
+		const int lane0 = cm[c] & 0xffff, S = cm[c] >> 16;
+		const int q = n / S, rem = n - q * S;	/* lane seg holds q + (seg < rem) entries */
+		for (int x = 0; x < n; x++)
+			out[start + x] = 0xffff;
+		/* two sweeps over the carriers: the first places the entries that find
+		 * a lane of their residue, the second the others */
+		for (int sweep = 0; sweep < 2; sweep++) {
+			int cs_s[8], cs_seg[8];		/* next free slot of every residue */
+			for (int r = 0; r < 8; r++) {
+				cs_s[r] = 0;
+				cs_seg[r] = (r - lane0) & 7;
+			}
+			int fill = 0;
+			for (int ii = 0; ii < A3_IT; ii++) {
+				int cn = 0, first = 0;
+				for (int a = PP - 1; a >= 0; a--)
+					if (cd[ii * 8 + ll * PP + a] == j) {
+						cn++;
+						first = a;
+					}
+				if (!cn)
+					continue;
+				const int r = ii & 7;
+				/* skip over slots that do not exist (lanes beyond S or the
+				 * short last step) */
+				int s_ = cs_s[r], seg = cs_seg[r];
+				while (s_ <= q && (seg >= S || (s_ == q && seg >= rem))) {
+					s_++;
+					seg = (r - lane0) & 7;
+					if (seg >= S)
+						s_ = q + 1;	/* the residue has no lane at all */
 				}
-			if (n)
-				out[pos++] = (unsigned short)(ii | first << 9 | (n - 1) << 12);
+				const bool ok = s_ < q || (s_ == q && seg < rem);
+				if (ok) {
+					if (sweep == 0)
+						out[start + s_ * S + seg] = (unsigned short)(ii | first << 9
+							| (cn - 1) << 12);
+					cs_s[r] = s_;
+					cs_seg[r] = seg + 8;
+				} else {
+					cs_s[r] = q + 1;
+					if (sweep == 1) {
+						while (out[start + fill] != 0xffff)
+							fill++;
+						out[start + fill++] = (unsigned short)(ii | first << 9
+							| (cn - 1) << 12);
+					}
+				}
+			}
 		}
 	}
 }
@@ -203,14 +253,15 @@ __device__ __forceinline__ unsigned a3_lds_u16(unsigned addr)
 	return v;
 }
 
-/* pieces of 16 bytes per eta row in shared memory */
-template <int KP> struct A3Row { static constexpr int NP = KP <= 4 ? 4 : 8; };
+/* 16-byte pieces per eta row in shared memory: an odd number, so that the rows
+ * of 8 individuals with different i % 8 start in 8 different bank groups */
+template <int KP> struct A3Row { static constexpr int NP = KP | 1; };
 
 /* bytes of dynamic shared memory; the host planner uses the same formula */
 static inline size_t a3_smem_bytes(int KP, bool em, int max_chunk_rows, int PR,
 	int ncolmax, int cap)
 {
-	const int KR = 2 * KP, NP = KP <= 4 ? 4 : 8;
+	const int KR = 2 * KP, NP = KP | 1;
 	size_t d = (size_t)KR * PR + 16;
 	if (em)
 		d += (size_t)max_chunk_rows * KR + (size_t)A3_IT * NP * 2 + 8 * (size_t)A3_IT
@@ -235,7 +286,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 	constexpr int LT = 8 / PP;
 	constexpr bool EM = (MODE == 0);
 	extern __shared__ __align__(128) double smem3d[];
-	const int t = threadIdx.x, lane = t & 31, m = t & (NP - 1);
+	const int t = threadIdx.x, lane = t & 31;
 	const int PR = a.PR;
 	const int csw = ((a.ncolmax + 1 + 7) / 8) * 8;	/* colstart row, 16-byte multiple */
 
@@ -331,9 +382,8 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 				 * barrier that follows pass 2 */
 				double2 *dst = reinterpret_cast<double2 *>(eta_s + (size_t)t * NP * 2);
 #pragma unroll
-				for (int pc = 0; pc < NP; pc++)
-					dst[pc] = pc < KP ? make_double2(e[2 * pc], e[2 * pc + 1])
-						: make_double2(0.0, 0.0);
+				for (int pc = 0; pc < KP; pc++)
+					dst[pc] = make_double2(e[2 * pc], e[2 * pc + 1]);
 			}
 
 			for (int lt = lt0; lt < lt1; lt++, buf ^= 1) {
@@ -423,9 +473,9 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					continue;
 
 				/* ---- pass 2: G_lj += eta_i w over the lane's entries ---- */
-				double g[2 * NP];
+				double g[KR];
 #pragma unroll
-				for (int k = 0; k < 2 * NP; k++)
+				for (int k = 0; k < KR; k++)
 					g[k] = 0.0;
 				if (A3_LM_COL(lm) != A3_IDLE) {
 					const int S2 = (int)A3_LM_S(lm) * 2;	/* list stride, bytes */
@@ -438,59 +488,61 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					double w = x < xe ? a3_lds_f64(wb + ((ent >> 9) & 7) * (A3_IT * 8)
 						+ (ent & (A3_IT - 1)) * 8) * (double)((ent >> 12) + 1) : 0.0;
 					while (x < xe) {
-						/* piece m ^ s of the row in step s */
-						const unsigned rm = eta_sa + (ent & (A3_IT - 1)) * (NP * 16) + (m << 4);
+						const unsigned rm = eta_sa + (ent & (A3_IT - 1)) * (NP * 16);
 						const double wc = w;
 						x += S2;
 						ent = x < xe ? a3_lds_u16(x) : 0u;
-						double2 v[NP];
+						double2 v[KP];
 #pragma unroll
-						for (int s = 0; s < NP; s++)
-							v[s] = a3_lds_f64x2(rm ^ (s << 4));
+						for (int s = 0; s < KP; s++)
+							v[s] = a3_lds_f64x2(rm + (s << 4));
 						w = x < xe ? a3_lds_f64(wb + ((ent >> 9) & 7) * (A3_IT * 8)
 							+ (ent & (A3_IT - 1)) * 8) * (double)((ent >> 12) + 1) : 0.0;
 #pragma unroll
-						for (int s = 0; s < NP; s++) {
+						for (int s = 0; s < KP; s++) {
 							g[2 * s] = fma(v[s].x, wc, g[2 * s]);
 							g[2 * s + 1] = fma(v[s].y, wc, g[2 * s + 1]);
 						}
 					}
 				}
-				/* the lane's partial sums, un-rotated */
+				/* the lane's partial sums */
 #pragma unroll
-				for (int s = 0; s < NP; s++) {
-					const int pc = m ^ s;
-					if (pc < KP)
-						*reinterpret_cast<double2 *>(part_s + (size_t)t * KR + 2 * pc)
-							= make_double2(g[2 * s], g[2 * s + 1]);
-				}
+				for (int pc = 0; pc < KP; pc++)
+					*reinterpret_cast<double2 *>(part_s + (size_t)t * KR + 2 * pc)
+						= make_double2(g[2 * pc], g[2 * pc + 1]);
 				__syncthreads();
 				if (more)
 					stage_lists(itn, ltn);
 				else
 					a3_cp_async_commit();
 
-				/* ---- fold: 4 adjacent threads <-> (column, piece); each adds
-				 * every 4th partial, two shuffle steps, one of them updates
-				 * the CTA's accumulator (idle items carry 0 lanes) ---- */
+				/* ---- fold: g = 1, 2, 4 or 8 adjacent threads <-> (column, piece);
+				 * each adds every g-th partial, shuffle steps inside the
+				 * group, its first thread updates the CTA's accumulator ---- */
 				for (int fi = 0; fi < a.nfi; fi++) {
 					const uint2 fmi = fi == 0 ? fm : __ldg(a.foldmap
 						+ ((size_t)lt * a.nfi + fi) * A3_THREADS + t);
 					const int S = (int)(fmi.x >> 16);
-					const int lane0 = fmi.x & 0xffffu, pc = fmi.y >> 24;
+					const int lane0 = fmi.x & 0xffffu, pc = (fmi.y >> 24) & 15;
+					const int gg = 1 << (fmi.y >> 28), sub = t & (gg - 1);
 					const double2 *src = reinterpret_cast<const double2 *>(
 						part_s + (size_t)lane0 * KR + 2 * pc);
 					double2 acc = make_double2(0.0, 0.0);
-					for (int sx = t & 3; sx < S; sx += 4) {
+					for (int sx = sub; sx < S; sx += gg) {
 						const double2 v0 = src[(size_t)sx * KP];
 						acc.x += v0.x;
 						acc.y += v0.y;
 					}
-					acc.x += shfl_xor_f64(acc.x, 1);
-					acc.y += shfl_xor_f64(acc.y, 1);
-					acc.x += shfl_xor_f64(acc.x, 2);
-					acc.y += shfl_xor_f64(acc.y, 2);
-					if (S && (t & 3) == 0) {
+#pragma unroll
+					for (int mm = 1; mm < 8; mm <<= 1) {
+						const double vx = shfl_xor_f64(acc.x, mm);
+						const double vy = shfl_xor_f64(acc.y, mm);
+						if (mm < gg) {
+							acc.x += vx;
+							acc.y += vy;
+						}
+					}
+					if (S && sub == 0) {
 						double2 *dst = reinterpret_cast<double2 *>(B_s
 							+ (size_t)(fmi.y & 0xffffffu) * KR + 2 * pc);
 						double2 v = *dst;

@@ -83,7 +83,7 @@ struct mc_ctx {
 	size_t smem3 = 0, smem3_ll = 0;
 	int *d3_lt_ncol = nullptr, *d3_lc_first = nullptr;
 	unsigned short *d3_colinfo = nullptr, *d3_csc = nullptr, *d3_colstart = nullptr;
-	unsigned *d3_lanemap = nullptr;
+	unsigned *d3_lanemap = nullptr, *d3_colmeta = nullptr;
 	uint2 *d3_foldmap = nullptr;
 	unsigned char *d3_codes = nullptr;
 	/* sizes of the partial-sum buffers of the active plan */
@@ -187,7 +187,7 @@ static void free_plan(mc_ctx *c)
 	dfree(c->d2_colstart); dfree(c->d2_csr);
 	c->use2 = false;
 	dfree(c->d3_lt_ncol); dfree(c->d3_lc_first); dfree(c->d3_colinfo);
-	dfree(c->d3_csc); dfree(c->d3_colstart); dfree(c->d3_foldmap);
+	dfree(c->d3_csc); dfree(c->d3_colstart); dfree(c->d3_foldmap); dfree(c->d3_colmeta);
 	dfree(c->d3_lanemap); dfree(c->d3_codes);
 	c->use3 = false;
 }
@@ -743,11 +743,13 @@ static int make_plan3(mc_ctx *c)
 
 	/* lanes per column in proportion to the allele counts (largest
 	 * remainder on count / lanes), lanes handed out in column order */
-	const int nfi = (4 * ncolmax * KP + A3_THREADS - 1) / A3_THREADS;
-	const size_t fstride = (size_t)nfi * A3_THREADS;
 	std::vector<unsigned short> colinfo((size_t)n_ltiles * ncolmax, 0);
+	std::vector<unsigned> colmeta((size_t)n_ltiles * ncolmax, 0);
 	std::vector<unsigned> lanemap((size_t)n_ltiles * A3_THREADS, A3_IDLE);
-	std::vector<uint2> foldmap((size_t)n_ltiles * fstride, make_uint2(0u, 0u));
+	/* fold items of every tile: (column, piece) x group of 1, 2, 4 or 8 threads */
+	struct FoldItem { unsigned x, y; int g; };
+	std::vector<std::vector<FoldItem>> fold((size_t)n_ltiles);
+	size_t max_items = 1;
 	for (int lt = 0; lt < n_ltiles; lt++) {
 		const auto &v = cols[lt];
 		const int ncol = (int)v.size();
@@ -776,23 +778,54 @@ static int make_plan3(mc_ctx *c)
 					b = x;
 			S[b]++; used++;
 		}
+		/* fold groups: double the group of the column with the longest serial
+		 * sum while the items still fit one per thread */
+		std::vector<int> G((size_t)ncol, 1);
+		int items = ncol * KP;
+		for (;;) {
+			int b = -1;
+			for (int x = 0; x < ncol; x++)
+				if (G[x] < 8 && S[x] / G[x] > 4
+					&& (b < 0 || S[x] / (double)G[x] > S[b] / (double)G[b]))
+					b = x;
+			if (b < 0 || items + G[b] * KP > A3_THREADS)
+				break;
+			items += G[b] * KP;
+			G[b] *= 2;
+		}
 		int lane0 = 0;
+		std::vector<int> first_lane((size_t)ncol);
 		for (int x = 0; x < ncol; x++) {
 			const unsigned loc = v[x].second >> 8;
 			colinfo[(size_t)lt * ncolmax + x] = v[x].second;
+			colmeta[(size_t)lt * ncolmax + x] = (unsigned)lane0 | (unsigned)S[x] << 16;
 			for (int sgm = 0; sgm < S[x]; sgm++)
 				lanemap[(size_t)lt * A3_THREADS + lane0 + sgm] = (unsigned)x
 					| (unsigned)sgm << 10 | (unsigned)S[x] << 19 | loc << 29;
-			/* the row inside the locus chunk is added once the chunks are known */
-			for (int pc = 0; pc < KP; pc++)
-				for (int sub = 0; sub < 4; sub++)	/* 4 adjacent fold threads */
-					foldmap[(size_t)lt * fstride + ((size_t)x * KP + pc) * 4 + sub]
-						= make_uint2((unsigned)lane0 | (unsigned)S[x] << 16,
-						(unsigned)(c->off[lt * LT + (int)loc] + (v[x].second & 0xff))
-						| (unsigned)pc << 24);
+			first_lane[x] = lane0;
 			lane0 += S[x];
 		}
+		/* large groups first, so that every group is aligned to its size; the
+		 * row inside the locus chunk is filled in once the chunks are known */
+		for (int g = 8; g >= 1; g >>= 1)
+			for (int x = 0; x < ncol; x++) {
+				if (G[x] != g)
+					continue;
+				const unsigned loc = v[x].second >> 8;
+				int lg = 0;
+				while ((1 << lg) < g)
+					lg++;
+				for (int pc = 0; pc < KP; pc++)
+					for (int sub = 0; sub < g; sub++)
+						fold[lt].push_back({ (unsigned)first_lane[x] | (unsigned)S[x] << 16,
+							(unsigned)(c->off[lt * LT + (int)loc] + (v[x].second & 0xff))
+							| (unsigned)pc << 24 | (unsigned)lg << 28, g });
+			}
+		max_items = std::max(max_items, fold[lt].size());
 	}
+	const int nfi = (int)((max_items + A3_THREADS - 1) / A3_THREADS);
+	const size_t fstride = (size_t)nfi * A3_THREADS;
+	std::vector<uint2> foldmap((size_t)n_ltiles * fstride, make_uint2(0u, 0u));
 
 	/* shared memory: fixed part, the rest holds the chunk's accumulators */
 	const int PR = (max_tile_rows + 1) & ~1;
@@ -869,8 +902,9 @@ static int make_plan3(mc_ctx *c)
 	for (int ch = 0; ch + 1 < (int)lc_first.size(); ch++) {
 		const unsigned row0 = (unsigned)c->off[std::min(L, lc_first[ch] * LT)];
 		for (int lt = lc_first[ch]; lt < lc_first[ch + 1]; lt++)
-			for (int f = 0; f < lt_ncol[lt] * KP * 4; f++)
-				foldmap[(size_t)lt * fstride + f].y -= row0;
+			for (size_t f = 0; f < fold[lt].size(); f++)
+				foldmap[(size_t)lt * fstride + f] = make_uint2(fold[lt][f].x,
+					fold[lt][f].y - row0);
 	}
 
 	Admix3Args &a = c->a3;
@@ -892,6 +926,7 @@ static int make_plan3(mc_ctx *c)
 	if ((rc = upload(c, c->d3_lc_first, lc_first))) return rc;
 	if ((rc = upload(c, c->d3_colinfo, colinfo))) return rc;
 	if ((rc = upload(c, c->d3_foldmap, foldmap))) return rc;
+	if ((rc = upload(c, c->d3_colmeta, colmeta))) return rc;
 	if ((rc = upload(c, c->d3_lanemap, lanemap))) return rc;
 	const size_t ntile = (size_t)n_itiles * n_ltiles;
 	CK(cudaMalloc(&c->d3_codes, ntile * A3_THREADS * 8));
@@ -902,7 +937,7 @@ static int make_plan3(mc_ctx *c)
 	LAUNCH_CHECK("k3_build_codes");
 	const size_t bsm = (size_t)A3_IT * 8 + sizeof(int) * (size_t)ncolmax;
 	k3_build_csc<<<(unsigned)ntile, 128, bsm, c->stream>>>(c->d3_codes, PP, n_ltiles,
-		ncolmax, cap, c->d3_lt_ncol, c->d3_colinfo, c->d3_csc, c->d3_colstart);
+		ncolmax, cap, c->d3_lt_ncol, c->d3_colinfo, c->d3_colmeta, c->d3_csc, c->d3_colstart);
 	LAUNCH_CHECK("k3_build_csc");
 	a.lt_ncol = c->d3_lt_ncol; a.colinfo = c->d3_colinfo; a.foldmap = c->d3_foldmap;
 	a.lanemap = c->d3_lanemap; a.lc_first = c->d3_lc_first; a.off = c->d_off;
