@@ -325,7 +325,8 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 		/* what the NEXT tile needs, fetched one tile ahead: the thread's
 		 * 8 allele codes and its pass-2 / fold assignments in registers,
 		 * the p rows and the entry lists by cp.async */
-		uint2 cw_n = make_uint2(0xffffffffu, 0xffffffffu), fm_n = make_uint2(0u, 0u);
+		uint2 cw_n = make_uint2(0xffffffffu, 0xffffffffu), fm_n = make_uint2(0u, 0u),
+			fm2_n = make_uint2(0u, 0u);
 		unsigned lm_n = A3_IDLE;
 		auto fetch_regs = [&](long long it, int lt) {
 			const size_t tix = (size_t)it * a.n_ltiles + lt;
@@ -333,6 +334,8 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 			if (EM) {
 				lm_n = __ldg(a.lanemap + (size_t)lt * A3_THREADS + t);
 				fm_n = __ldg(a.foldmap + (size_t)lt * a.nfi * A3_THREADS + t);
+				if (a.nfi > 1)
+					fm2_n = __ldg(a.foldmap + ((size_t)lt * a.nfi + 1) * A3_THREADS + t);
 			}
 		};
 		auto stage_p = [&](int lt, int buf) {
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 			}
 
 			for (int lt = lt0; lt < lt1; lt++, buf ^= 1) {
-				const uint2 cw = cw_n, fm = fm_n;
+				const uint2 cw = cw_n, fm = fm_n, fm2 = fm2_n;
 				const unsigned lm = lm_n;
 				const bool last = lt + 1 == lt1;
 				const long long itn = last ? it + 1 : it;
@@ -520,19 +523,33 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 				 * each adds every g-th partial, shuffle steps inside the
 				 * group, its first thread updates the CTA's accumulator ---- */
 				for (int fi = 0; fi < a.nfi; fi++) {
-					const uint2 fmi = fi == 0 ? fm : __ldg(a.foldmap
+					const uint2 fmi = fi == 0 ? fm : fi == 1 ? fm2 : __ldg(a.foldmap
 						+ ((size_t)lt * a.nfi + fi) * A3_THREADS + t);
 					const int S = (int)(fmi.x >> 16);
 					const int lane0 = fmi.x & 0xffffu, pc = (fmi.y >> 24) & 15;
 					const int gg = 1 << (fmi.y >> 28), sub = t & (gg - 1);
 					const double2 *src = reinterpret_cast<const double2 *>(
 						part_s + (size_t)lane0 * KR + 2 * pc);
-					double2 acc = make_double2(0.0, 0.0);
-					for (int sx = sub; sx < S; sx += gg) {
+					/* four independent partial sums keep four loads in flight */
+					double2 acc = make_double2(0.0, 0.0), a1 = acc, a2 = acc, a3 = acc;
+					int sx = sub;
+					for (; sx + 3 * gg < S; sx += 4 * gg) {
+						const double2 v0 = src[(size_t)sx * KP];
+						const double2 v1 = src[(size_t)(sx + gg) * KP];
+						const double2 v2 = src[(size_t)(sx + 2 * gg) * KP];
+						const double2 v3 = src[(size_t)(sx + 3 * gg) * KP];
+						acc.x += v0.x; acc.y += v0.y;
+						a1.x += v1.x; a1.y += v1.y;
+						a2.x += v2.x; a2.y += v2.y;
+						a3.x += v3.x; a3.y += v3.y;
+					}
+					for (; sx < S; sx += gg) {
 						const double2 v0 = src[(size_t)sx * KP];
 						acc.x += v0.x;
 						acc.y += v0.y;
 					}
+					acc.x = (acc.x + a1.x) + (a2.x + a3.x);
+					acc.y = (acc.y + a1.y) + (a2.y + a3.y);
 #pragma unroll
 					for (int mm = 1; mm < 8; mm <<= 1) {
 						const double vx = shfl_xor_f64(acc.x, mm);
