@@ -58,20 +58,15 @@ struct Admix3Args {
 	/* per locus tile (static) */
 	const int *lt_ncol;		/* [n_ltiles] real allele columns */
 	const unsigned short *colinfo;	/* [n_ltiles][ncolmax] locus_in_tile << 8 | allele */
-	const unsigned *lanemap;	/* [n_ltiles][A3_THREADS] pass-2 lane: col | seg << 10 |
-					 * lanes << 19 | locus_in_tile << 29 */
-	const uint2 *foldmap;		/* [n_ltiles][nfi][A3_THREADS] fold thread: x = first lane |
-					 * lanes << 16 (0: idle), y = row in chunk | piece << 24 |
-					 * log2(threads of the group) << 28 */
 	const int *lc_first;		/* [n_lchunks + 1] first locus tile of each chunk */
 	const int *off;			/* [L + 1] prefix sums of J */
 	/* data */
 	const unsigned char *codes;	/* [n_itiles][n_ltiles][A3_THREADS][8] */
 	const unsigned short *csc;	/* [n_itiles][n_ltiles][cap] sorted entries */
-	const unsigned short *colstart;	/* [n_itiles][n_ltiles][csw], csw = ncolmax + 1
-					 * rounded up to a multiple of 8 */
+	const unsigned short *colstart;	/* [n_itiles][n_ltiles][3][csw], csw = ncolmax + 1
+					 * rounded up to a multiple of 8: first entry, first
+					 * lane, locus_in_tile << 8 | allele of every column */
 	int cap;			/* entries per tile: A3_IT * 8 */
-	int nfi;			/* fold items per thread */
 	/* parameters */
 	const double *p, *eta;
 	long long eta_stride;
@@ -109,25 +104,27 @@ __global__ void k3_build_codes(const unsigned char *nat, unsigned char *codes,
 /* entry lists of one (itile, ltile): for every real allele column in `colinfo`
  * order, one entry per (individual, allele) carrying it:
  *     i | first copy << 9 | (count - 1) << 12.
- * The column owns S consecutive pass-2 lanes (colmeta: first lane | S << 16);
- * lane seg reads the entries at start + s * S + seg, s = 0, 1, ...  The eta rows
+ * The column owns S consecutive pass-2 lanes, S chosen per tile from the tile's
+ * own counts so that no lane gets more than q = ceil(entries / A3_THREADS) (+1)
+ * entries; lane seg reads the entries at start + s * S + seg, s = 0, 1, ...  The eta rows
  * of 8 individuals with different i % 8 lie in different bank groups, so an
- * entry is dealt to a lane with (lane % 8) == (i % 8) wherever such a lane still
- * has room; the rest fill the remaining positions in ascending order of i. */
+ * entry is dealt to a slot whose (lane + step) % 8 equals i % 8 wherever such a
+ * slot is still free; the rest fill the remaining positions in ascending order
+ * of i. */
 __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 	int ncolmax, int cap, const int *lt_ncol, const unsigned short *colinfo,
-	const unsigned *colmeta, unsigned short *csc, unsigned short *colstart)
+	unsigned short *csc, unsigned short *colstart)
 {
 	extern __shared__ unsigned char sm3[];
 	unsigned char *cd = sm3;				/* [A3_IT][8] */
-	int *cnt = reinterpret_cast<int *>(sm3 + (size_t)A3_IT * 8);
+	int *cnt = reinterpret_cast<int *>(sm3 + (size_t)A3_IT * 8);	/* [ncolmax] */
+	int *lane_first = cnt + ncolmax;				/* [ncolmax + 1] */
 	const int lt = blockIdx.x % n_ltiles;
 	const int ncol = lt_ncol[lt];
 	const unsigned short *ci = colinfo + (size_t)lt * ncolmax;
-	const unsigned *cm = colmeta + (size_t)lt * ncolmax;
 	unsigned short *out = csc + (size_t)blockIdx.x * cap;
 	const int csw = ((ncolmax + 1 + 7) / 8) * 8;
-	unsigned short *cs = colstart + (size_t)blockIdx.x * csw;
+	unsigned short *cs = colstart + (size_t)blockIdx.x * 3 * csw;
 	const uint2 *src = reinterpret_cast<const uint2 *>(codes) + (size_t)blockIdx.x * A3_THREADS;
 
 	for (int x = threadIdx.x; x < A3_IT; x += blockDim.x)
@@ -154,19 +151,48 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 		}
 		for (int c = ncol; c < csw; c++)
 			cs[c] = (unsigned short)acc;
+		/* lanes of THIS tile: the smallest list length q with
+		 * sum_c ceil(n_c / q) <= A3_THREADS, column c gets ceil(n_c / q) lanes */
+		int q = (acc + A3_THREADS - 1) / A3_THREADS;
+		if (q < 1)
+			q = 1;
+		for (;; q++) {
+			int lanes = 0;
+			for (int c = 0; c < ncol; c++)
+				lanes += (cnt[c] + q - 1) / q;
+			if (lanes <= A3_THREADS)
+				break;
+		}
+		int l0 = 0;
+		for (int c = 0; c < ncol; c++) {
+			lane_first[c] = l0;
+			cs[csw + c] = (unsigned short)l0;
+			l0 += (cnt[c] + q - 1) / q;
+		}
+		lane_first[ncol] = l0;
+		for (int c = ncol; c < csw; c++)
+			cs[csw + c] = (unsigned short)l0;
+		for (int c = 0; c < csw; c++)	/* column -> locus_in_tile << 8 | allele */
+			cs[2 * csw + c] = c < ncol ? ci[c] : 0;
 	}
 	__syncthreads();
 	for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
 		const int ll = ci[c] >> 8, j = ci[c] & 0xff;
 		const int n = cnt[c], start = cs[c];
-		const int lane0 = cm[c] & 0xffff, S = cm[c] >> 16;
+		const int lane0 = lane_first[c], S = lane_first[c + 1] - lane0;
+		if (!n)
+			continue;
 		const int q = n / S, rem = n - q * S;	/* lane seg holds q + (seg < rem) entries */
 		for (int x = 0; x < n; x++)
 			out[start + x] = 0xffff;
-		/* two sweeps over the carriers: the first places the entries that find
-		 * a lane of their residue, the second the others */
+		/* slot (seg, s) belongs to residue class (lane0 + seg + s) % 8: in step s
+		 * the 8 lanes of a quarter warp then want 8 different residues, and every
+		 * lane meets every residue once in 8 steps, so a column finds room for
+		 * all residues however few lanes it owns.  Two sweeps over the carriers:
+		 * the first places the entries that find a slot of their class, the
+		 * second the others */
 		for (int sweep = 0; sweep < 2; sweep++) {
-			int cs_s[8], cs_seg[8];		/* next free slot of every residue */
+			int cs_s[8], cs_seg[8];		/* next free slot of every class */
 			for (int r = 0; r < 8; r++) {
 				cs_s[r] = 0;
 				cs_seg[r] = (r - lane0) & 7;
@@ -182,14 +208,12 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 				if (!cn)
 					continue;
 				const int r = ii & 7;
-				/* skip over slots that do not exist (lanes beyond S or the
+				/* skip over slots that do not exist (segments beyond S, the
 				 * short last step) */
 				int s_ = cs_s[r], seg = cs_seg[r];
 				while (s_ <= q && (seg >= S || (s_ == q && seg >= rem))) {
 					s_++;
-					seg = (r - lane0) & 7;
-					if (seg >= S)
-						s_ = q + 1;	/* the residue has no lane at all */
+					seg = (r - lane0 - s_) & 7;
 				}
 				const bool ok = s_ < q || (s_ == q && seg < rem);
 				if (ok) {
@@ -267,15 +291,9 @@ static inline size_t a3_smem_bytes(int KP, bool em, int max_chunk_rows, int PR,
 		d += (size_t)max_chunk_rows * KR + (size_t)A3_IT * NP * 2 + 8 * (size_t)A3_IT
 			+ (size_t)A3_THREADS * KR;
 	return d * sizeof(double)
-		+ ((em ? (size_t)cap : 0) + (size_t)(ncolmax + 1 + 7) / 8 * 8) * sizeof(unsigned short)
+		+ ((em ? (size_t)cap : 0) + 6 * ((size_t)(ncolmax + 1 + 7) / 8 * 8)) * sizeof(unsigned short)
 		+ 16 * sizeof(int);
 }
-
-/* lane map word: col | seg << 10 | lanes << 19 | locus_in_tile << 29 */
-#define A3_LM_COL(x) ((x) & 1023u)
-#define A3_LM_SEG(x) (((x) >> 10) & 511u)
-#define A3_LM_S(x) (((x) >> 19) & 1023u)
-#define A3_LM_LOC(x) ((x) >> 29)
 
 /* MODE 0: E+M step, MODE 1: log likelihood only */
 template <int KP, int PP, int MODE>
@@ -298,8 +316,11 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 	double *p_s = B_s + (EM ? (size_t)a.max_chunk_rows * KR : 0);	/* [KR][PR] */
 	double *red = p_s + (size_t)KR * PR;				/* [16] */
 	unsigned short *csc_s = reinterpret_cast<unsigned short *>(red + 16);	/* [cap] */
-	unsigned short *cst_s = csc_s + (EM ? a.cap : 0);		/* [csw] */
-	int *rb_s = reinterpret_cast<int *>(cst_s + csw);		/* [2][8] row bases */
+	unsigned short *cst2_s = csc_s + (EM ? a.cap : 0);		/* [2][3][csw]: first entry, first
+									 * lane, locus/allele per column;
+									 * two tiles (the fold still reads
+									 * one while the next one lands) */
+	int *rb_s = reinterpret_cast<int *>(cst2_s + 6 * csw);		/* [2][8] row bases */
 	const unsigned eta_sa = (unsigned)__cvta_generic_to_shared(eta_s);
 	const unsigned w_sa = (unsigned)__cvta_generic_to_shared(w_s);
 	const unsigned csc_sa = (unsigned)__cvta_generic_to_shared(csc_s);
@@ -325,18 +346,12 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 		/* what the NEXT tile needs, fetched one tile ahead: the thread's
 		 * 8 allele codes and its pass-2 / fold assignments in registers,
 		 * the p rows and the entry lists by cp.async */
-		uint2 cw_n = make_uint2(0xffffffffu, 0xffffffffu), fm_n = make_uint2(0u, 0u),
-			fm2_n = make_uint2(0u, 0u);
-		unsigned lm_n = A3_IDLE;
+		uint2 cw_n = make_uint2(0xffffffffu, 0xffffffffu);
+		int tro_n = 0;	/* first allele row of the tile inside the chunk */
 		auto fetch_regs = [&](long long it, int lt) {
 			const size_t tix = (size_t)it * a.n_ltiles + lt;
 			cw_n = __ldg(reinterpret_cast<const uint2 *>(a.codes) + tix * A3_THREADS + t);
-			if (EM) {
-				lm_n = __ldg(a.lanemap + (size_t)lt * A3_THREADS + t);
-				fm_n = __ldg(a.foldmap + (size_t)lt * a.nfi * A3_THREADS + t);
-				if (a.nfi > 1)
-					fm2_n = __ldg(a.foldmap + ((size_t)lt * a.nfi + 1) * A3_THREADS + t);
-			}
+			tro_n = __ldg(a.off + lt * LT) - row0;
 		};
 		auto stage_p = [&](int lt, int buf) {
 			const int lf = lt * LT;
@@ -355,19 +370,20 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 				rb_s[buf * 8 + t] = lf + t < a.L ? a.off[lf + t] - trow0 : 0;
 			a3_cp_async_commit();
 		};
-		auto stage_lists = [&](long long it, int lt) {
+		auto stage_lists = [&](long long it, int lt, int buf) {
 			const size_t tix = (size_t)it * a.n_ltiles + lt;
+			unsigned short *cst_s = cst2_s + buf * 3 * csw;
 			if (t * 8 < a.cap)
 				a3_cp_async16(csc_s + t * 8, a.csc + tix * a.cap + t * 8);
-			if (t * 8 < csw)
-				a3_cp_async16(cst_s + t * 8, a.colstart + tix * csw + t * 8);
+			if (t * 8 < 3 * csw)
+				a3_cp_async16(cst_s + t * 8, a.colstart + tix * 3 * csw + t * 8);
 			a3_cp_async_commit();
 		};
 
 		fetch_regs(it0, lt0);
 		stage_p(lt0, 0);
 		if (EM)
-			stage_lists(it0, lt0);
+			stage_lists(it0, lt0, 0);
 		int buf = 0;
 
 		for (long long it = it0; it < it1; it++) {
@@ -390,13 +406,14 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 			}
 
 			for (int lt = lt0; lt < lt1; lt++, buf ^= 1) {
-				const uint2 cw = cw_n, fm = fm_n, fm2 = fm2_n;
-				const unsigned lm = lm_n;
+				const uint2 cw = cw_n;
+				const int tro = tro_n;
 				const bool last = lt + 1 == lt1;
 				const long long itn = last ? it + 1 : it;
 				const int ltn = last ? lt0 : lt + 1;
 				const bool more = itn < it1;
 				const int *rb = rb_s + buf * 8;
+				const unsigned short *cst_s = cst2_s + buf * 3 * csw;
 
 				if (more)
 					fetch_regs(itn, ltn);
@@ -480,12 +497,20 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 #pragma unroll
 				for (int k = 0; k < KR; k++)
 					g[k] = 0.0;
-				if (A3_LM_COL(lm) != A3_IDLE) {
-					const int S2 = (int)A3_LM_S(lm) * 2;	/* list stride, bytes */
-					const unsigned col = A3_LM_COL(lm);
-					const unsigned wb = w_sa + A3_LM_LOC(lm) * (PP * A3_IT * 8);
+				/* the lane's column: first-lane table of this tile (binary search;
+				 * trailing entries repeat the number of lanes in use) */
+				int col = 0;
+#pragma unroll
+				for (int step = 128; step >= 1; step >>= 1)
+					if (col + step < csw - 1 && (int)cst_s[csw + col + step] <= t)
+						col += step;
+				const int lane0c = cst_s[csw + col], lane1c = cst_s[csw + col + 1];
+				if (t < lane1c) {
+					const int S2 = (lane1c - lane0c) * 2;	/* list stride, bytes */
+					const unsigned wb = w_sa + (unsigned)(cst_s[2 * csw + col] >> 8)
+						* (PP * A3_IT * 8);
 					const unsigned xe = csc_sa + 2u * cst_s[col + 1];
-					unsigned x = csc_sa + 2u * (cst_s[col] + A3_LM_SEG(lm));
+					unsigned x = csc_sa + 2u * (cst_s[col] + (t - lane0c));
 					/* ids and weights are fetched one trip ahead */
 					unsigned ent = x < xe ? a3_lds_u16(x) : 0u;
 					double w = x < xe ? a3_lds_f64(wb + ((ent >> 9) & 7) * (A3_IT * 8)
@@ -515,58 +540,43 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 						= make_double2(g[2 * pc], g[2 * pc + 1]);
 				__syncthreads();
 				if (more)
-					stage_lists(itn, ltn);
+					stage_lists(itn, ltn, buf ^ 1);
 				else
 					a3_cp_async_commit();
 
-				/* ---- fold: g = 1, 2, 4 or 8 adjacent threads <-> (column, piece);
-				 * each adds every g-th partial, shuffle steps inside the
-				 * group, its first thread updates the CTA's accumulator ---- */
-				for (int fi = 0; fi < a.nfi; fi++) {
-					const uint2 fmi = fi == 0 ? fm : fi == 1 ? fm2 : __ldg(a.foldmap
-						+ ((size_t)lt * a.nfi + fi) * A3_THREADS + t);
-					const int S = (int)(fmi.x >> 16);
-					const int lane0 = fmi.x & 0xffffu, pc = (fmi.y >> 24) & 15;
-					const int gg = 1 << (fmi.y >> 28), sub = t & (gg - 1);
+				/* ---- fold: thread <-> (column, piece), lanes in order ---- */
+				for (int f = t; f < a.ncolmax * KP; f += A3_THREADS) {
+					const int cc = f / KP, pc = f - cc * KP;
+					const int lane0 = cst_s[csw + cc], S = cst_s[csw + cc + 1] - lane0;
+					if (S <= 0)
+						continue;
+					const unsigned info = cst_s[2 * csw + cc];
 					const double2 *src = reinterpret_cast<const double2 *>(
 						part_s + (size_t)lane0 * KR + 2 * pc);
 					/* four independent partial sums keep four loads in flight */
 					double2 acc = make_double2(0.0, 0.0), a1 = acc, a2 = acc, a3 = acc;
-					int sx = sub;
-					for (; sx + 3 * gg < S; sx += 4 * gg) {
+					int sx = 0;
+					for (; sx + 3 < S; sx += 4) {
 						const double2 v0 = src[(size_t)sx * KP];
-						const double2 v1 = src[(size_t)(sx + gg) * KP];
-						const double2 v2 = src[(size_t)(sx + 2 * gg) * KP];
-						const double2 v3 = src[(size_t)(sx + 3 * gg) * KP];
+						const double2 v1 = src[(size_t)(sx + 1) * KP];
+						const double2 v2 = src[(size_t)(sx + 2) * KP];
+						const double2 v3 = src[(size_t)(sx + 3) * KP];
 						acc.x += v0.x; acc.y += v0.y;
 						a1.x += v1.x; a1.y += v1.y;
 						a2.x += v2.x; a2.y += v2.y;
 						a3.x += v3.x; a3.y += v3.y;
 					}
-					for (; sx < S; sx += gg) {
+					for (; sx < S; sx++) {
 						const double2 v0 = src[(size_t)sx * KP];
 						acc.x += v0.x;
 						acc.y += v0.y;
 					}
-					acc.x = (acc.x + a1.x) + (a2.x + a3.x);
-					acc.y = (acc.y + a1.y) + (a2.y + a3.y);
-#pragma unroll
-					for (int mm = 1; mm < 8; mm <<= 1) {
-						const double vx = shfl_xor_f64(acc.x, mm);
-						const double vy = shfl_xor_f64(acc.y, mm);
-						if (mm < gg) {
-							acc.x += vx;
-							acc.y += vy;
-						}
-					}
-					if (S && sub == 0) {
-						double2 *dst = reinterpret_cast<double2 *>(B_s
-							+ (size_t)(fmi.y & 0xffffffu) * KR + 2 * pc);
-						double2 v = *dst;
-						v.x += acc.x;
-						v.y += acc.y;
-						*dst = v;
-					}
+					double2 *dst = reinterpret_cast<double2 *>(B_s + (size_t)(tro
+						+ rb[info >> 8] + (int)(info & 0xff)) * KR + 2 * pc);
+					double2 v = *dst;
+					v.x += (acc.x + a1.x) + (a2.x + a3.x);
+					v.y += (acc.y + a1.y) + (a2.y + a3.y);
+					*dst = v;
 				}
 			}
 			if (EM) {

@@ -83,8 +83,6 @@ struct mc_ctx {
 	size_t smem3 = 0, smem3_ll = 0;
 	int *d3_lt_ncol = nullptr, *d3_lc_first = nullptr;
 	unsigned short *d3_colinfo = nullptr, *d3_csc = nullptr, *d3_colstart = nullptr;
-	unsigned *d3_lanemap = nullptr, *d3_colmeta = nullptr;
-	uint2 *d3_foldmap = nullptr;
 	unsigned char *d3_codes = nullptr;
 	/* sizes of the partial-sum buffers of the active plan */
 	int act_tiles = 0, act_chunks = 0, act_units = 0;
@@ -187,8 +185,8 @@ static void free_plan(mc_ctx *c)
 	dfree(c->d2_colstart); dfree(c->d2_csr);
 	c->use2 = false;
 	dfree(c->d3_lt_ncol); dfree(c->d3_lc_first); dfree(c->d3_colinfo);
-	dfree(c->d3_csc); dfree(c->d3_colstart); dfree(c->d3_foldmap); dfree(c->d3_colmeta);
-	dfree(c->d3_lanemap); dfree(c->d3_codes);
+	dfree(c->d3_csc); dfree(c->d3_colstart);
+	dfree(c->d3_codes);
 	c->use3 = false;
 }
 
@@ -738,94 +736,15 @@ static int make_plan3(mc_ctx *c)
 		lt_ncol[lt] = (int)v.size();
 		ncolmax = std::max(ncolmax, (int)v.size());
 	}
-	if (ncolmax > A3_THREADS || ncolmax >= (int)A3_IDLE)
+	if (ncolmax > A3_THREADS || ncolmax >= 255)
 		return MC_OK;	/* more allele columns in a tile than lanes */
 
-	/* lanes per column in proportion to the allele counts (largest
-	 * remainder on count / lanes), lanes handed out in column order */
+	/* column order of every locus tile (most frequent allele first); the lanes
+	 * per column are chosen per tile by k3_build_csc */
 	std::vector<unsigned short> colinfo((size_t)n_ltiles * ncolmax, 0);
-	std::vector<unsigned> colmeta((size_t)n_ltiles * ncolmax, 0);
-	std::vector<unsigned> lanemap((size_t)n_ltiles * A3_THREADS, A3_IDLE);
-	/* fold items of every tile: (column, piece) x group of 1, 2, 4 or 8 threads */
-	struct FoldItem { unsigned x, y; int g; };
-	std::vector<std::vector<FoldItem>> fold((size_t)n_ltiles);
-	size_t max_items = 1;
-	for (int lt = 0; lt < n_ltiles; lt++) {
-		const auto &v = cols[lt];
-		const int ncol = (int)v.size();
-		if (!ncol)
-			continue;
-		double total = 0;
-		for (auto &e : v)
-			total += e.first;
-		std::vector<int> S((size_t)ncol);
-		int used = 0;
-		for (int x = 0; x < ncol; x++) {
-			S[x] = std::max(1, (int)floor(v[x].first * (double)A3_THREADS / total));
-			used += S[x];
-		}
-		while (used > A3_THREADS) {	/* only through the max(1, .) floor */
-			int b = 0;
-			for (int x = 1; x < ncol; x++)
-				if (S[x] > 1 && (S[b] <= 1 || v[x].first / (double)S[x] < v[b].first / (double)S[b]))
-					b = x;
-			S[b]--; used--;
-		}
-		while (used < A3_THREADS) {
-			int b = 0;
-			for (int x = 1; x < ncol; x++)
-				if (v[x].first / (double)S[x] > v[b].first / (double)S[b])
-					b = x;
-			S[b]++; used++;
-		}
-		/* fold groups: double the group of the column with the longest serial
-		 * sum while the items still fit one per thread */
-		std::vector<int> G((size_t)ncol, 1);
-		int items = ncol * KP;
-		for (;;) {
-			int b = -1;
-			for (int x = 0; x < ncol; x++)
-				if (G[x] < 8 && S[x] / G[x] > 4
-					&& (b < 0 || S[x] / (double)G[x] > S[b] / (double)G[b]))
-					b = x;
-			if (b < 0 || items + G[b] * KP > A3_THREADS)
-				break;
-			items += G[b] * KP;
-			G[b] *= 2;
-		}
-		int lane0 = 0;
-		std::vector<int> first_lane((size_t)ncol);
-		for (int x = 0; x < ncol; x++) {
-			const unsigned loc = v[x].second >> 8;
-			colinfo[(size_t)lt * ncolmax + x] = v[x].second;
-			colmeta[(size_t)lt * ncolmax + x] = (unsigned)lane0 | (unsigned)S[x] << 16;
-			for (int sgm = 0; sgm < S[x]; sgm++)
-				lanemap[(size_t)lt * A3_THREADS + lane0 + sgm] = (unsigned)x
-					| (unsigned)sgm << 10 | (unsigned)S[x] << 19 | loc << 29;
-			first_lane[x] = lane0;
-			lane0 += S[x];
-		}
-		/* large groups first, so that every group is aligned to its size; the
-		 * row inside the locus chunk is filled in once the chunks are known */
-		for (int g = 8; g >= 1; g >>= 1)
-			for (int x = 0; x < ncol; x++) {
-				if (G[x] != g)
-					continue;
-				const unsigned loc = v[x].second >> 8;
-				int lg = 0;
-				while ((1 << lg) < g)
-					lg++;
-				for (int pc = 0; pc < KP; pc++)
-					for (int sub = 0; sub < g; sub++)
-						fold[lt].push_back({ (unsigned)first_lane[x] | (unsigned)S[x] << 16,
-							(unsigned)(c->off[lt * LT + (int)loc] + (v[x].second & 0xff))
-							| (unsigned)pc << 24 | (unsigned)lg << 28, g });
-			}
-		max_items = std::max(max_items, fold[lt].size());
-	}
-	const int nfi = (int)((max_items + A3_THREADS - 1) / A3_THREADS);
-	const size_t fstride = (size_t)nfi * A3_THREADS;
-	std::vector<uint2> foldmap((size_t)n_ltiles * fstride, make_uint2(0u, 0u));
+	for (int lt = 0; lt < n_ltiles; lt++)
+		for (size_t x = 0; x < cols[lt].size(); x++)
+			colinfo[(size_t)lt * ncolmax + x] = cols[lt][x].second;
 
 	/* shared memory: fixed part, the rest holds the chunk's accumulators */
 	const int PR = (max_tile_rows + 1) & ~1;
@@ -897,16 +816,6 @@ static int make_plan3(mc_ctx *c)
 	}
 	const int n_lchunks = (int)lc_first.size() - 1;
 
-	if (c->T >= (1 << 24))
-		return MC_OK;
-	for (int ch = 0; ch + 1 < (int)lc_first.size(); ch++) {
-		const unsigned row0 = (unsigned)c->off[std::min(L, lc_first[ch] * LT)];
-		for (int lt = lc_first[ch]; lt < lc_first[ch + 1]; lt++)
-			for (size_t f = 0; f < fold[lt].size(); f++)
-				foldmap[(size_t)lt * fstride + f] = make_uint2(fold[lt][f].x,
-					fold[lt][f].y - row0);
-	}
-
 	Admix3Args &a = c->a3;
 	memset(&a, 0, sizeof a);
 	a.K = K;
@@ -914,33 +823,28 @@ static int make_plan3(mc_ctx *c)
 	a.n_ichunks = n_ichunks; a.n_units = n_lchunks * n_ichunks;
 	a.I = c->I; a.Ipad = n_itiles * A3_IT; a.T = c->T; a.L = L;
 	a.ncolmax = ncolmax; a.max_chunk_rows = max_chunk_rows; a.PR = PR; a.cap = cap;
-	a.nfi = nfi;
 	c->KP3 = KP;
 	c->smem3 = a3_smem_bytes(KP, true, max_chunk_rows, PR, ncolmax, cap);
 	c->smem3_ll = a3_smem_bytes(KP, false, max_chunk_rows, PR, ncolmax, cap);
 	c->grid3 = (int)std::min<long long>(a.n_units, sms);
-	(void)fstride;
 
 	int rc;
 	if ((rc = upload(c, c->d3_lt_ncol, lt_ncol))) return rc;
 	if ((rc = upload(c, c->d3_lc_first, lc_first))) return rc;
 	if ((rc = upload(c, c->d3_colinfo, colinfo))) return rc;
-	if ((rc = upload(c, c->d3_foldmap, foldmap))) return rc;
-	if ((rc = upload(c, c->d3_colmeta, colmeta))) return rc;
-	if ((rc = upload(c, c->d3_lanemap, lanemap))) return rc;
 	const size_t ntile = (size_t)n_itiles * n_ltiles;
 	CK(cudaMalloc(&c->d3_codes, ntile * A3_THREADS * 8));
 	CK(cudaMalloc(&c->d3_csc, ntile * cap * sizeof(unsigned short)));
-	CK(cudaMalloc(&c->d3_colstart, ntile * (size_t)((ncolmax + 1 + 7) / 8 * 8) * sizeof(unsigned short)));
+	CK(cudaMalloc(&c->d3_colstart, ntile * 3 * (size_t)((ncolmax + 1 + 7) / 8 * 8) * sizeof(unsigned short)));
 	k3_build_codes<<<grid_for(c, (long long)ntile * A3_THREADS, 256), 256, 0, c->stream>>>(
 		c->d_nat, c->d3_codes, c->I, L, c->P, PP, (int)n_itiles, n_ltiles);
 	LAUNCH_CHECK("k3_build_codes");
-	const size_t bsm = (size_t)A3_IT * 8 + sizeof(int) * (size_t)ncolmax;
+	const size_t bsm = (size_t)A3_IT * 8 + sizeof(int) * (2 * (size_t)ncolmax + 1);
 	k3_build_csc<<<(unsigned)ntile, 128, bsm, c->stream>>>(c->d3_codes, PP, n_ltiles,
-		ncolmax, cap, c->d3_lt_ncol, c->d3_colinfo, c->d3_colmeta, c->d3_csc, c->d3_colstart);
+		ncolmax, cap, c->d3_lt_ncol, c->d3_colinfo, c->d3_csc, c->d3_colstart);
 	LAUNCH_CHECK("k3_build_csc");
-	a.lt_ncol = c->d3_lt_ncol; a.colinfo = c->d3_colinfo; a.foldmap = c->d3_foldmap;
-	a.lanemap = c->d3_lanemap; a.lc_first = c->d3_lc_first; a.off = c->d_off;
+	a.lt_ncol = c->d3_lt_ncol; a.colinfo = c->d3_colinfo;
+	 a.lc_first = c->d3_lc_first; a.off = c->d_off;
 	a.codes = c->d3_codes; a.csc = c->d3_csc; a.colstart = c->d3_colstart;
 	if ((rc = alloc_outputs(c, n_lchunks, n_ichunks, a.n_units, a.Ipad))) return rc;
 	a.Apart = c->d_Apart; a.Npart = c->d_Npart; a.llpart = c->d_llpart;
