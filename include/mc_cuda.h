@@ -104,6 +104,20 @@ int mc_init_admixture(mc_ctx *ctx, int slot, const uint8_t *z);
  * individuals (eta rows of `slot` are final, the allele counts are left in
  * the exchange buffer); sum over ranks, then mc_em_step_finish(slot) */
 int mc_init_admixture_local(mc_ctx *ctx, int slot, const uint8_t *z);
+/* The same initialiser with the draws made on the device (SURVEY.md 8f rank 1:
+ * at I*L*P = 2e9 copies the host loop over rand() costs more than the fit).
+ * The reference's generator is glibc's TYPE_3 rand(): x[n] = x[n-31] + x[n-3]
+ * mod 2^32, rand() = x[n] >> 1 (rnd_init.c:460-481 draws k = rand() % K per
+ * copy).  The host cuts this context's I*L*P draws into n_blocks blocks of
+ * block_draws (a multiple of 16; the last block may be short) and hands over,
+ * for every block, the 31 words x[n-31 .. n-1] in front of its first draw
+ * (hist[n_blocks][31]); it owns the stream and advances it by the same number
+ * of draws (host/mc_rand.h: mcr_jump_matrix / mcr_apply).  Results are
+ * bit-identical to mc_init_admixture with the z the host loop would draw. */
+int mc_init_admixture_rand(mc_ctx *ctx, int slot, const uint32_t *hist,
+	int64_t n_blocks, int64_t block_draws);
+int mc_init_admixture_rand_local(mc_ctx *ctx, int slot, const uint32_t *hist,
+	int64_t n_blocks, int64_t block_draws);
 
 /* ---- the hot path ------------------------------------------------------ */
 

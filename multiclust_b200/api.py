@@ -15,7 +15,7 @@ SYMBOLS = [
     "mc_last_error", "mc_abi_version", "mc_create", "mc_destroy",
     "mc_set_stream", "mc_sync", "mc_ctx_device", "mc_ctx_stream", "mc_set_data", "mc_set_data_synth",
     "mc_get_dims", "mc_get_J", "mc_get_codes", "mc_alloc_model", "mc_eta_len",
-    "mc_set_params", "mc_get_params", "mc_init_admixture", "mc_init_admixture_local", "mc_em_step", "mc_loglik", "mc_read_ll",
+    "mc_set_params", "mc_get_params", "mc_init_admixture", "mc_init_admixture_local", "mc_init_admixture_rand", "mc_init_admixture_rand_local", "mc_em_step", "mc_loglik", "mc_read_ll",
     "mc_get_posterior", "mc_partition", "mc_delta", "mc_step_dots",
     "mc_qn_dots", "mc_accel_update", "mc_qn_update", "mc_project",
     "mc_copy_slot", "mc_em_step_local", "mc_exchange_buffer",
@@ -92,6 +92,8 @@ def load_library():
     L.mc_get_params.argtypes = [vp, C.c_int, vp, vp]
     L.mc_init_admixture.argtypes = [vp, C.c_int, vp]
     L.mc_init_admixture_local.argtypes = [vp, C.c_int, vp]
+    L.mc_init_admixture_rand.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int64]
+    L.mc_init_admixture_rand_local.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int64]
     L.mc_em_step.argtypes = [vp, C.c_int, C.c_int, dp]
     L.mc_loglik.argtypes = [vp, C.c_int, dp]
     L.mc_read_ll.argtypes = [vp, dp]
@@ -213,6 +215,13 @@ class Context:
         z = np.ascontiguousarray(z, dtype=np.uint8)
         assert z.size == self.I * self.L * self.P
         self._ck(self.lib.mc_init_admixture(self.h, slot, _ptr(z)), "mc_init_admixture")
+
+    def init_admixture_rand(self, slot, hist, block_draws):
+        """draws made on the device from per-block generator histories [n_blocks][31]"""
+        hist = np.ascontiguousarray(hist, dtype=np.uint32)
+        assert hist.ndim == 2 and hist.shape[1] == 31
+        self._ck(self.lib.mc_init_admixture_rand(self.h, slot, _ptr(hist), hist.shape[0],
+                                                 int(block_draws)), "mc_init_admixture_rand")
 
     # -- hot path
     def em_step(self, frm=0, to=0):

@@ -1327,22 +1327,11 @@ extern "C" int mc_init_admixture(mc_ctx *c, int slot, const uint8_t *z)
 	return rc;
 }
 
-extern "C" int mc_init_admixture_local(mc_ctx *c, int slot, const uint8_t *z)
+/* counts + M-step from the assignment d_z (device), which is freed */
+static int init_from_assignment(mc_ctx *c, int slot, unsigned char *d_z)
 {
-	NEED_MODEL();
-	CHECK_SLOT(slot);
-	if (!z)
-		return fail(c, MC_ERR_ARG, "mc_init_admixture: null assignment");
-	if (!c->admixture)
-		return fail(c, MC_ERR_STATE, "mc_init_admixture: not an admixture model");
-	if (c->K > 255)
-		return fail(c, MC_ERR_UNSUPPORTED, "mc_init_admixture: K > 255");
-	const size_t n = (size_t)c->I * c->L * c->P;
-	unsigned char *d_z = nullptr;
 	unsigned *d_N = nullptr;
-	CK(cudaMalloc(&d_z, n));
 	CK(cudaMalloc(&d_N, sizeof(unsigned) * (size_t)std::max<int64_t>(c->np, 1)));
-	CK(cudaMemcpyAsync(d_z, z, n, cudaMemcpyHostToDevice, c->stream));
 	CK(cudaMemsetAsync(d_N, 0, sizeof(unsigned) * (size_t)std::max<int64_t>(c->np, 1), c->stream));
 	k_init_counts<<<grid_for(c, c->I, 128), 128, 0, c->stream>>>(c->d_nat, d_z,
 		c->I, c->L, c->P, c->K, c->d_off, c->T, c->d_post, d_N);
@@ -1361,6 +1350,68 @@ extern "C" int mc_init_admixture_local(mc_ctx *c, int slot, const uint8_t *z)
 	cudaFree(d_z);
 	cudaFree(d_N);
 	return MC_OK;
+}
+
+static int init_checks(mc_ctx *c, int slot, const void *arg)
+{
+	NEED_MODEL();
+	CHECK_SLOT(slot);
+	if (!arg)
+		return fail(c, MC_ERR_ARG, "mc_init_admixture: null argument");
+	if (!c->admixture)
+		return fail(c, MC_ERR_STATE, "mc_init_admixture: not an admixture model");
+	if (c->K > 255)
+		return fail(c, MC_ERR_UNSUPPORTED, "mc_init_admixture: K > 255");
+	return MC_OK;
+}
+
+extern "C" int mc_init_admixture_local(mc_ctx *c, int slot, const uint8_t *z)
+{
+	int rc = init_checks(c, slot, z);
+	if (rc)
+		return rc;
+	const size_t n = (size_t)c->I * c->L * c->P;
+	unsigned char *d_z = nullptr;
+	CK(cudaMalloc(&d_z, n ? n : 1));
+	CK(cudaMemcpyAsync(d_z, z, n, cudaMemcpyHostToDevice, c->stream));
+	return init_from_assignment(c, slot, d_z);
+}
+
+extern "C" int mc_init_admixture_rand_local(mc_ctx *c, int slot, const uint32_t *hist,
+	int64_t n_blocks, int64_t block_draws)
+{
+	int rc = init_checks(c, slot, hist);
+	if (rc)
+		return rc;
+	const long long n = (long long)c->I * c->L * c->P;
+	if (block_draws < 1 || block_draws % 16 || n_blocks * block_draws < n
+		|| (n_blocks - 1) * block_draws >= std::max<long long>(n, 1))
+		return fail(c, MC_ERR_ARG, "mc_init_admixture_rand: %lld blocks of %lld draws "
+			"do not tile the %lld allele copies (blocks must be multiples of 16)",
+			(long long)n_blocks, (long long)block_draws, n);
+	unsigned char *d_z = nullptr;
+	unsigned *d_h = nullptr;
+	CK(cudaMalloc(&d_z, n ? (size_t)n : 1));
+	CK(cudaMalloc(&d_h, sizeof(unsigned) * 31 * (size_t)n_blocks));
+	CK(cudaMemcpyAsync(d_h, hist, sizeof(unsigned) * 31 * (size_t)n_blocks,
+		cudaMemcpyHostToDevice, c->stream));
+	k_rand_assign<<<(unsigned)((n_blocks + 63) / 64), 64, 0, c->stream>>>(d_h, n_blocks,
+		block_draws, n, (unsigned)c->K, d_z);
+	LAUNCH_CHECK("k_rand_assign");
+	rc = init_from_assignment(c, slot, d_z);
+	cudaFree(d_h);
+	return rc;
+}
+
+extern "C" int mc_init_admixture_rand(mc_ctx *c, int slot, const uint32_t *hist,
+	int64_t n_blocks, int64_t block_draws)
+{
+	int rc = mc_init_admixture_rand_local(c, slot, hist, n_blocks, block_draws);
+	if (rc)
+		return rc;
+	rc = mc_em_step_finish(c, slot, nullptr);
+	CK(cudaStreamSynchronize(c->stream));
+	return rc;
 }
 
 extern "C" int mc_em_step(mc_ctx *c, int from, int to, double *ll)

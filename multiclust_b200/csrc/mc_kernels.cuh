@@ -907,6 +907,54 @@ __global__ void k_init_counts(const unsigned char *nat, const unsigned char *z,
 	}
 }
 
+/* the reference's cluster draws made on the device: thread b continues glibc's
+ * TYPE_3 rand() -- x[n] = x[n-31] + x[n-3] mod 2^32, draw = x[n] >> 1 -- from
+ * the 31 words in front of its block of draws and writes z = draw % K for the
+ * block's allele copies (rnd_init.c:460-481).  The 31 words stay in registers:
+ * 496 = 16 x 31 draws per round, all indices static. */
+#define MC_RAND_ROUND 496
+__global__ void k_rand_assign(const unsigned *hist, long long n_blocks, long long block_draws,
+	long long n, unsigned K, unsigned char *z)
+{
+	const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	if (b >= n_blocks)
+		return;
+	unsigned h[31];
+#pragma unroll
+	for (int j = 0; j < 31; j++)
+		h[j] = hist[(size_t)b * 31 + j];
+	const long long first = b * block_draws;
+	const long long cnt = n - first < block_draws ? n - first : block_draws;
+	unsigned char *out = z + first;
+	long long done = 0;
+	for (; done + MC_RAND_ROUND <= cnt; done += MC_RAND_ROUND) {
+#pragma unroll
+		for (int g = 0; g < 31; g++) {
+			unsigned w[4] = { 0u, 0u, 0u, 0u };
+#pragma unroll
+			for (int q = 0; q < 16; q++) {
+				const int i = (g * 16 + q) % 31;
+				h[i] += h[(i + 28) % 31];
+				w[q >> 2] |= ((h[i] >> 1) % K) << ((q & 3) * 8);
+			}
+			*reinterpret_cast<uint4 *>(out + done + g * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+		}
+	}
+	if (done < cnt) {	/* tail of the last block: a circular buffer in local memory */
+		unsigned t[31];
+#pragma unroll
+		for (int j = 0; j < 31; j++)
+			t[j] = h[j];
+		int f = 0;
+		for (; done < cnt; done++) {
+			t[f] += t[f >= 3 ? f - 3 : f + 28];
+			out[done] = (unsigned char)((t[f] >> 1) % K);
+			if (++f == 31)
+				f = 0;
+		}
+	}
+}
+
 __global__ void k_u32_to_f64(const unsigned *x, double *y, long long n)
 {
 	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;

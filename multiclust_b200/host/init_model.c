@@ -6,8 +6,9 @@
  * initialisations and all K (multiclust.c:516-531, never reseeded unless -r) --
  * and parity needs the same stream, so the draws are made here on the host in
  * the reference's order, from the bit-identical generator of mc_rand.h.  What is done with them runs on the device:
- *   admixture: one cluster per allele copy -> hard-assignment counts and the
- *              M-step (mc_init_admixture);
+ *   admixture: one cluster per allele copy, drawn on the device from the
+ *              stream positions the host computes (mc_init_admixture_rand),
+ *              -> hard-assignment counts and the M-step;
  *   mixture:   K random centre individuals, nearest-centre partition, smoothed
  *              counts; the O(I*L) counting is done here on the 8-bit codes and
  *              the resulting parameters are uploaded (mc_set_params).
@@ -20,32 +21,58 @@
 
 #define GPU(call) gpu_check(mod, (call), #call)
 
-/* rnd_init.c:456-482: k = rand() % K for every copy, missing ones included */
+/* draws per device thread: a multiple of the kernel's 496-draw round */
+#define RAND_BLOCK (496LL * 64)
+
+/* rnd_init.c:456-482: k = rand() % K for every copy, missing ones included.
+ * The draws are made on the device (mc_init_admixture_rand): the stream is a
+ * linear recurrence, so the host only computes where every block of RAND_BLOCK
+ * draws starts -- one 31 x 31 matrix-vector product per block -- and advances
+ * its own generator by the same I*L*P draws.  With --gpus N device r draws for
+ * its rows of individuals, i.e. from draw row_first[r]*L*P on. */
 static int random_initialize_admixture(options *opt, data *dat, model *mod)
 {
-	const size_t n = (size_t)dat->I * dat->L * dat->ploidy;
-	uint8_t *z = malloc(n ? n : 1);
+	static uint32_t jump[MCR_LAG * MCR_LAG];
+	static int have_jump;
+	uint32_t h[MCR_LAG];
+	const long long per_row = (long long)dat->L * dat->ploidy;
 
 	(void)opt;
-	if (!z)
-		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "allele partition\n");
-	for (size_t x = 0; x < n; x++)
-		z[x] = (uint8_t)(mcr_next(mod->rng) % mod->K);
-	if (mod->n_gpus == 1) {
-		GPU(mc_init_admixture(mod->gpu, mod->tindex, z));
-	} else {
-		/* each device counts its rows of z; the allele counts are summed
-		 * over devices before p is normalised */
-		for (int r = 0; r < mod->n_gpus; r++)
-			GPU(mc_init_admixture_local(mod->gpus[r], mod->tindex,
-				z + (size_t)mod->row_first[r] * dat->L * dat->ploidy));
+	if (!have_jump) {
+		mcr_jump_matrix(RAND_BLOCK, jump);
+		have_jump = 1;
+	}
+	mcr_history(mod->rng, h);
+	for (int r = 0; r < mod->n_gpus; r++) {
+		const long long n = (long long)(mod->row_first[r + 1] - mod->row_first[r]) * per_row;
+		const long long nb = n ? (n + RAND_BLOCK - 1) / RAND_BLOCK : 1;
+		uint32_t *hist = malloc(sizeof *hist * MCR_LAG * (size_t)nb);
+
+		if (!hist)
+			return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "generator states\n");
+		for (long long b = 0; b < nb; b++) {
+			memcpy(hist + b * MCR_LAG, h, sizeof h);
+			if (b + 1 < nb)
+				mcr_apply(jump, h);
+			else
+				mcr_step_history(h, n - b * RAND_BLOCK);
+		}
+		if (mod->n_gpus == 1)
+			GPU(mc_init_admixture_rand(mod->gpus[r], mod->tindex, hist, nb, RAND_BLOCK));
+		else
+			GPU(mc_init_admixture_rand_local(mod->gpus[r], mod->tindex, hist, nb,
+				RAND_BLOCK));
+		free(hist);
+	}
+	mcr_from_history(mod->rng, h);
+	if (mod->n_gpus > 1) {
+		/* the allele counts are summed over devices before p is normalised */
 		if (mc_comm_exchange(mod->comm) != MC_OK)
 			return mmessage(ERROR_MSG, GPU_ERROR, "%s\n",
 				mc_comm_last_error(mod->comm));
 		for (int r = 0; r < mod->n_gpus; r++)
 			GPU(mc_em_step_finish(mod->gpus[r], mod->tindex, NULL));
 	}
-	free(z);
 	return NO_ERROR;
 }
 

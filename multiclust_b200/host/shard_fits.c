@@ -83,9 +83,18 @@ static void job_release(fit_job *job)
 static void skip_draws(const options *opt, const data *dat, int K, mcr_state *rng)
 {
 	if (opt->admixture) {
-		const size_t n = (size_t)dat->I * dat->L * dat->ploidy;
-		for (size_t x = 0; x < n; x++)
-			(void)mcr_next(rng);
+		/* I*L*P draws whatever K: one matrix-vector product */
+		static uint32_t jump[MCR_LAG * MCR_LAG];
+		static long long jump_n = -1;
+		const long long n = (long long)dat->I * dat->L * dat->ploidy;
+		uint32_t h[MCR_LAG];
+		if (jump_n != n) {
+			mcr_jump_matrix(n, jump);
+			jump_n = n;
+		}
+		mcr_history(rng, h);
+		mcr_apply(jump, h);
+		mcr_from_history(rng, h);
 	} else if (K > 1) {
 		/* rnd_init.c:205-217, the draws only */
 		int *center = malloc(sizeof *center * (size_t)K);

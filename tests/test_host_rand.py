@@ -53,3 +53,49 @@ def test_mc_rand_equals_glibc_rand(tmp_path):
                            os.path.join(HOST, "mc_rand.c")])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout
+
+
+JUMP = r"""
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "mc_rand.h"
+int main(void)
+{
+	static uint32_t M[MCR_LAG * MCR_LAG];
+	const long long jumps[] = { 0, 1, 2, 30, 31, 32, 496, 31744, 1000003 };
+	for (unsigned k = 0; k < sizeof jumps / sizeof *jumps; k++) {
+		mcr_state a, b;
+		uint32_t h[MCR_LAG], g[MCR_LAG];
+		mcr_seed(&a, 12345);
+		for (int i = 0; i < 77; i++)
+			(void)mcr_next(&a);	/* an arbitrary position, f != 0 */
+		b = a;
+		mcr_history(&a, h);
+		memcpy(g, h, sizeof g);
+		mcr_jump_matrix(jumps[k], M);
+		mcr_apply(M, h);		/* by matrix */
+		mcr_step_history(g, jumps[k]);	/* by stepping the history */
+		for (long long i = 0; i < jumps[k]; i++)
+			(void)mcr_next(&b);	/* by drawing */
+		if (memcmp(h, g, sizeof h)) { printf("matrix != stepping at %lld\n", jumps[k]); return 1; }
+		mcr_from_history(&a, h);
+		for (int i = 0; i < 100; i++)
+			if (mcr_next(&a) != mcr_next(&b)) { printf("stream differs after jump %lld\n", jumps[k]); return 1; }
+	}
+	printf("ok\n");
+	return 0;
+}
+"""
+
+
+def test_mc_rand_jump_ahead(tmp_path):
+    """the generator as a linear recurrence: advancing by a matrix power, by
+    stepping the 31-word history and by drawing give the same stream"""
+    src = tmp_path / "j.c"
+    src.write_text(JUMP)
+    exe = str(tmp_path / "j")
+    subprocess.check_call(["gcc", "-std=c17", "-O2", "-I" + HOST, "-o", exe, str(src),
+                           os.path.join(HOST, "mc_rand.c")])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout
