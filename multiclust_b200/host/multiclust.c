@@ -24,6 +24,17 @@
 #include "mc_format.h"
 #include "multiclust.h"
 
+/* --timing: wall-clock seconds of every phase on stderr */
+static double wall_now(void)
+{
+	struct timespec ts;
+
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+static int g_timing;
+static double g_t_init, g_t_em, g_t_write;
+
 /* the initialisers' random stream: glibc's rand() state after no srand()
  * call equals srand(1) */
 static mcr_state g_rng;
@@ -214,6 +225,7 @@ void fprint_usage(FILE *fp, const char *cmd)
 "  --gpus <n>    shard the individuals of one fit over n devices (NCCL exchange)\n"
 "  --shard-fits  with --gpus: deal whole fits (K, initialisation) to the devices\n"
 "  --trace <f>   write every log likelihood at full precision to <f>\n"
+"  --timing      wall-clock seconds of every phase on stderr\n"
 "  --dump <pre>  binary parameters before / after every fit to <pre>.K*.init*.bin\n"
 "  --parse-only <f>  read and recode the data, write it as MCB1 to <f>, stop\n", cmd);
 }
@@ -425,6 +437,10 @@ int parse_options(options *opt, data *dat, int argc, const char **argv)
 				if (++i >= argc)
 					goto bad_arg;
 				opt->trace_file = argv[i];
+				break;
+			}
+			if (!strncmp(name, "ti", 2)) {	/* --timing */
+				opt->timing = 1;
 				break;
 			}
 			if (read_int_arg(argc, argv, ++i, 0, &tmp))
@@ -645,6 +661,8 @@ static int write_best_from_device(options *opt, data *dat, model *mod, void *ctx
 {
 	int err;
 
+	const double t0 = wall_now();
+
 	(void)ctx;
 	if ((err = fetch_results(opt, dat, mod)))
 		return err;
@@ -652,7 +670,9 @@ static int write_best_from_device(options *opt, data *dat, model *mod, void *ctx
 		partition_admixture(dat, mod);
 	else
 		partition_mixture(dat, mod);
-	return write_result_files(opt, dat, mod);
+	err = write_result_files(opt, dat, mod);
+	g_t_write += wall_now() - t0;
+	return err;
 }
 
 int record_fit_public(options *opt, data *dat, model *mod, int i,
@@ -694,11 +714,15 @@ int maximize_likelihood(options *opt, data *dat, model *mod, int bootstrap)
 		mod->iter_stop = 0;
 		if (mod->trace)
 			fprintf(mod->trace, "init %d %d\n", mod->K, i);
+		double t0 = wall_now();
 		if ((err = initialize_model(opt, dat, mod)))
 			return err;
+		g_t_init += wall_now() - t0;
 		if (opt->dump_prefix && (err = dump_state(opt, dat, mod, i, "start", mod->tindex)))
 			return err;
+		t0 = wall_now();
 		em(opt, dat, mod);
+		g_t_em += wall_now() - t0;
 		if (opt->dump_prefix && (err = dump_state(opt, dat, mod, i, "final", mod->pindex)))
 			return err;
 
@@ -820,8 +844,12 @@ int main(int argc, const char **argv)
 		goto done;
 	if ((err = parse_options(opt, dat, argc, argv)))
 		goto done;
+	g_timing = opt->timing;
+	const double t_start = wall_now();
+	start_device_contexts(opt);
 	if ((err = read_file(opt, dat)))
 		goto done;
+	const double t_read = wall_now();
 	if (opt->verbosity >= TALKATIVE)
 		mmessage(INFO_MSG, NO_ERROR, "Finished reading data: %u %u-ploid "
 			"individuals at %u loci.\n", dat->I, dat->ploidy, dat->L);
@@ -852,12 +880,20 @@ int main(int argc, const char **argv)
 	}
 	if ((err = upload_data(opt, dat, mod)))
 		goto done;
+	const double t_upload = wall_now();
 	if (opt->n_repeat > 1)
 		err = timed_model_estimation(opt, dat, mod);
 	else if (opt->n_repeat == 1)
 		err = estimate_model(opt, dat, mod, 0);
 	if (!err && opt->parallel)
 		printf("%f\n", mod->max_logL);
+	if (g_timing)
+		fprintf(stderr, "timing (s): read %.3f, upload %.3f, plan+other %.3f, initialise "
+			"%.3f, em %.3f (%d iterations), fetch+write %.3f, total %.3f\n",
+			t_read - t_start, t_upload - t_read,
+			wall_now() - t_upload - g_t_init - g_t_em - g_t_write, g_t_init,
+			g_t_em, mod->n_total_iter ? mod->n_total_iter : mod->n_iter, g_t_write,
+			wall_now() - t_start);
 done:
 	free_model(mod, opt);
 	free_options(opt);

@@ -94,6 +94,7 @@ struct _options {
 	const char *trace_file;		/* --trace: every log likelihood, %.17g */
 	const char *dump_prefix;	/* --dump: binary parameters per fit */
 	const char *parse_only;		/* --parse-only: MCB1 file to write */
+	int timing;			/* --timing: wall-clock seconds per phase on stderr */
 	int shard_fits;			/* --shard-fits: with --gpus N, deal whole fits
 					 * (K, initialisation) to the devices instead of
 					 * sharding the individuals of one fit */
@@ -186,6 +187,7 @@ void fprint_usage(FILE *fp, const char *cmd);
 /* ---- input (reference read_file.c) ---- */
 int read_file(options *opt, data *dat);
 int upload_data(options *opt, data *dat, model *mod);
+void start_device_contexts(options *opt);	/* CUDA start-up overlapped with the parse */
 
 /* ---- EM hot path (reference multiclust.h:371-388) ---- */
 int initialize_model(options *opt, data *dat, model *mod);

@@ -19,6 +19,8 @@
 #include <errno.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <pthread.h>
 
 #include "mc_format.h"
 #include "multiclust.h"
@@ -344,6 +346,37 @@ int read_file(options *opt, data *dat)
 	return NO_ERROR;
 }
 
+/* CUDA contexts take 1-3 s to come up; they are created by a helper thread
+ * while the main thread reads and recodes the data file */
+static struct {
+	pthread_t thread;
+	int started, n, device, rc[64];
+	mc_ctx *ctx[64];
+	double seconds;
+} g_early;
+
+static void *early_main(void *arg)
+{
+	struct timespec t0, t1;
+
+	(void)arg;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for (int r = 0; r < g_early.n; r++)
+		g_early.rc[r] = mc_create(&g_early.ctx[r], g_early.device + r);
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	g_early.seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+	return NULL;
+}
+
+void start_device_contexts(options *opt)
+{
+	if (opt->parse_only || opt->n_gpus > 64 || (opt->shard_fits && opt->n_gpus > 1))
+		return;
+	g_early.n = opt->n_gpus;
+	g_early.device = opt->device;
+	g_early.started = !pthread_create(&g_early.thread, NULL, early_main, NULL);
+}
+
 /* hand the recoded genotypes to the device(s): with --gpus N device r gets
  * the individuals [r*I/N, (r+1)*I/N) and the allele slots of the whole sample */
 int upload_data(options *opt, data *dat, model *mod)
@@ -361,10 +394,21 @@ int upload_data(options *opt, data *dat, model *mod)
 			"number of individuals (%d)\n", n, dat->I);
 	for (int r = 0; r <= n; r++)
 		mod->row_first[r] = (int)((long long)dat->I * r / n);
+	if (g_early.started) {
+		pthread_join(g_early.thread, NULL);
+		g_early.started = 0;
+		if (opt->timing)
+			fprintf(stderr, "timing (s): %d device context(s) %.3f, overlapped with "
+				"reading the data\n", g_early.n, g_early.seconds);
+	}
 	for (int r = 0; r < n; r++) {
 		const int rows = mod->row_first[r + 1] - mod->row_first[r];
-		if ((rc = mc_create(&mod->gpus[r], opt->device + r)))
+		if (r < g_early.n && g_early.ctx[r]) {
+			mod->gpus[r] = g_early.ctx[r];
+			g_early.ctx[r] = NULL;
+		} else if ((rc = mc_create(&mod->gpus[r], opt->device + r))) {
 			return mmessage(ERROR_MSG, GPU_ERROR, "%s\n", mc_last_error(NULL));
+		}
 		if ((rc = mc_set_data(mod->gpus[r], rows, dat->L, dat->ploidy,
 			dat->uniquealleles, dat->codes
 			+ (size_t)mod->row_first[r] * dat->L * dat->ploidy)))
