@@ -381,7 +381,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_source": peak_src,
-                "kernel": "admix3_kernel<MODE_EM> (two-pass, rotation gather)"
+                "kernel": "admix3_kernel<MODE_EM> (two-pass, residue-matched gather)"
                 if plan.get("two_pass") == 2
                 else "admix2_kernel<MODE_EM> (two-pass)" if plan.get("two_pass")
                 else "tile_kernel<MODE_ADMIX_EM>",

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <chrono>
 
 #include <cuda_runtime.h>
 
@@ -701,6 +702,17 @@ static int make_plan3(mc_ctx *c)
 	const int n_ltiles = (L + LT - 1) / LT;
 	const long long n_itiles = (c->I + A3_IT - 1) / A3_IT;
 	const int cap = A3_IT * 8;
+	const bool timing = getenv("MC_TIMING") != nullptr;
+	auto t_prev = std::chrono::steady_clock::now();
+	auto mark = [&](const char *what) {
+		if (!timing)
+			return;
+		cudaStreamSynchronize(c->stream);
+		const auto t = std::chrono::steady_clock::now();
+		fprintf(stderr, "plan3: %-28s %.3f s\n", what,
+			std::chrono::duration<double>(t - t_prev).count());
+		t_prev = t;
+	};
 	if (n_itiles * n_ltiles > 0x7fffffffLL)
 		return MC_OK;
 
@@ -716,6 +728,7 @@ static int make_plan3(mc_ctx *c)
 		cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	cudaFree(d_hist);
+	mark("allele histogram");
 
 	std::vector<int> lt_ncol((size_t)n_ltiles), lt_rows((size_t)n_ltiles);
 	std::vector<std::vector<std::pair<unsigned, unsigned short>>> cols((size_t)n_ltiles);
@@ -833,22 +846,27 @@ static int make_plan3(mc_ctx *c)
 	if ((rc = upload(c, c->d3_lc_first, lc_first))) return rc;
 	if ((rc = upload(c, c->d3_colinfo, colinfo))) return rc;
 	const size_t ntile = (size_t)n_itiles * n_ltiles;
+	mark("host planning + uploads");
 	CK(cudaMalloc(&c->d3_codes, ntile * A3_THREADS * 8));
 	CK(cudaMalloc(&c->d3_csc, ntile * cap * sizeof(unsigned short)));
 	CK(cudaMalloc(&c->d3_colstart, ntile * 3 * (size_t)((ncolmax + 1 + 7) / 8 * 8) * sizeof(unsigned short)));
+	mark("cudaMalloc codes/lists");
 	k3_build_codes<<<grid_for(c, (long long)ntile * A3_THREADS, 256), 256, 0, c->stream>>>(
 		c->d_nat, c->d3_codes, c->I, L, c->P, PP, (int)n_itiles, n_ltiles);
 	LAUNCH_CHECK("k3_build_codes");
+	mark("k3_build_codes");
 	const size_t bsm = (size_t)A3_IT * 8 + sizeof(int) * (2 * (size_t)ncolmax + 1);
 	k3_build_csc<<<(unsigned)ntile, 128, bsm, c->stream>>>(c->d3_codes, PP, n_ltiles,
 		ncolmax, cap, c->d3_lt_ncol, c->d3_colinfo, c->d3_csc, c->d3_colstart);
 	LAUNCH_CHECK("k3_build_csc");
+	mark("k3_build_csc");
 	a.lt_ncol = c->d3_lt_ncol; a.colinfo = c->d3_colinfo;
 	 a.lc_first = c->d3_lc_first; a.off = c->d_off;
 	a.codes = c->d3_codes; a.csc = c->d3_csc; a.colstart = c->d3_colstart;
 	if ((rc = alloc_outputs(c, n_lchunks, n_ichunks, a.n_units, a.Ipad))) return rc;
 	a.Apart = c->d_Apart; a.Npart = c->d_Npart; a.llpart = c->d_llpart;
 	CK(cudaStreamSynchronize(c->stream));
+	mark("partial-sum buffers");
 	c->use3 = true;
 	return MC_OK;
 }
