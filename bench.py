@@ -223,8 +223,19 @@ def init_params(a, ctx, rng_seed):
     return eta.ravel(), p.ravel()
 
 
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version
+    there when NCCL_DEBUG is set) write to fd 1 as well, so fd 1 is pointed at
+    stderr for the rest of the run and the line goes to a private duplicate."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 def main():
     a = parse_args()
+    out = _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -232,7 +243,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        return reference_arm(a)
+        return reference_arm(a, out)
 
     import numpy as np
     import torch
@@ -415,14 +426,15 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu,
         "logL_first": lls[0], "logL_last": lls[-1],
     }
-    print(json.dumps(line))
+    out.write(json.dumps(line) + "\n")
+    out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
-def reference_arm(a):
+def reference_arm(a, out):
     """--impl reference: the reference's own CPU implementation (oracle/_ref,
     compiled in place from the unmodified sources) on a bounded sample."""
     t0 = time.perf_counter()
@@ -439,7 +451,8 @@ def reference_arm(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line))
+    out.write(json.dumps(line) + "\n")
+    out.flush()
     return 0
 
 
