@@ -25,45 +25,50 @@
 #include "mc_format.h"
 #include "multiclust.h"
 
-/* next white-space delimited word, newly allocated; NULL at end of file */
-static char *next_word(FILE *fp)
-{
-	size_t n = 0, cap = 32;
-	char *w;
-	int c;
+/* the whole text file in memory and a read position: the scanner below does
+ * what fgetc / fscanf("%d") did for the reference, a few hundred MB/s faster */
+typedef struct {
+	const char *p, *end;
+} cursor;
 
-	do {
-		c = fgetc(fp);
-	} while (c == ' ' || c == '\t' || c == '\n' || c == '\r');
-	if (c == EOF)
+static int is_blank(int c)
+{
+	return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f';
+}
+
+/* next white-space delimited word, newly allocated; NULL at end of file */
+static char *next_word(cursor *cu)
+{
+	const char *b;
+	char *w;
+
+	while (cu->p < cu->end && is_blank((unsigned char)*cu->p))
+		cu->p++;
+	if (cu->p >= cu->end)
 		return NULL;
-	w = malloc(cap);
-	while (c != EOF && !isspace(c)) {
-		if (n + 2 > cap)
-			w = realloc(w, cap *= 2);
-		w[n++] = (char)c;
-		c = fgetc(fp);
-	}
-	if (c != EOF)
-		ungetc(c, fp);
-	w[n] = 0;
+	b = cu->p;
+	while (cu->p < cu->end && !is_blank((unsigned char)*cu->p))
+		cu->p++;
+	w = malloc((size_t)(cu->p - b) + 1);
+	memcpy(w, b, (size_t)(cu->p - b));
+	w[cu->p - b] = 0;
 	return w;
 }
 
-static void skip_line(FILE *fp)
+static void skip_line(cursor *cu)
 {
-	int c;
-	do {
-		c = fgetc(fp);
-	} while (c != EOF && c != '\n');
+	const char *nl = memchr(cu->p, '\n', (size_t)(cu->end - cu->p));
+
+	cu->p = nl ? nl + 1 : cu->end;
 }
 
-/* columns on the rest of the current line; leaves fp on the next line */
-static int count_columns(FILE *fp)
+/* columns on the rest of the current line; leaves the cursor on the next line */
+static int count_columns(cursor *cu)
 {
-	int n = 0, in_word = 0, c;
+	int n = 0, in_word = 0;
 
-	while ((c = fgetc(fp)) != EOF && c != '\n') {
+	while (cu->p < cu->end && *cu->p != '\n') {
+		const int c = (unsigned char)*cu->p++;
 		if (c == ' ' || c == '\t' || c == '\r') {
 			in_word = 0;
 		} else if (!in_word) {
@@ -71,23 +76,72 @@ static int count_columns(FILE *fp)
 			n++;
 		}
 	}
+	if (cu->p < cu->end)
+		cu->p++;
 	return n;
 }
 
-/* non-empty lines from fp to the end of the file */
-static int count_lines(FILE *fp)
+/* non-empty lines from the cursor to the end of the file (cursor unchanged) */
+static int count_lines(const cursor *cu)
 {
-	int n = 0, blank = 1, c;
+	const char *q = cu->p;
+	int n = 0;
 
-	while ((c = fgetc(fp)) != EOF) {
-		if (c == '\n') {
-			n += !blank;
-			blank = 1;
-		} else if (!isspace(c)) {
-			blank = 0;
-		}
+	while (q < cu->end) {
+		const char *nl = memchr(q, '\n', (size_t)(cu->end - q));
+		const char *e = nl ? nl : cu->end;
+		/* a line counts when it holds anything but white space */
+		while (q < e && is_blank((unsigned char)*q))
+			q++;
+		n += q < e;
+		q = e + 1;
 	}
-	return n + !blank;
+	return n;
+}
+
+/* fscanf("%d"): skip white space, optional sign, decimal digits */
+static int scan_int(cursor *cu, int *out)
+{
+	const char *q = cu->p;
+	long long v = 0;
+	int neg = 0, digits = 0;
+
+	while (q < cu->end && is_blank((unsigned char)*q))
+		q++;
+	if (q < cu->end && (*q == '-' || *q == '+'))
+		neg = *q++ == '-';
+	while (q < cu->end && *q >= '0' && *q <= '9') {
+		v = v * 10 + (*q++ - '0');
+		if (v > 4294967296LL)
+			v = 4294967296LL;	/* out of range anyway */
+		digits++;
+	}
+	if (!digits)
+		return 0;
+	cu->p = q;
+	*out = (int)(neg ? -v : v);
+	return 1;
+}
+
+static char *slurp(const char *path, size_t *len)
+{
+	FILE *fp = fopen(path, "rb");
+	char *buf = NULL;
+	long long n;
+
+	if (!fp)
+		return NULL;
+	if (fseeko(fp, 0, SEEK_END) || (n = ftello(fp)) < 0 || fseeko(fp, 0, SEEK_SET)
+		|| !(buf = malloc((size_t)n + 1))
+		|| fread(buf, 1, (size_t)n, fp) != (size_t)n) {
+		free(buf);
+		fclose(fp);
+		return NULL;
+	}
+	fclose(fp);
+	buf[n] = 0;
+	*len = (size_t)n;
+	return buf;
 }
 
 static int locale_index(data *dat, const char *name)
@@ -106,54 +160,105 @@ static int cmp_int(const void *a, const void *b)
 	return (x > y) - (x < y);
 }
 
-/* recode one locus: raw[h] for h < nhap (stride `stride`) -> codes */
-static int recode_locus(data *dat, int l, const int *raw, size_t stride, int nhap,
-	int *scratch, int32_t **labels, int64_t *nlab, int64_t *caplab)
-{
-	int n = 0, miss = 0, nreal = 0;
+/* distinct non-missing labels of one locus, in order of first appearance */
+typedef struct {
+	int *v;
+	int n, cap, miss;
+} label_set;
 
-	for (int h = 0; h < nhap; h++) {
-		const int v = raw[(size_t)h * stride];
-		if (v == MISSING)
-			miss = 1;
-		else
-			scratch[n++] = v;
+/* position of v in the set, appended when new; -1 when memory runs out */
+static inline int label_add(label_set *ls, int v)
+{
+	for (int x = 0; x < ls->n; x++)
+		if (ls->v[x] == v)
+			return x;
+	if (ls->n == ls->cap) {
+		ls->cap = ls->cap ? 2 * ls->cap : 8;
+		if (!(ls->v = realloc(ls->v, sizeof *ls->v * (size_t)ls->cap)))
+			return -1;
 	}
-	qsort(scratch, (size_t)n, sizeof *scratch, cmp_int);
-	for (int x = 0; x < n; x++)
-		if (!x || scratch[x] != scratch[x - 1])
-			scratch[nreal++] = scratch[x];
-	if (nreal > 254)
-		return mmessage(ERROR_MSG, INVALID_USER_SETUP, "locus %d has %d "
-			"distinct alleles; 8-bit allele codes allow 254\n", l + 1, nreal);
-	if (*nlab + nreal > *caplab) {
-		*caplab = 2 * (*caplab + nreal);
-		*labels = realloc(*labels, sizeof **labels * (size_t)*caplab);
-	}
-	memcpy(*labels + *nlab, scratch, sizeof *scratch * (size_t)nreal);
-	dat->label_off[l] = *nlab;
-	*nlab += nreal;
-	dat->nreal[l] = nreal;
-	dat->uniquealleles[l] = nreal ? nreal + miss : 0;
-	if (miss && nreal)
-		dat->missing_data = 1;
-	return NO_ERROR;
+	ls->v[ls->n] = v;
+	return ls->n++;
 }
 
-static int code_of(const int32_t *labels, int n, int v)
+/* the alleles of every locus recoded 0..n-1 in ascending label order
+ * (read_file.c:572-588): one row-major sweep over the raw table collects the
+ * distinct labels per locus (a handful each), which are then sorted -- instead
+ * of the reference's two bubble sorts over all haplotypes of every locus */
+static int recode_loci(data *dat, const int *raw, int nhap, int32_t **labels_out,
+	int64_t *nlab_out)
 {
-	int lo = 0, hi = n - 1;
+	const int L = dat->L, P = dat->ploidy;
+	label_set *sets = calloc((size_t)L, sizeof *sets);
+	/* first sweep: position of every copy's label in its locus's set */
+	const size_t ncell = (size_t)nhap * (size_t)L;
+	uint8_t *prov = malloc(ncell ? ncell : 1);
+	uint8_t (*rank)[256];
+	int32_t *labels;
+	int64_t nlab = 0;
 
-	while (lo <= hi) {
-		const int mid = (lo + hi) / 2;
-		if (labels[mid] == v)
-			return mid;
-		if (labels[mid] < v)
-			lo = mid + 1;
-		else
-			hi = mid - 1;
+	if (!sets || !prov)
+		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "allele labels\n");
+	for (int h = 0; h < nhap; h++) {
+		const int *row = raw + (size_t)h * L;
+		uint8_t *pr = prov + (size_t)h * L;
+		for (int l = 0; l < L; l++) {
+			if (row[l] == MISSING) {
+				sets[l].miss = 1;
+				pr[l] = MC_CODE_MISSING;
+			} else {
+				const int x = sets[l].n < 255 ? label_add(&sets[l], row[l]) : -2;
+				if (x == -1)
+					return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "allele labels\n");
+				if (x == -2 || x > 254)
+					return mmessage(ERROR_MSG, INVALID_USER_SETUP, "locus %d has "
+						"more than 254 distinct alleles; 8-bit allele codes "
+						"allow 254\n", l + 1);
+				pr[l] = (uint8_t)x;
+			}
+		}
 	}
-	return MC_CODE_MISSING;
+	for (int l = 0; l < L; l++)
+		nlab += sets[l].n;
+	labels = malloc(sizeof *labels * (size_t)(nlab ? nlab : 1));
+	rank = malloc(sizeof *rank * ((size_t)L + 1));
+	if (!labels || !rank)
+		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "allele labels\n");
+	nlab = 0;
+	for (int l = 0; l < L; l++) {
+		const int nreal = sets[l].n;
+		int first[256];
+
+		memcpy(first, sets[l].v, sizeof(int) * (size_t)nreal);
+		qsort(sets[l].v, (size_t)nreal, sizeof(int), cmp_int);
+		for (int x = 0; x < nreal; x++)		/* first-appearance position -> rank */
+			for (int y = 0; y < nreal; y++)
+				if (sets[l].v[y] == first[x])
+					rank[l][x] = (uint8_t)y;
+		rank[l][MC_CODE_MISSING] = MC_CODE_MISSING;
+		memcpy(labels + nlab, sets[l].v, sizeof(int) * (size_t)nreal);
+		dat->label_off[l] = nlab;
+		nlab += nreal;
+		dat->nreal[l] = nreal;
+		dat->uniquealleles[l] = nreal ? nreal + sets[l].miss : 0;
+		if (sets[l].miss && nreal)
+			dat->missing_data = 1;
+		free(sets[l].v);
+	}
+	free(sets);
+	/* second sweep: codes in individual-major [I][L][P] order */
+	for (int i = 0; i < dat->I; i++)
+		for (int a = 0; a < P; a++) {
+			const uint8_t *pr = prov + (size_t)(i * P + a) * L;
+			uint8_t *out = dat->codes + (size_t)i * L * P + a;
+			for (int l = 0; l < L; l++)
+				out[(size_t)l * P] = rank[l][pr[l]];
+		}
+	free(prov);
+	free(rank);
+	*labels_out = labels;
+	*nlab_out = nlab;
+	return NO_ERROR;
 }
 
 static void finish_dims(data *dat)
@@ -204,18 +309,27 @@ static int read_mcb_file(options *opt, data *dat)
 int read_file(options *opt, data *dat)
 {
 	const size_t flen = strlen(opt->filename);
-	FILE *fp;
-	char *name1, *name2, *word;
-	int skip_line_two = 0, ncol, nhap, *raw = NULL, *scratch, err = NO_ERROR;
+	cursor cur, *fp = &cur, data_start;
+	char *text, *name1, *name2, *word;
+	size_t text_len = 0;
+	int skip_line_two = 0, ncol, nhap, *raw = NULL, err = NO_ERROR;
 	int32_t *labels = NULL;
-	int64_t nlab = 0, caplab = 0;
+	int64_t nlab = 0;
 
 	if (flen > 4 && !strcmp(opt->filename + flen - 4, ".mcb"))
 		return read_mcb_file(opt, dat);
 
-	if (!(fp = fopen(opt->filename, "r")))
+	struct timespec tq0, tq1;
+	clock_gettime(CLOCK_MONOTONIC, &tq0);
+#define LAP(what) do { if (opt->timing) { clock_gettime(CLOCK_MONOTONIC, &tq1); \
+	fprintf(stderr, "timing (s): parse: %-22s %.3f\n", what, (double)(tq1.tv_sec - tq0.tv_sec) \
+		+ 1e-9 * (double)(tq1.tv_nsec - tq0.tv_nsec)); tq0 = tq1; } } while (0)
+	if (!(text = slurp(opt->filename, &text_len)))
 		return message(stderr, __FILE__, __func__, __LINE__, ERROR_MSG,
 			FILE_OPEN_ERROR, opt->filename);
+	cur.p = text;
+	cur.end = text + text_len;
+	LAP("file into memory");
 
 	/* header: one name per locus (or per column) */
 	dat->L = count_columns(fp);
@@ -267,12 +381,15 @@ int read_file(options *opt, data *dat)
 		return mmessage(ERROR_MSG, INVALID_USER_SETUP, "ploidy %d exceeds the "
 			"16 copies per locus the device layout holds\n", dat->ploidy);
 
+	LAP("header, line count");
 	/* raw alleles, haplotype-major like dat->IL */
 	raw = malloc(sizeof *raw * (size_t)nhap * dat->L);
 	dat->idv = calloc((size_t)dat->I, sizeof *dat->idv);
 	if (!raw || !dat->idv)
 		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "genotype table\n");
-	rewind(fp);
+	data_start.p = text;
+	data_start.end = text + text_len;
+	*fp = data_start;
 	skip_line(fp);
 	if (skip_line_two)
 		skip_line(fp);
@@ -294,7 +411,7 @@ int read_file(options *opt, data *dat)
 		for (int l = 0; l < dat->L; l++)
 			for (int j = 0; j < rows; j++) {
 				int v;
-				if (fscanf(fp, "%d", &v) != 1)
+				if (!scan_int(fp, &v))
 					return mmessage(ERROR_MSG, FILE_FORMAT_ERROR,
 						"failed to read locus %d of haplotype "
 						"%d in file '%s'.  Check option -R.\n",
@@ -302,7 +419,8 @@ int read_file(options *opt, data *dat)
 				raw[(size_t)(h + j) * dat->L + l] = v;
 			}
 	}
-	fclose(fp);
+	free(text);
+	LAP("numbers");
 
 	/* --missing: remap to the default marker (read_file.c:411-429) */
 	if (opt->missing_value != MISSING)
@@ -323,26 +441,14 @@ int read_file(options *opt, data *dat)
 	dat->allele_off = calloc((size_t)dat->L + 1, sizeof(int32_t));
 	dat->label_off = calloc((size_t)dat->L + 1, sizeof(int64_t));
 	dat->codes = malloc((size_t)dat->I * dat->L * dat->ploidy);
-	scratch = malloc(sizeof *scratch * (size_t)nhap);
-	for (int l = 0; l < dat->L && !err; l++)
-		err = recode_locus(dat, l, raw + l, (size_t)dat->L, nhap, scratch,
-			&labels, &nlab, &caplab);
-	if (err)
+	if ((err = recode_loci(dat, raw, nhap, &labels, &nlab)))
 		return err;
+	LAP("labels and 8-bit codes");
 	dat->label_off[dat->L] = nlab;
 	dat->labels = labels;
-	for (int i = 0; i < dat->I; i++)
-		for (int l = 0; l < dat->L; l++)
-			for (int a = 0; a < dat->ploidy; a++) {
-				const int v = raw[(size_t)(i * dat->ploidy + a) * dat->L + l];
-				dat->codes[((size_t)i * dat->L + l) * dat->ploidy + a]
-					= v == MISSING ? MC_CODE_MISSING
-					: (uint8_t)code_of(labels + dat->label_off[l],
-						dat->nreal[l], v);
-			}
-	free(scratch);
 	free(raw);
 	finish_dims(dat);
+	LAP("finish");
 	return NO_ERROR;
 }
 
