@@ -393,9 +393,7 @@ def main():
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_source": peak_src,
                 "kernel": "admix3_kernel<MODE_EM> (two-pass, residue-matched gather)"
-                if plan.get("two_pass") == 2
-                else "admix2_kernel<MODE_EM> (two-pass)" if plan.get("two_pass")
-                else "tile_kernel<MODE_ADMIX_EM>",
+                if plan.get("two_pass") else "tile_kernel<MODE_ADMIX_EM>",
                 "kernel_ms": k_ms, "kernel_launches_timed": nk,
                 "algorithmic_bytes_per_launch": alg,
                 "kernel_share_of_step": (k_ms / ms_per_step) if nk else None}

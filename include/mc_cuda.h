@@ -199,7 +199,8 @@ typedef struct {
 	int32_t loci_per_warp, warps, groups;	/* tile = warps*groups*loci_per_warp loci */
 	int32_t n_tiles, n_chunks, n_units, grid, block;
 	int32_t indiv_per_block, ploidy_padded;
-	int32_t two_pass;	/* 1: the two-pass admixture kernel is in use */
+	int32_t two_pass;	/* 2: the two-pass admixture kernel (mc_admix3.cuh) is in use,
+				 * 0: the one-pass tile kernel */
 	int32_t reserved;
 	int64_t smem_bytes;
 	int64_t algorithmic_bytes_em;	/* I*L*P + 16*I*K + 16*K*T */

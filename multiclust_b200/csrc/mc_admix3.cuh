@@ -79,6 +79,22 @@ struct Admix3Args {
 /* ---------------------------------------------------------------------- */
 /* one-time layout builders                                                 */
 
+/* how often each allele slot occurs (orders the columns of a locus tile) */
+__global__ void k_allele_hist(const unsigned char *nat, long long I, int L, int P,
+	const int *off, unsigned *hist)
+{
+	const long long n = I * (long long)L;
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		const int l = (int)(x % L);
+		for (int ap = 0; ap < P; ap++) {
+			const unsigned char c = nat[(size_t)x * P + ap];
+			if (c != 255)
+				atomicAdd(&hist[off[l] + c], 1u);
+		}
+	}
+}
+
 /* natural [I][L][P] codes -> 8 bytes per (tile, individual): LT = 8 / PP loci
  * x PP copies, thread-major inside a tile */
 __global__ void k3_build_codes(const unsigned char *nat, unsigned char *codes,

@@ -19,7 +19,6 @@
 
 #include "mc_cuda.h"
 #include "mc_kernels.cuh"
-#include "mc_admix2.cuh"
 #include "mc_admix3.cuh"
 
 #define KH_MAX 6
@@ -68,16 +67,7 @@ struct mc_ctx {
 	double *d_small = nullptr;	/* small results for the host */
 	int *d_IK = nullptr;
 
-	/* two-pass admixture plan (mc_admix2.cuh); used when `use2` */
-	bool use2 = false;
-	Admix2Args a2;
-	int KP2 = 0, grid2 = 0;
-	size_t smem2 = 0;
-	int *d2_lt_first = nullptr, *d2_lt_ncol = nullptr, *d2_lt_S = nullptr,
-		*d2_lc_first = nullptr;
-	unsigned short *d2_colinfo = nullptr, *d2_csc = nullptr, *d2_colstart = nullptr;
-	unsigned char *d2_csr = nullptr;
-	/* rotation two-pass plan (mc_admix3.cuh); used when `use3` */
+	/* two-pass admixture plan (mc_admix3.cuh); used when `use3` */
 	bool use3 = false;
 	Admix3Args a3;
 	int KP3 = 0, grid3 = 0;
@@ -181,10 +171,6 @@ static void free_plan(mc_ctx *c)
 	dfree(c->d_group_rowbase); dfree(c->d_group_rows); dfree(c->d_tile_rows);
 	dfree(c->d_tiled); dfree(c->d_Apart); dfree(c->d_Npart);
 	dfree(c->d_llpart); dfree(c->d_xbuf); dfree(c->d_red);
-	dfree(c->d2_lt_first); dfree(c->d2_lt_ncol); dfree(c->d2_lt_S);
-	dfree(c->d2_lc_first); dfree(c->d2_colinfo); dfree(c->d2_csc);
-	dfree(c->d2_colstart); dfree(c->d2_csr);
-	c->use2 = false;
 	dfree(c->d3_lt_ncol); dfree(c->d3_lc_first); dfree(c->d3_colinfo);
 	dfree(c->d3_csc); dfree(c->d3_colstart);
 	dfree(c->d3_codes);
@@ -471,222 +457,7 @@ static int alloc_outputs(mc_ctx *c, int n_tiles, int n_chunks, int n_units, long
 	return MC_OK;
 }
 
-/* returns MC_OK with c->use2 set when the two-pass kernel applies */
-static int make_plan2(mc_ctx *c)
-{
-	c->use2 = false;
-	if (!c->admixture || c->PP > 8 || c->K > 16 || c->T < 1)
-		return MC_OK;
-	if (const char *ev = getenv("MC_KERNEL"))
-		if (atoi(ev) == 1)
-			return MC_OK;	/* tuning knob: force the one-pass kernel */
-	const int K = c->K, KP = (K + 1) / 2, KR = 2 * KP, PP = c->PP, L = c->L;
-	const int LH = 8 / PP, LT = A2_H * LH;
-	const int n_ltiles = (L + LT - 1) / LT;
-	const long long n_itiles = (c->I + A2_IT - 1) / A2_IT;
-	const int cap = A2_IT * LT * PP;
-	if (n_itiles * n_ltiles > 0x7fffffffLL)
-		return MC_OK;
-
-	/* allele counts order the columns of every locus tile */
-	unsigned *d_hist = nullptr;
-	std::vector<unsigned> hist((size_t)c->T);
-	CK(cudaMalloc(&d_hist, sizeof(unsigned) * (size_t)c->T));
-	CK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * (size_t)c->T, c->stream));
-	k_allele_hist<<<grid_for(c, c->I * (long long)L, 256), 256, 0, c->stream>>>(
-		c->d_nat, c->I, L, c->P, c->d_off, d_hist);
-	LAUNCH_CHECK("k_allele_hist");
-	CK(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned) * (size_t)c->T,
-		cudaMemcpyDeviceToHost, c->stream));
-	CK(cudaStreamSynchronize(c->stream));
-	cudaFree(d_hist);
-
-	std::vector<int> lt_first((size_t)n_ltiles), lt_ncol((size_t)n_ltiles),
-		lt_S((size_t)n_ltiles), lt_rows((size_t)n_ltiles);
-	std::vector<std::vector<unsigned short>> cols((size_t)n_ltiles);
-	int ncolmax = 1, max_tile_rows = 1;
-	for (int lt = 0; lt < n_ltiles; lt++) {
-		const int lf = lt * LT, le = std::min(L, lf + LT);
-		lt_first[lt] = lf;
-		lt_rows[lt] = c->off[le] - c->off[lf];
-		max_tile_rows = std::max(max_tile_rows, lt_rows[lt]);
-		std::vector<std::pair<unsigned, unsigned short>> v;
-		for (int l = lf; l < le; l++)
-			for (int j = 0; j < c->J[l]; j++)
-				if (hist[(size_t)c->off[l] + j])
-					v.push_back({ hist[(size_t)c->off[l] + j],
-						(unsigned short)((l - lf) << 8 | j) });
-		std::stable_sort(v.begin(), v.end(),
-			[](const std::pair<unsigned, unsigned short> &x,
-			   const std::pair<unsigned, unsigned short> &y) { return x.first > y.first; });
-		for (auto &e : v)
-			cols[lt].push_back(e.second);
-		const int ncol = (int)v.size();
-		lt_ncol[lt] = ncol;
-		ncolmax = std::max(ncolmax, ncol);
-		int S = 1;
-		while (S < 32 && 2 * S * std::max(ncol, 1) <= A2_THREADS)
-			S *= 2;
-		lt_S[lt] = S;
-	}
-	if (ncolmax > A2_THREADS)
-		return MC_OK;	/* more allele columns in a tile than threads */
-
-	/* shared memory: fixed part, the rest holds the chunk's accumulators */
-	const size_t fixed = ((size_t)max_tile_rows * KR + (size_t)A2_IT * KR + cap
-		+ A2_THREADS / 32) * sizeof(double)
-		+ ((size_t)cap + (size_t)(ncolmax + 1 + 7) / 8 * 8) * sizeof(unsigned short)
-		+ (size_t)LT * sizeof(int) + 64;
-	/* per CTA; A2_CTAS_PER_SM of them share the SM (1 KB each is reserved) */
-	const size_t smem_cap = (size_t)(228 * 1024) / A2_CTAS_PER_SM - 1024 - 64;
-	if (fixed + (size_t)max_tile_rows * KR * sizeof(double) > smem_cap)
-		return MC_OK;
-	const long long budget_rows = (long long)((smem_cap - fixed) / (KR * sizeof(double)));
-	const long long total_rows = c->T;
-	int n_lchunks = (int)((total_rows + budget_rows - 1) / budget_rows);
-	std::vector<int> lc_first;
-	int max_chunk_rows = 1;
-	for (;;) {	/* even chunks, none above the budget */
-		const double target = (double)total_rows / n_lchunks;
-		lc_first.assign(1, 0);
-		long long rows = 0;
-		bool ok = true;
-		max_chunk_rows = 1;
-		for (int lt = 0; lt < n_ltiles; lt++) {
-			if (rows > 0 && (rows + lt_rows[lt] > budget_rows
-				|| (rows + lt_rows[lt] / 2.0 > target
-					&& (int)lc_first.size() < n_lchunks))) {
-				lc_first.push_back(lt);
-				rows = 0;
-			}
-			rows += lt_rows[lt];
-			if (rows > budget_rows)
-				ok = false;
-			max_chunk_rows = std::max<long long>(max_chunk_rows, rows);
-		}
-		lc_first.push_back(n_ltiles);
-		if (ok)
-			break;
-		n_lchunks++;
-	}
-	n_lchunks = (int)lc_first.size() - 1;
-
-	/* chunks of individual tiles: balance the persistent grid */
-	int n_ichunks = 1;
-	{
-		const long long sms = (long long)c->num_sms * A2_CTAS_PER_SM;
-		double best_eff = -1;
-		const long long cmax = std::min<long long>(n_itiles,
-			std::max<long long>(1, (6 * sms + n_lchunks - 1) / n_lchunks));
-		for (long long cc = 1; cc <= cmax; cc++) {
-			const long long units = cc * n_lchunks;
-			const long long rounds = (units + sms - 1) / sms;
-			double eff = (double)units / (double)(rounds * sms) - 0.002 * (double)cc;
-			if (eff > best_eff + 1e-12) {
-				best_eff = eff;
-				n_ichunks = (int)cc;
-			}
-		}
-	}
-
-	Admix2Args &a = c->a2;
-	memset(&a, 0, sizeof a);
-	a.K = K; a.KR = KR; a.LT = LT; a.LH = LH;
-	a.n_itiles = (int)n_itiles; a.n_ltiles = n_ltiles; a.n_lchunks = n_lchunks;
-	a.n_ichunks = n_ichunks; a.n_units = n_lchunks * n_ichunks;
-	a.I = c->I; a.Ipad = n_itiles * A2_IT; a.T = c->T; a.L = L;
-	a.ncolmax = ncolmax; a.max_chunk_rows = max_chunk_rows;
-	a.max_tile_rows = max_tile_rows; a.cap = cap;
-	c->KP2 = KP;
-	c->smem2 = fixed + (size_t)max_chunk_rows * KR * sizeof(double);
-	c->grid2 = std::min(a.n_units, c->num_sms * A2_CTAS_PER_SM);
-
-	std::vector<unsigned short> colinfo((size_t)n_ltiles * ncolmax, 0);
-	for (int lt = 0; lt < n_ltiles; lt++)
-		std::copy(cols[lt].begin(), cols[lt].end(), colinfo.begin() + (size_t)lt * ncolmax);
-	int rc;
-	if ((rc = upload(c, c->d2_lt_first, lt_first))) return rc;
-	if ((rc = upload(c, c->d2_lt_ncol, lt_ncol))) return rc;
-	if ((rc = upload(c, c->d2_lt_S, lt_S))) return rc;
-	if ((rc = upload(c, c->d2_lc_first, lc_first))) return rc;
-	if ((rc = upload(c, c->d2_colinfo, colinfo))) return rc;
-	const size_t ntile = (size_t)n_itiles * n_ltiles;
-	CK(cudaMalloc(&c->d2_csr, ntile * A2_THREADS * 8));
-	CK(cudaMalloc(&c->d2_csc, ntile * cap * sizeof(unsigned short)));
-	CK(cudaMalloc(&c->d2_colstart, ntile * (ncolmax + 1) * sizeof(unsigned short)));
-	k_build_csr<<<grid_for(c, (long long)ntile * A2_THREADS, 256), 256, 0, c->stream>>>(
-		c->d_nat, c->d2_csr, c->I, L, c->P, PP, LT, LH, (int)n_itiles, n_ltiles);
-	LAUNCH_CHECK("k_build_csr");
-	const size_t bsm = ((size_t)cap + 15) / 16 * 16 + sizeof(int) * (size_t)ncolmax;
-	k_build_csc<<<(unsigned)ntile, 128, bsm, c->stream>>>(c->d_nat, c->I, L, c->P, PP, LT,
-		n_ltiles, ncolmax, cap, c->d2_lt_ncol, c->d2_colinfo, c->d2_csc, c->d2_colstart);
-	LAUNCH_CHECK("k_build_csc");
-	a.lt_first = c->d2_lt_first; a.lt_ncol = c->d2_lt_ncol; a.lt_S = c->d2_lt_S;
-	a.colinfo = c->d2_colinfo; a.lc_first = c->d2_lc_first; a.off = c->d_off;
-	a.csr = c->d2_csr; a.csc = c->d2_csc; a.colstart = c->d2_colstart;
-	if ((rc = alloc_outputs(c, n_lchunks * A2_H, n_ichunks, a.n_units, a.Ipad))) return rc;
-	a.Apart = c->d_Apart; a.Npart = c->d_Npart; a.llpart = c->d_llpart;
-	CK(cudaStreamSynchronize(c->stream));
-	c->use2 = true;
-	return MC_OK;
-}
-
-typedef void (*admix2_fn)(const Admix2Args);
-
-template <int KP, int MODE> static admix2_fn pick2_pp(int PP)
-{
-	switch (PP) {
-	case 1: return admix2_kernel<KP, 1, MODE>;
-	case 2: return admix2_kernel<KP, 2, MODE>;
-	case 4: return admix2_kernel<KP, 4, MODE>;
-	case 8: return admix2_kernel<KP, 8, MODE>;
-	}
-	return nullptr;
-}
-
-template <int MODE> static admix2_fn pick2(int KP, int PP)
-{
-	switch (KP) {
-	case 1: return pick2_pp<1, MODE>(PP);
-	case 2: return pick2_pp<2, MODE>(PP);
-	case 3: return pick2_pp<3, MODE>(PP);
-	case 4: return pick2_pp<4, MODE>(PP);
-	case 5: return pick2_pp<5, MODE>(PP);
-	case 6: return pick2_pp<6, MODE>(PP);
-	case 7: return pick2_pp<7, MODE>(PP);
-	case 8: return pick2_pp<8, MODE>(PP);
-	}
-	return nullptr;
-}
-
-static int launch_admix2(mc_ctx *c, int ll_only, const double *p, const double *eta,
-	long long eta_stride)
-{
-	admix2_fn fn = ll_only ? pick2<1>(c->KP2, c->PP) : pick2<0>(c->KP2, c->PP);
-	if (!fn)
-		return fail(c, MC_ERR_UNSUPPORTED, "no two-pass kernel for K=%d P=%d", c->K, c->P);
-	Admix2Args a = c->a2;
-	a.p = p; a.eta = eta; a.eta_stride = eta_stride;
-	CK(cudaFuncSetAttribute((const void *)fn,
-		cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem2));
-	cudaEvent_t e0 = nullptr, e1 = nullptr;
-	if (c->profile) {
-		CK(cudaEventCreate(&e0));
-		CK(cudaEventCreate(&e1));
-		CK(cudaEventRecord(e0, c->stream));
-	}
-	fn<<<c->grid2, A2_THREADS, c->smem2, c->stream>>>(a);
-	LAUNCH_CHECK("admix2_kernel");
-	if (c->profile) {
-		CK(cudaEventRecord(e1, c->stream));
-		c->prof_events.push_back({ e0, e1 });
-	}
-	return MC_OK;
-}
-
-
-
-/* ------------------------------------------ rotation two-pass plan (admix3) */
+/* ------------------------------------------------ two-pass plan (admix3) */
 
 /* returns MC_OK with c->use3 set when the kernel of mc_admix3.cuh applies */
 static int make_plan3(mc_ctx *c)
@@ -695,8 +466,8 @@ static int make_plan3(mc_ctx *c)
 	if (!c->admixture || c->PP > 8 || c->K > 16 || c->T < 1)
 		return MC_OK;
 	if (const char *ev = getenv("MC_KERNEL"))
-		if (atoi(ev) == 1 || atoi(ev) == 2)
-			return MC_OK;	/* tuning knob: force an older kernel */
+		if (atoi(ev) == 1)
+			return MC_OK;	/* tuning knob: force the one-pass kernel */
 	const int K = c->K, KP = (K + 1) / 2, KR = 2 * KP, PP = c->PP, L = c->L;
 	const int LT = 8 / PP;
 	const int n_ltiles = (L + LT - 1) / LT;
@@ -932,11 +703,6 @@ static int make_plan(mc_ctx *c)
 		const int rc3 = make_plan3(c);
 		if (rc3 || c->use3)
 			return rc3;
-	}
-	{
-		const int rc2 = make_plan2(c);
-		if (rc2 || c->use2)
-			return rc2;
 	}
 	int ks = 1, kh_max = KH_MAX;
 	if (const char *ev = getenv("MC_KH_MAX")) {	/* tuning knob */
@@ -1246,8 +1012,6 @@ extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 	if (c->admixture) {
 		rc = c->use3
 			? launch_admix3(c, 0, c->d_p[from], c->d_eta[from], c->per_indiv ? K : 0)
-			: c->use2
-			? launch_admix2(c, 0, c->d_p[from], c->d_eta[from], c->per_indiv ? K : 0)
 			: launch_tile(c, MODE_ADMIX_EM, c->d_p[from], c->d_eta[from],
 				c->per_indiv ? K : 0);
 		if (rc) return rc;
@@ -1448,8 +1212,6 @@ extern "C" int mc_loglik(mc_ctx *c, int slot, double *ll)
 	if (c->admixture) {
 		rc = c->use3
 			? launch_admix3(c, 1, c->d_p[slot], c->d_eta[slot], c->per_indiv ? c->K : 0)
-			: c->use2
-			? launch_admix2(c, 1, c->d_p[slot], c->d_eta[slot], c->per_indiv ? c->K : 0)
 			: launch_tile(c, MODE_ADMIX_LL, c->d_p[slot], c->d_eta[slot],
 				c->per_indiv ? c->K : 0);
 		if (rc) return rc;
@@ -1668,15 +1430,8 @@ extern "C" int mc_get_plan(const mc_ctx *c, mc_plan_info *o)
 	o->grid = c->grid; o->block = c->block;
 	o->indiv_per_block = c->IB; o->ploidy_padded = c->PP;
 	o->smem_bytes = (int64_t)c->smem_em;
-	o->two_pass = c->use2 ? 1 : 0;
-	if (c->use2) {	/* two-pass admixture kernel: tiles are locus chunks */
-		o->k_split = 1; o->k_per_lane = c->a2.KR;
-		o->loci_per_warp = c->a2.LT; o->warps = A2_THREADS / 32; o->groups = 1;
-		o->n_tiles = c->a2.n_lchunks; o->n_chunks = c->a2.n_ichunks;
-		o->n_units = c->a2.n_units; o->grid = c->grid2; o->block = A2_THREADS;
-		o->indiv_per_block = A2_IT; o->smem_bytes = (int64_t)c->smem2;
-	}
-	if (c->use3) {	/* rotation two-pass kernel */
+	o->two_pass = 0;
+	if (c->use3) {	/* two-pass admixture kernel: tiles are locus chunks */
 		o->two_pass = 2;
 		o->k_split = 1; o->k_per_lane = 2 * c->KP3;
 		o->loci_per_warp = 8 / c->PP; o->warps = A3_THREADS / 32; o->groups = 1;

@@ -47,7 +47,7 @@ def start_params(ctx, seed):
 
 def test_full_size_properties(big):
     ctx, lb = big
-    assert ctx.plan()["two_pass"] in (1, 2)
+    assert ctx.plan()["two_pass"] == 2
     eta0, p0, J, seg = start_params(ctx, 3)
     runs = []
     for rep in range(2):
@@ -107,7 +107,7 @@ def test_mid_size_against_oracle(orc, tmp_path):
     ctx = Context(0)
     ctx.set_data(d["J"], d["codes"])
     ctx.alloc_model(K, admixture=1, q=0, eta_lb=fit.lower_bound, p_lb=fit.lower_bound)
-    assert ctx.plan()["two_pass"] in (1, 2)
+    assert ctx.plan()["two_pass"] == 2
     eta, p = random_params(np.random.default_rng(11), 600, K, d["J"], True)
     fit.set_params(0, eta, p)
     ctx.set_params(0, eta, p)
