@@ -33,7 +33,7 @@
  *   fold    the lanes' partial sums go through a shared scratch; thread
  *           (column, piece) adds the column's partials in lane order and
  *           updates the CTA's accumulator B_s: no atomics, fixed order.
- * Three barriers per (A3_IT individuals x 8 copies) tile; two CTAs per SM so
+ * Two barriers per (A3_IT individuals x 8 copies) tile; two CTAs per SM so
  * that one's pass 1 (FP64) overlaps the other's pass 2 (shared-memory pipe).
  */
 #pragma once
@@ -398,8 +398,13 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 
 		fetch_regs(it0, lt0);
 		stage_p(lt0, 0);
-		if (EM)
+		if (EM) {
 			stage_lists(it0, lt0, 0);
+			/* the E+M sweep keeps two barriers per tile (after pass 1, after
+			 * pass 2); the first tile's p rows are waited for here */
+			a3_cp_async_wait<0>();
+			__syncthreads();
+		}
 		int buf = 0;
 
 		for (long long it = it0; it < it1; it++) {
@@ -433,13 +438,13 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 
 				if (more)
 					fetch_regs(itn, ltn);
-				/* the p rows must have landed; the entry lists (the younger
-				 * group) are only needed after pass 1 */
-				if (EM)
-					a3_cp_async_wait<1>();
-				else
+				if (!EM) {
 					a3_cp_async_wait<0>();
-				__syncthreads();
+					__syncthreads();
+				}
+				/* E+M: this tile's p rows landed before the barrier that closed
+				 * the previous tile's pass 2; its entry lists are only needed
+				 * after pass 1 */
 
 				/* ---- pass 1: tmp, w, A, log likelihood ---- */
 				double pr[2][KR];
@@ -554,6 +559,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 				for (int pc = 0; pc < KP; pc++)
 					*reinterpret_cast<double2 *>(part_s + (size_t)t * KR + 2 * pc)
 						= make_double2(g[2 * pc], g[2 * pc + 1]);
+				a3_cp_async_wait<0>();	/* the next tile's p rows */
 				__syncthreads();
 				if (more)
 					stage_lists(itn, ltn, buf ^ 1);
