@@ -280,10 +280,6 @@ __device__ __forceinline__ double2 a3_lds_f64x2(unsigned addr)
 	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
 	return v;
 }
-__device__ __forceinline__ void a3_sts_f64x2(unsigned addr, double2 v)
-{
-	asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(addr), "d"(v.x), "d"(v.y) : "memory");
-}
 __device__ __forceinline__ double a3_lds_f64(unsigned addr)
 {
 	double v;
@@ -344,8 +340,6 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 	const unsigned eta_sa = (unsigned)__cvta_generic_to_shared(eta_s);
 	const unsigned w_sa = (unsigned)__cvta_generic_to_shared(w_s);
 	const unsigned csc_sa = (unsigned)__cvta_generic_to_shared(csc_s);
-	const unsigned part_sa = (unsigned)__cvta_generic_to_shared(part_s);
-	const unsigned B_sa = (unsigned)__cvta_generic_to_shared(B_s);
 
 	for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
 		const int c = u % a.n_lchunks, r = u / a.n_lchunks;
@@ -565,27 +559,6 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 				for (int pc = 0; pc < KP; pc++)
 					*reinterpret_cast<double2 *>(part_s + (size_t)t * KR + 2 * pc)
 						= make_double2(g[2 * pc], g[2 * pc + 1]);
-				/* what this thread folds after the barrier -- (column, piece) items
-				 * t and t + A3_THREADS -- is looked up before it: under the other
-				 * CTA's pass 2 every dependent shared-memory access costs hundreds
-				 * of cycles, so the fold is kept to two dependent steps */
-				unsigned fsrc[2], fdst[2];
-				int fS[2];
-#pragma unroll
-				for (int z = 0; z < 2; z++) {
-					const int f = t + z * A3_THREADS;
-					const int cc = f / KP, pc = f - cc * KP;
-					fS[z] = 0;
-					fsrc[z] = fdst[z] = 0u;
-					if (f < a.ncolmax * KP) {
-						const int lane0 = cst_s[csw + cc];
-						const unsigned info = cst_s[2 * csw + cc];
-						fS[z] = cst_s[csw + cc + 1] - lane0;
-						fsrc[z] = part_sa + (unsigned)(lane0 * KR + 2 * pc) * 8u;
-						fdst[z] = B_sa + (unsigned)((tro + rb[info >> 8] + (int)(info & 0xff))
-							* KR + 2 * pc) * 8u;
-					}
-				}
 				a3_cp_async_wait<0>();	/* the next tile's p rows */
 				__syncthreads();
 				if (more)
@@ -593,34 +566,8 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 				else
 					a3_cp_async_commit();
 
-				/* ---- fold: thread <-> (column, piece), lanes in order; the first
-				 * eight partials and the accumulator are loaded together ---- */
-#pragma unroll
-				for (int z = 0; z < 2; z++) {
-					const int S = fS[z];
-					if (S <= 0)
-						continue;
-					double2 v[8];
-#pragma unroll
-					for (int sx = 0; sx < 8; sx++)
-						v[sx] = sx < S ? a3_lds_f64x2(fsrc[z] + sx * (KR * 8))
-							: make_double2(0.0, 0.0);
-					double2 bv = a3_lds_f64x2(fdst[z]);
-					double2 acc = make_double2(((v[0].x + v[1].x) + (v[2].x + v[3].x))
-						+ ((v[4].x + v[5].x) + (v[6].x + v[7].x)),
-						((v[0].y + v[1].y) + (v[2].y + v[3].y))
-						+ ((v[4].y + v[5].y) + (v[6].y + v[7].y)));
-					for (int sx = 8; sx < S; sx++) {
-						const double2 w8 = a3_lds_f64x2(fsrc[z] + sx * (KR * 8));
-						acc.x += w8.x;
-						acc.y += w8.y;
-					}
-					bv.x += acc.x;
-					bv.y += acc.y;
-					a3_sts_f64x2(fdst[z], bv);
-				}
-				/* more than two items per thread: many small columns (rare) */
-				for (int f = t + 2 * A3_THREADS; f < a.ncolmax * KP; f += A3_THREADS) {
+				/* ---- fold: thread <-> (column, piece), lanes in order ---- */
+				for (int f = t; f < a.ncolmax * KP; f += A3_THREADS) {
 					const int cc = f / KP, pc = f - cc * KP;
 					const int lane0 = cst_s[csw + cc], S = cst_s[csw + cc + 1] - lane0;
 					if (S <= 0)
@@ -628,16 +575,29 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					const unsigned info = cst_s[2 * csw + cc];
 					const double2 *src = reinterpret_cast<const double2 *>(
 						part_s + (size_t)lane0 * KR + 2 * pc);
-					double2 acc = make_double2(0.0, 0.0);
-					for (int sx = 0; sx < S; sx++) {
-						acc.x += src[(size_t)sx * KP].x;
-						acc.y += src[(size_t)sx * KP].y;
+					/* four independent partial sums keep four loads in flight */
+					double2 acc = make_double2(0.0, 0.0), a1 = acc, a2 = acc, a3 = acc;
+					int sx = 0;
+					for (; sx + 3 < S; sx += 4) {
+						const double2 v0 = src[(size_t)sx * KP];
+						const double2 v1 = src[(size_t)(sx + 1) * KP];
+						const double2 v2 = src[(size_t)(sx + 2) * KP];
+						const double2 v3 = src[(size_t)(sx + 3) * KP];
+						acc.x += v0.x; acc.y += v0.y;
+						a1.x += v1.x; a1.y += v1.y;
+						a2.x += v2.x; a2.y += v2.y;
+						a3.x += v3.x; a3.y += v3.y;
+					}
+					for (; sx < S; sx++) {
+						const double2 v0 = src[(size_t)sx * KP];
+						acc.x += v0.x;
+						acc.y += v0.y;
 					}
 					double2 *dst = reinterpret_cast<double2 *>(B_s + (size_t)(tro
 						+ rb[info >> 8] + (int)(info & 0xff)) * KR + 2 * pc);
 					double2 v = *dst;
-					v.x += acc.x;
-					v.y += acc.y;
+					v.x += (acc.x + a1.x) + (a2.x + a3.x);
+					v.y += (acc.y + a1.y) + (a2.y + a3.y);
 					*dst = v;
 				}
 			}
