@@ -16,6 +16,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 
 #include "multiclust.h"
 
@@ -30,18 +31,22 @@
  * draws starts -- one 31 x 31 matrix-vector product per block -- and advances
  * its own generator by the same I*L*P draws.  With --gpus N device r draws for
  * its rows of individuals, i.e. from draw row_first[r]*L*P on. */
+static uint32_t g_jump[MCR_LAG * MCR_LAG];	/* advance by RAND_BLOCK draws */
+static pthread_once_t g_jump_once = PTHREAD_ONCE_INIT;
+
+static void make_jump(void)
+{
+	mcr_jump_matrix(RAND_BLOCK, g_jump);
+}
+
 static int random_initialize_admixture(options *opt, data *dat, model *mod)
 {
-	static uint32_t jump[MCR_LAG * MCR_LAG];
-	static int have_jump;
+	const uint32_t *jump = g_jump;
 	uint32_t h[MCR_LAG];
 	const long long per_row = (long long)dat->L * dat->ploidy;
 
 	(void)opt;
-	if (!have_jump) {
-		mcr_jump_matrix(RAND_BLOCK, jump);
-		have_jump = 1;
-	}
+	pthread_once(&g_jump_once, make_jump);	/* fits may run on several host threads */
 	mcr_history(mod->rng, h);
 	for (int r = 0; r < mod->n_gpus; r++) {
 		const long long n = (long long)(mod->row_first[r + 1] - mod->row_first[r]) * per_row;
