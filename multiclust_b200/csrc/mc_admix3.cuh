@@ -532,26 +532,33 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 						* (PP * A3_IT * 8);
 					const unsigned xe = csc_sa + 2u * cst_s[col + 1];
 					unsigned x = csc_sa + 2u * (cst_s[col] + (t - lane0c));
-					/* ids and weights are fetched one trip ahead */
-					unsigned ent = x < xe ? a3_lds_u16(x) : 0u;
-					double w = x < xe ? a3_lds_f64(wb + ((ent >> 9) & 7) * (A3_IT * 8)
-						+ (ent & (A3_IT - 1)) * 8) * (double)((ent >> 12) + 1) : 0.0;
+					/* ids run two trips ahead and weights one, and nothing is
+					 * computed from a load in the trip that issues it: the warp
+					 * issues in order, so a multiply on a fresh load would hold
+					 * the accumulation of the current entry back */
+					auto w_addr = [&](unsigned en) {
+						return wb + ((en >> 9) & 7) * (A3_IT * 8) + (en & (A3_IT - 1)) * 8;
+					};
+					unsigned e0 = x < xe ? a3_lds_u16(x) : 0u;
+					unsigned e1 = x + S2 < xe ? a3_lds_u16(x + S2) : 0u;
+					double w0 = x < xe ? a3_lds_f64(w_addr(e0)) : 0.0;
 					while (x < xe) {
-						const unsigned rm = eta_sa + (ent & (A3_IT - 1)) * (NP * 16);
-						const double wc = w;
-						x += S2;
-						ent = x < xe ? a3_lds_u16(x) : 0u;
+						const unsigned rm = eta_sa + (e0 & (A3_IT - 1)) * (NP * 16);
+						const double wc = w0 * (double)((e0 >> 12) + 1);
+						const unsigned e2 = x + 2 * S2 < xe ? a3_lds_u16(x + 2 * S2) : 0u;
 						double2 v[KP];
 #pragma unroll
 						for (int s = 0; s < KP; s++)
 							v[s] = a3_lds_f64x2(rm + (s << 4));
-						w = x < xe ? a3_lds_f64(wb + ((ent >> 9) & 7) * (A3_IT * 8)
-							+ (ent & (A3_IT - 1)) * 8) * (double)((ent >> 12) + 1) : 0.0;
+						x += S2;
+						w0 = x < xe ? a3_lds_f64(w_addr(e1)) : 0.0;
 #pragma unroll
 						for (int s = 0; s < KP; s++) {
 							g[2 * s] = fma(v[s].x, wc, g[2 * s]);
 							g[2 * s + 1] = fma(v[s].y, wc, g[2 * s + 1]);
 						}
+						e0 = e1;
+						e1 = e2;
 					}
 				}
 				/* the lane's partial sums */
