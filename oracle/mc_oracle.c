@@ -5,7 +5,7 @@
  * function cites the reference lines it follows.  Loop orders and expression
  * shapes are kept identical to the reference so that, compiled without FMA
  * contraction, results are bit-identical to the reference objects (checked by
- * tests/test_oracle_vs_ref.py).  The reference materialises d_iklm
+ * tests/test_oracle_golden.py on vectors written by the reference itself).  The reference materialises d_iklm
  * (multiclust.c:1197); here the E-step folds it straight into the sums the
  * M-step needs, visiting terms in the reference's order.
  */

@@ -6,7 +6,7 @@
  * --impl reference legs may load this library; the product (libmc_cuda.so and
  * the multiclust host binary) never links or calls it.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_ref.py checks this restatement
+ * Parity status: PINNED.  tests/test_oracle_golden.py on vectors written by the reference itself checks this restatement
  * bit-for-bit (log likelihood, parameters, posterior sums) against the
  * unmodified reference objects driven by oracle/ref_harness.c, and against the
  * golden vectors that harness wrote into tests/golden/.
