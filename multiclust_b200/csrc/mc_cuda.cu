@@ -69,12 +69,19 @@ struct mc_ctx {
 
 	/* two-pass admixture plan (mc_admix3.cuh); used when `use3` */
 	bool use3 = false;
+	bool layout3 = false;		/* codes / lists / column tables are built */
+	int l3_ncolmax = 0, l3_max_tile_rows = 0;
+	std::vector<int> l3_lt_rows;	/* allele rows per locus tile (host) */
 	Admix3Args a3;
 	int KP3 = 0, grid3 = 0;
 	size_t smem3 = 0, smem3_ll = 0;
 	int *d3_lt_ncol = nullptr, *d3_lc_first = nullptr;
 	unsigned short *d3_colinfo = nullptr, *d3_csc = nullptr, *d3_colstart = nullptr;
 	unsigned char *d3_codes = nullptr;
+	/* scratch of the admixture initialiser, kept between fits */
+	unsigned char *d_init_z = nullptr;
+	unsigned *d_init_N = nullptr, *d_init_h = nullptr;
+	size_t init_z_n = 0, init_N_n = 0, init_h_n = 0;
 	/* sizes of the partial-sum buffers of the active plan */
 	int act_tiles = 0, act_chunks = 0, act_units = 0;
 	long long act_Ipad = 0;
@@ -171,10 +178,18 @@ static void free_plan(mc_ctx *c)
 	dfree(c->d_group_rowbase); dfree(c->d_group_rows); dfree(c->d_tile_rows);
 	dfree(c->d_tiled); dfree(c->d_Apart); dfree(c->d_Npart);
 	dfree(c->d_llpart); dfree(c->d_xbuf); dfree(c->d_red);
-	dfree(c->d3_lt_ncol); dfree(c->d3_lc_first); dfree(c->d3_colinfo);
+	dfree(c->d3_lc_first);
+	c->use3 = false;
+}
+
+/* the admixture kernel's tile codes and entry lists depend on the data only,
+ * not on K: they survive mc_alloc_model and are rebuilt by mc_set_data */
+static void free_layout3(mc_ctx *c)
+{
+	dfree(c->d3_lt_ncol); dfree(c->d3_colinfo);
 	dfree(c->d3_csc); dfree(c->d3_colstart);
 	dfree(c->d3_codes);
-	c->use3 = false;
+	c->layout3 = false;
 }
 
 static void free_model(mc_ctx *c)
@@ -196,6 +211,9 @@ static void free_model(mc_ctx *c)
 static void free_data(mc_ctx *c)
 {
 	free_model(c);
+	free_layout3(c);
+	dfree(c->d_init_z); dfree(c->d_init_N); dfree(c->d_init_h);
+	c->init_z_n = c->init_N_n = c->init_h_n = 0;
 	dfree(c->d_nat); dfree(c->d_J); dfree(c->d_off);
 	c->I = 0;
 }
@@ -487,48 +505,76 @@ static int make_plan3(mc_ctx *c)
 	if (n_itiles * n_ltiles > 0x7fffffffLL)
 		return MC_OK;
 
-	/* allele counts: column order and lanes per column */
-	unsigned *d_hist = nullptr;
-	std::vector<unsigned> hist((size_t)c->T);
-	CK(cudaMalloc(&d_hist, sizeof(unsigned) * (size_t)c->T));
-	CK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * (size_t)c->T, c->stream));
-	k_allele_hist<<<grid_for(c, c->I * (long long)L, 256), 256, 0, c->stream>>>(
-		c->d_nat, c->I, L, c->P, c->d_off, d_hist);
-	LAUNCH_CHECK("k_allele_hist");
-	CK(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned) * (size_t)c->T,
-		cudaMemcpyDeviceToHost, c->stream));
-	CK(cudaStreamSynchronize(c->stream));
-	cudaFree(d_hist);
-	mark("allele histogram");
+	/* ---- data-only part: built once per data set, reused for every K ---- */
+	if (!c->layout3) {
+		/* allele counts: column order of every locus tile */
+		unsigned *d_hist = nullptr;
+		std::vector<unsigned> hist((size_t)c->T);
+		CK(cudaMalloc(&d_hist, sizeof(unsigned) * (size_t)c->T));
+		CK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * (size_t)c->T, c->stream));
+		k_allele_hist<<<grid_for(c, c->I * (long long)L, 256), 256, 0, c->stream>>>(
+			c->d_nat, c->I, L, c->P, c->d_off, d_hist);
+		LAUNCH_CHECK("k_allele_hist");
+		CK(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned) * (size_t)c->T,
+			cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		cudaFree(d_hist);
+		mark("allele histogram");
 
-	std::vector<int> lt_ncol((size_t)n_ltiles), lt_rows((size_t)n_ltiles);
-	std::vector<std::vector<std::pair<unsigned, unsigned short>>> cols((size_t)n_ltiles);
-	int ncolmax = 1, max_tile_rows = 1;
-	for (int lt = 0; lt < n_ltiles; lt++) {
-		const int lf = lt * LT, le = std::min(L, lf + LT);
-		lt_rows[lt] = c->off[le] - c->off[lf];
-		max_tile_rows = std::max(max_tile_rows, lt_rows[lt]);
-		auto &v = cols[lt];
-		for (int l = lf; l < le; l++)
-			for (int j = 0; j < c->J[l]; j++)
-				if (hist[(size_t)c->off[l] + j])
-					v.push_back({ hist[(size_t)c->off[l] + j],
-						(unsigned short)((l - lf) << 8 | j) });
-		std::stable_sort(v.begin(), v.end(),
-			[](const std::pair<unsigned, unsigned short> &x,
-			   const std::pair<unsigned, unsigned short> &y) { return x.first > y.first; });
-		lt_ncol[lt] = (int)v.size();
-		ncolmax = std::max(ncolmax, (int)v.size());
+		std::vector<int> lt_ncol((size_t)n_ltiles);
+		std::vector<std::vector<std::pair<unsigned, unsigned short>>> cols((size_t)n_ltiles);
+		int ncm = 1, mtr = 1;
+		c->l3_lt_rows.assign((size_t)n_ltiles, 0);
+		for (int lt = 0; lt < n_ltiles; lt++) {
+			const int lf = lt * LT, le = std::min(L, lf + LT);
+			c->l3_lt_rows[lt] = c->off[le] - c->off[lf];
+			mtr = std::max(mtr, c->l3_lt_rows[lt]);
+			auto &v = cols[lt];
+			for (int l = lf; l < le; l++)
+				for (int j = 0; j < c->J[l]; j++)
+					if (hist[(size_t)c->off[l] + j])
+						v.push_back({ hist[(size_t)c->off[l] + j],
+							(unsigned short)((l - lf) << 8 | j) });
+			std::stable_sort(v.begin(), v.end(),
+				[](const std::pair<unsigned, unsigned short> &x,
+				   const std::pair<unsigned, unsigned short> &y) { return x.first > y.first; });
+			lt_ncol[lt] = (int)v.size();
+			ncm = std::max(ncm, (int)v.size());
+		}
+		if (ncm > A3_THREADS || ncm >= 255)
+			return MC_OK;	/* more allele columns in a tile than lanes */
+		/* most frequent allele first; the lanes per column are chosen per
+		 * tile by k3_build_csc */
+		std::vector<unsigned short> colinfo((size_t)n_ltiles * ncm, 0);
+		for (int lt = 0; lt < n_ltiles; lt++)
+			for (size_t x = 0; x < cols[lt].size(); x++)
+				colinfo[(size_t)lt * ncm + x] = cols[lt][x].second;
+		free_layout3(c);
+		int rc;
+		if ((rc = upload(c, c->d3_lt_ncol, lt_ncol))) return rc;
+		if ((rc = upload(c, c->d3_colinfo, colinfo))) return rc;
+		const size_t ntile = (size_t)n_itiles * n_ltiles;
+		mark("column order + uploads");
+		CK(cudaMalloc(&c->d3_codes, ntile * A3_THREADS * 8));
+		CK(cudaMalloc(&c->d3_csc, ntile * cap * sizeof(unsigned short)));
+		CK(cudaMalloc(&c->d3_colstart, ntile * 3 * (size_t)((ncm + 1 + 7) / 8 * 8)
+			* sizeof(unsigned short)));
+		mark("cudaMalloc codes/lists");
+		k3_build_codes<<<grid_for(c, (long long)ntile * A3_THREADS, 256), 256, 0, c->stream>>>(
+			c->d_nat, c->d3_codes, c->I, L, c->P, PP, (int)n_itiles, n_ltiles);
+		LAUNCH_CHECK("k3_build_codes");
+		mark("k3_build_codes");
+		const size_t bsm = (size_t)A3_IT * 8 + sizeof(int) * (2 * (size_t)ncm + 1);
+		k3_build_csc<<<(unsigned)ntile, 128, bsm, c->stream>>>(c->d3_codes, PP, n_ltiles,
+			ncm, cap, c->d3_lt_ncol, c->d3_colinfo, c->d3_csc, c->d3_colstart);
+		LAUNCH_CHECK("k3_build_csc");
+		mark("k3_build_csc");
+		c->l3_ncolmax = ncm;
+		c->l3_max_tile_rows = mtr;
+		c->layout3 = true;
 	}
-	if (ncolmax > A3_THREADS || ncolmax >= 255)
-		return MC_OK;	/* more allele columns in a tile than lanes */
-
-	/* column order of every locus tile (most frequent allele first); the lanes
-	 * per column are chosen per tile by k3_build_csc */
-	std::vector<unsigned short> colinfo((size_t)n_ltiles * ncolmax, 0);
-	for (int lt = 0; lt < n_ltiles; lt++)
-		for (size_t x = 0; x < cols[lt].size(); x++)
-			colinfo[(size_t)lt * ncolmax + x] = cols[lt][x].second;
+	const int ncolmax = c->l3_ncolmax, max_tile_rows = c->l3_max_tile_rows;
+	const std::vector<int> &lt_rows = c->l3_lt_rows;
 
 	/* shared memory: fixed part, the rest holds the chunk's accumulators */
 	const int PR = (max_tile_rows + 1) & ~1;
@@ -613,24 +659,7 @@ static int make_plan3(mc_ctx *c)
 	c->grid3 = (int)std::min<long long>(a.n_units, sms);
 
 	int rc;
-	if ((rc = upload(c, c->d3_lt_ncol, lt_ncol))) return rc;
 	if ((rc = upload(c, c->d3_lc_first, lc_first))) return rc;
-	if ((rc = upload(c, c->d3_colinfo, colinfo))) return rc;
-	const size_t ntile = (size_t)n_itiles * n_ltiles;
-	mark("host planning + uploads");
-	CK(cudaMalloc(&c->d3_codes, ntile * A3_THREADS * 8));
-	CK(cudaMalloc(&c->d3_csc, ntile * cap * sizeof(unsigned short)));
-	CK(cudaMalloc(&c->d3_colstart, ntile * 3 * (size_t)((ncolmax + 1 + 7) / 8 * 8) * sizeof(unsigned short)));
-	mark("cudaMalloc codes/lists");
-	k3_build_codes<<<grid_for(c, (long long)ntile * A3_THREADS, 256), 256, 0, c->stream>>>(
-		c->d_nat, c->d3_codes, c->I, L, c->P, PP, (int)n_itiles, n_ltiles);
-	LAUNCH_CHECK("k3_build_codes");
-	mark("k3_build_codes");
-	const size_t bsm = (size_t)A3_IT * 8 + sizeof(int) * (2 * (size_t)ncolmax + 1);
-	k3_build_csc<<<(unsigned)ntile, 128, bsm, c->stream>>>(c->d3_codes, PP, n_ltiles,
-		ncolmax, cap, c->d3_lt_ncol, c->d3_colinfo, c->d3_csc, c->d3_colstart);
-	LAUNCH_CHECK("k3_build_csc");
-	mark("k3_build_csc");
 	a.lt_ncol = c->d3_lt_ncol; a.colinfo = c->d3_colinfo;
 	 a.lc_first = c->d3_lc_first; a.off = c->d_off;
 	a.codes = c->d3_codes; a.csc = c->d3_csc; a.colstart = c->d3_colstart;
@@ -1109,18 +1138,33 @@ extern "C" int mc_init_admixture(mc_ctx *c, int slot, const uint8_t *z)
 	return rc;
 }
 
-/* counts + M-step from the assignment d_z (device), which is freed */
-static int init_from_assignment(mc_ctx *c, int slot, unsigned char *d_z)
+/* scratch buffer of the initialiser, grown when needed and kept between fits
+ * (cudaMalloc / cudaFree per fit cost more than a small fit's EM) */
+template <typename T> static int init_scratch(mc_ctx *c, T *&buf, size_t &have, size_t want)
 {
-	unsigned *d_N = nullptr;
-	CK(cudaMalloc(&d_N, sizeof(unsigned) * (size_t)std::max<int64_t>(c->np, 1)));
-	CK(cudaMemsetAsync(d_N, 0, sizeof(unsigned) * (size_t)std::max<int64_t>(c->np, 1), c->stream));
-	k_init_counts<<<grid_for(c, c->I, 128), 128, 0, c->stream>>>(c->d_nat, d_z,
-		c->I, c->L, c->P, c->K, c->d_off, c->T, c->d_post, d_N);
+	if (want <= have)
+		return MC_OK;
+	dfree(buf);
+	have = 0;
+	CK(cudaMalloc(&buf, sizeof(T) * want));
+	have = want;
+	return MC_OK;
+}
+
+/* counts + M-step from the assignment in c->d_init_z */
+static int init_from_assignment(mc_ctx *c, int slot)
+{
+	const size_t np = (size_t)std::max<int64_t>(c->np, 1);
+	int rc = init_scratch(c, c->d_init_N, c->init_N_n, np);
+	if (rc)
+		return rc;
+	CK(cudaMemsetAsync(c->d_init_N, 0, sizeof(unsigned) * np, c->stream));
+	k_init_counts<<<(unsigned)std::min<long long>(std::max<long long>(c->I, 1),
+		(long long)c->num_sms * 32), 128, 0, c->stream>>>(c->d_nat, c->d_init_z,
+		c->I, c->L, c->P, c->K, c->d_off, c->T, c->d_post, c->d_init_N);
 	LAUNCH_CHECK("k_init_counts");
-	k_u32_to_f64<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(d_N, xb_N(c), c->np);
+	k_u32_to_f64<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_init_N, xb_N(c), c->np);
 	LAUNCH_CHECK("k_u32_to_f64");
-	int rc = MC_OK;
 	if (c->per_indiv) {
 		k_eta_from_D<<<grid_for(c, c->I, 128), 128, 0, c->stream>>>(c->d_post,
 			c->d_eta[slot], c->I, c->K, c->do_proj, c->eta_lb);
@@ -1128,9 +1172,6 @@ static int init_from_assignment(mc_ctx *c, int slot, unsigned char *d_z)
 	} else {
 		if ((rc = reduce_columns(c, c->d_post, c->I, c->K, xb_S(c)))) return rc;
 	}
-	CK(cudaStreamSynchronize(c->stream));
-	cudaFree(d_z);
-	cudaFree(d_N);
 	return MC_OK;
 }
 
@@ -1153,10 +1194,12 @@ extern "C" int mc_init_admixture_local(mc_ctx *c, int slot, const uint8_t *z)
 	if (rc)
 		return rc;
 	const size_t n = (size_t)c->I * c->L * c->P;
-	unsigned char *d_z = nullptr;
-	CK(cudaMalloc(&d_z, n ? n : 1));
-	CK(cudaMemcpyAsync(d_z, z, n, cudaMemcpyHostToDevice, c->stream));
-	return init_from_assignment(c, slot, d_z);
+	if ((rc = init_scratch(c, c->d_init_z, c->init_z_n, n ? n : 1)))
+		return rc;
+	CK(cudaMemcpyAsync(c->d_init_z, z, n, cudaMemcpyHostToDevice, c->stream));
+	rc = init_from_assignment(c, slot);
+	CK(cudaStreamSynchronize(c->stream));	/* z is the caller's again */
+	return rc;
 }
 
 extern "C" int mc_init_admixture_rand_local(mc_ctx *c, int slot, const uint32_t *hist,
@@ -1171,17 +1214,16 @@ extern "C" int mc_init_admixture_rand_local(mc_ctx *c, int slot, const uint32_t 
 		return fail(c, MC_ERR_ARG, "mc_init_admixture_rand: %lld blocks of %lld draws "
 			"do not tile the %lld allele copies (blocks must be multiples of 16)",
 			(long long)n_blocks, (long long)block_draws, n);
-	unsigned char *d_z = nullptr;
-	unsigned *d_h = nullptr;
-	CK(cudaMalloc(&d_z, n ? (size_t)n : 1));
-	CK(cudaMalloc(&d_h, sizeof(unsigned) * 31 * (size_t)n_blocks));
-	CK(cudaMemcpyAsync(d_h, hist, sizeof(unsigned) * 31 * (size_t)n_blocks,
+	if ((rc = init_scratch(c, c->d_init_z, c->init_z_n, n ? (size_t)n : 1))
+		|| (rc = init_scratch(c, c->d_init_h, c->init_h_n, 31 * (size_t)n_blocks)))
+		return rc;
+	CK(cudaMemcpyAsync(c->d_init_h, hist, sizeof(unsigned) * 31 * (size_t)n_blocks,
 		cudaMemcpyHostToDevice, c->stream));
-	k_rand_assign<<<(unsigned)((n_blocks + 63) / 64), 64, 0, c->stream>>>(d_h, n_blocks,
-		block_draws, n, (unsigned)c->K, d_z);
+	k_rand_assign<<<(unsigned)((n_blocks + 63) / 64), 64, 0, c->stream>>>(c->d_init_h,
+		n_blocks, block_draws, n, (unsigned)c->K, c->d_init_z);
 	LAUNCH_CHECK("k_rand_assign");
-	rc = init_from_assignment(c, slot, d_z);
-	cudaFree(d_h);
+	rc = init_from_assignment(c, slot);
+	CK(cudaStreamSynchronize(c->stream));	/* hist is the caller's again */
 	return rc;
 }
 

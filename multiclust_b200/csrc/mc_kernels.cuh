@@ -881,15 +881,19 @@ __global__ void k_partition(const double *post, long long I, int K, int *I_K)
 /* ------------------------------------------------------------------ */
 /* admixture initialiser (rnd_init.c:456-482): hard assignment counts     */
 
+/* one CTA per individual, threads stride over its loci (coalesced reads of the
+ * codes and of z); D_i is counted in shared memory, the allele counts with
+ * integer atomics in global memory: order-independent, so deterministic */
 __global__ void k_init_counts(const unsigned char *nat, const unsigned char *z,
 	long long I, int L, int P, int K, const int *off, long long T,
 	double *D /* [I][K] */, unsigned *N /* [K][T] */)
 {
-	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < I;
-		i += (long long)gridDim.x * blockDim.x) {
-		for (int k = 0; k < K; k++)
-			D[(size_t)i * K + k] = 0.0;
-		for (int l = 0; l < L; l++) {
+	__shared__ unsigned Dsm[256];
+	for (long long i = blockIdx.x; i < I; i += gridDim.x) {
+		for (int k = threadIdx.x; k < K; k += blockDim.x)
+			Dsm[k] = 0u;
+		__syncthreads();
+		for (int l = threadIdx.x; l < L; l += blockDim.x) {
 			const unsigned char *c = nat + ((size_t)i * L + l) * P;
 			const unsigned char *zz = z + ((size_t)i * L + l) * P;
 			for (int ap = 0; ap < P; ap++) {
@@ -900,10 +904,14 @@ __global__ void k_init_counts(const unsigned char *nat, const unsigned char *z,
 					seen |= (c[b] == c[ap] && zz[b] == zz[ap]);
 				if (seen)
 					continue;
-				D[(size_t)i * K + zz[ap]] += 1.0;
+				atomicAdd(&Dsm[zz[ap]], 1u);
 				atomicAdd(&N[(size_t)zz[ap] * T + off[l] + c[ap]], 1u);
 			}
 		}
+		__syncthreads();
+		for (int k = threadIdx.x; k < K; k += blockDim.x)
+			D[(size_t)i * K + k] = (double)Dsm[k];
+		__syncthreads();
 	}
 }
 

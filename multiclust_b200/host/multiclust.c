@@ -33,7 +33,7 @@ static double wall_now(void)
 	return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 static int g_timing;
-static double g_t_init, g_t_em, g_t_write;
+static double g_t_init, g_t_em, g_t_write, g_t_plan, g_t_record;
 
 /* the initialisers' random stream: glibc's rand() state after no srand()
  * call equals srand(1) */
@@ -726,8 +726,10 @@ int maximize_likelihood(options *opt, data *dat, model *mod, int bootstrap)
 		if (opt->dump_prefix && (err = dump_state(opt, dat, mod, i, "final", mod->pindex)))
 			return err;
 
+		t0 = wall_now();
 		if ((err = record_fit(opt, dat, mod, i, bootstrap, write_best_from_device, NULL)))
 			return err;
+		g_t_record += wall_now() - t0;
 		if (mod->K == 1)
 			break;
 		if (mod->time_stop)
@@ -788,8 +790,10 @@ int estimate_model(options *opt, data *dat, model *mod, int bootstrap)
 	for (;;) {
 		if (dat->max_M < mod->K)
 			dat->max_M = mod->K;
+		double t0 = wall_now();
 		if ((err = allocate_model_for_k(opt, mod, dat)))
 			return err;
+		g_t_plan += wall_now() - t0;
 		if ((err = maximize_likelihood(opt, dat, mod, bootstrap)))
 			return err;
 		if (opt->n_repeat == 1 && opt->verbosity)
@@ -803,7 +807,9 @@ int estimate_model(options *opt, data *dat, model *mod, int bootstrap)
 			min_bic = mod->bic;
 			mod->bic_K = mod->K;
 		}
+		t0 = wall_now();
 		free_model_data(mod, opt);
+		g_t_plan += wall_now() - t0;
 		if (mod->K >= opt->max_K)
 			break;
 		mod->K++;
@@ -888,10 +894,10 @@ int main(int argc, const char **argv)
 	if (!err && opt->parallel)
 		printf("%f\n", mod->max_logL);
 	if (g_timing)
-		fprintf(stderr, "timing (s): read %.3f, upload %.3f, plan+other %.3f, initialise "
-			"%.3f, em %.3f (%d iterations), fetch+write %.3f, total %.3f\n",
-			t_read - t_start, t_upload - t_read,
-			wall_now() - t_upload - g_t_init - g_t_em - g_t_write, g_t_init,
+		fprintf(stderr, "timing (s): read %.3f, upload %.3f, plan per K %.3f, other %.3f, "
+			"initialise %.3f, em %.3f (%d iterations), fetch+write %.3f, total %.3f\n",
+			t_read - t_start, t_upload - t_read, g_t_plan,
+			wall_now() - t_upload - g_t_init - g_t_em - g_t_record - g_t_plan, g_t_init,
 			g_t_em, mod->n_total_iter ? mod->n_total_iter : mod->n_iter, g_t_write,
 			wall_now() - t_start);
 done:

@@ -19,6 +19,7 @@ for extra in ([], ["--gpus", str(n_gpus), "--shard-fits"]):
     r = subprocess.run(base + ["-d", d] + extra, capture_output=True, text=True)
     dt = time.perf_counter() - t0
     outs.append((r.stdout, d))
+    print(r.stderr.strip().splitlines()[-1][:220] if r.stderr.strip() else "")
     print("%-28s rc %d  wall %.2f s  (%d fits)" % (" ".join(extra) or "one device", r.returncode, dt,
                                                 r.stdout.count("initialization =")))
 import re
