@@ -134,6 +134,21 @@ static int grid_for(const mc_ctx *c, long long n, int threads)
 	return (int)g;
 }
 
+/* Device memory comes from the device's stream-ordered pool with the release
+ * threshold lifted (mc_create): what a model or plan frees stays mapped and is
+ * handed out again by the next allocation.  A K sweep re-allocates ~15 buffers
+ * per K, and cudaMalloc / cudaFree cost 5-15 ms each on this platform. */
+template <typename T> static cudaError_t mc_dev_malloc(cudaStream_t stream, T **p, size_t n)
+{
+	cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(p), n ? n : 1, stream);
+	if (e != cudaSuccess) {	/* pool unsupported or exhausted: plain allocation */
+		(void)cudaGetLastError();
+		e = cudaMalloc(reinterpret_cast<void **>(p), n ? n : 1);
+	}
+	return e;
+}
+#define MC_DEV_MALLOC(ptr, n) mc_dev_malloc(c->stream, (ptr), (n))
+
 template <typename T> static void dfree(T *&p)
 {
 	if (p)
@@ -164,7 +179,15 @@ extern "C" int mc_create(mc_ctx **out, int device)
 	}
 	c->stream = c->own_stream;
 	cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
-	if (cudaMalloc(&c->d_small, 64 * sizeof(double)) != cudaSuccess) {
+	{	/* keep freed device memory in the pool (see mc_dev_malloc) */
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+			unsigned long long keep = ~0ULL;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+		(void)cudaGetLastError();
+	}
+	if (MC_DEV_MALLOC(&c->d_small, 64 * sizeof(double)) != cudaSuccess) {
 		delete c;
 		return fail(nullptr, MC_ERR_NOMEM, "cudaMalloc failed");
 	}
@@ -279,8 +302,8 @@ static int set_dims(mc_ctx *c, int64_t I, int32_t L, int32_t P, const int32_t *J
 		c->off[l + 1] = c->off[l] + J[l];
 	}
 	c->T = c->off[L];
-	CK(cudaMalloc(&c->d_J, sizeof(int) * (size_t)L));
-	CK(cudaMalloc(&c->d_off, sizeof(int) * ((size_t)L + 1)));
+	CK(MC_DEV_MALLOC(&c->d_J, sizeof(int) * (size_t)L));
+	CK(MC_DEV_MALLOC(&c->d_off, sizeof(int) * ((size_t)L + 1)));
 	CK(cudaMemcpyAsync(c->d_J, c->J.data(), sizeof(int) * (size_t)L,
 		cudaMemcpyHostToDevice, c->stream));
 	CK(cudaMemcpyAsync(c->d_off, c->off.data(), sizeof(int) * ((size_t)L + 1),
@@ -298,7 +321,7 @@ extern "C" int mc_set_data(mc_ctx *c, int64_t I, int32_t L, int32_t P,
 	if (rc)
 		return rc;
 	const size_t n = (size_t)I * L * P;
-	CK(cudaMalloc(&c->d_nat, n));
+	CK(MC_DEV_MALLOC(&c->d_nat, n));
 	CK(cudaMemcpyAsync(c->d_nat, codes, n, cudaMemcpyHostToDevice, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	return MC_OK;
@@ -317,9 +340,9 @@ extern "C" int mc_set_data_synth(mc_ctx *c, int64_t I, int32_t L,
 	const size_t n = (size_t)I * L * P;
 	unsigned *d_present = nullptr, *d_missing = nullptr;
 	unsigned char *d_map = nullptr;
-	CK(cudaMalloc(&c->d_nat, n));
-	CK(cudaMalloc(&d_present, sizeof(unsigned) * 8 * (size_t)L));
-	CK(cudaMalloc(&d_missing, sizeof(unsigned) * (size_t)L));
+	CK(MC_DEV_MALLOC(&c->d_nat, n));
+	CK(MC_DEV_MALLOC(&d_present, sizeof(unsigned) * 8 * (size_t)L));
+	CK(MC_DEV_MALLOC(&d_missing, sizeof(unsigned) * (size_t)L));
 	CK(cudaMemsetAsync(d_present, 0, sizeof(unsigned) * 8 * (size_t)L, c->stream));
 	CK(cudaMemsetAsync(d_missing, 0, sizeof(unsigned) * (size_t)L, c->stream));
 	k_synth_fill<<<grid_for(c, I * (long long)L, 256), 256, 0, c->stream>>>(
@@ -342,7 +365,7 @@ extern "C" int mc_set_data_synth(mc_ctx *c, int64_t I, int32_t L,
 				map[(size_t)l * 256 + code] = (unsigned char)nreal++;
 		J[l] = nreal ? nreal + (missing[l] ? 1 : 0) : 0;
 	}
-	CK(cudaMalloc(&d_map, (size_t)L * 256));
+	CK(MC_DEV_MALLOC(&d_map, (size_t)L * 256));
 	CK(cudaMemcpyAsync(d_map, map.data(), (size_t)L * 256, cudaMemcpyHostToDevice, c->stream));
 	k_synth_remap<<<grid_for(c, I * (long long)L, 256), 256, 0, c->stream>>>(
 		c->d_nat, I, L, P, d_map);
@@ -451,7 +474,7 @@ static void build_tiles(const mc_ctx *c, int W, int NG, int LW, HostPlan &hp)
 template <typename T>
 static int upload(mc_ctx *c, T *&dst, const std::vector<T> &src)
 {
-	CK(cudaMalloc(&dst, sizeof(T) * std::max<size_t>(src.size(), 1)));
+	CK(MC_DEV_MALLOC(&dst, sizeof(T) * std::max<size_t>(src.size(), 1)));
 	CK(cudaMemcpyAsync(dst, src.data(), sizeof(T) * src.size(),
 		cudaMemcpyHostToDevice, c->stream));
 	return MC_OK;
@@ -465,11 +488,11 @@ static int alloc_outputs(mc_ctx *c, int n_tiles, int n_chunks, int n_units, long
 	c->act_tiles = n_tiles; c->act_chunks = n_chunks; c->act_units = n_units;
 	c->act_Ipad = Ipad;
 	const size_t nN = (size_t)n_chunks * K * std::max<int64_t>(c->T, 1);
-	CK(cudaMalloc(&c->d_Apart, sizeof(double) * (size_t)n_tiles * Ipad * K));
-	CK(cudaMalloc(&c->d_Npart, sizeof(double) * nN));
-	CK(cudaMalloc(&c->d_llpart, sizeof(double) * (size_t)n_units));
-	CK(cudaMalloc(&c->d_xbuf, sizeof(double) * ((size_t)K * c->T + 1 + K)));
-	CK(cudaMalloc(&c->d_red, sizeof(double) * (size_t)RED_BLOCKS * 8));
+	CK(MC_DEV_MALLOC(&c->d_Apart, sizeof(double) * (size_t)n_tiles * Ipad * K));
+	CK(MC_DEV_MALLOC(&c->d_Npart, sizeof(double) * nN));
+	CK(MC_DEV_MALLOC(&c->d_llpart, sizeof(double) * (size_t)n_units));
+	CK(MC_DEV_MALLOC(&c->d_xbuf, sizeof(double) * ((size_t)K * c->T + 1 + K)));
+	CK(MC_DEV_MALLOC(&c->d_red, sizeof(double) * (size_t)RED_BLOCKS * 8));
 	CK(cudaMemsetAsync(c->d_Npart, 0, sizeof(double) * nN, c->stream));
 	CK(cudaMemsetAsync(c->d_xbuf, 0, sizeof(double) * ((size_t)K * c->T + 1 + K), c->stream));
 	return MC_OK;
@@ -510,7 +533,7 @@ static int make_plan3(mc_ctx *c)
 		/* allele counts: column order of every locus tile */
 		unsigned *d_hist = nullptr;
 		std::vector<unsigned> hist((size_t)c->T);
-		CK(cudaMalloc(&d_hist, sizeof(unsigned) * (size_t)c->T));
+		CK(MC_DEV_MALLOC(&d_hist, sizeof(unsigned) * (size_t)c->T));
 		CK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * (size_t)c->T, c->stream));
 		k_allele_hist<<<grid_for(c, c->I * (long long)L, 256), 256, 0, c->stream>>>(
 			c->d_nat, c->I, L, c->P, c->d_off, d_hist);
@@ -555,9 +578,9 @@ static int make_plan3(mc_ctx *c)
 		if ((rc = upload(c, c->d3_colinfo, colinfo))) return rc;
 		const size_t ntile = (size_t)n_itiles * n_ltiles;
 		mark("column order + uploads");
-		CK(cudaMalloc(&c->d3_codes, ntile * A3_THREADS * 8));
-		CK(cudaMalloc(&c->d3_csc, ntile * cap * sizeof(unsigned short)));
-		CK(cudaMalloc(&c->d3_colstart, ntile * 3 * (size_t)((ncm + 1 + 7) / 8 * 8)
+		CK(MC_DEV_MALLOC(&c->d3_codes, ntile * A3_THREADS * 8));
+		CK(MC_DEV_MALLOC(&c->d3_csc, ntile * cap * sizeof(unsigned short)));
+		CK(MC_DEV_MALLOC(&c->d3_colstart, ntile * 3 * (size_t)((ncm + 1 + 7) / 8 * 8)
 			* sizeof(unsigned short)));
 		mark("cudaMalloc codes/lists");
 		k3_build_codes<<<grid_for(c, (long long)ntile * A3_THREADS, 256), 256, 0, c->stream>>>(
@@ -819,7 +842,7 @@ static int make_plan(mc_ctx *c)
 	ta.slot_J = c->d_slot_J; ta.group_rowbase = c->d_group_rowbase;
 	ta.group_rows = c->d_group_rows; ta.tile_rows = c->d_tile_rows;
 
-	CK(cudaMalloc(&c->d_tiled, (size_t)ta.tile_stride * best.n_tiles));
+	CK(MC_DEV_MALLOC(&c->d_tiled, (size_t)ta.tile_stride * best.n_tiles));
 	k_tile_codes<<<grid_for(c, (long long)best.n_tiles * n_blocks * best.tile_slots, 256),
 		256, 0, c->stream>>>(c->d_nat, c->d_tiled, c->d_slot_locus, best.n_tiles,
 		best.tile_slots, n_blocks, c->I, c->L, c->P, c->PP, c->IB, ta.tile_stride);
@@ -854,24 +877,24 @@ extern "C" int mc_alloc_model(mc_ctx *c, int32_t K, int admixture,
 	const size_t npb = sizeof(double) * (size_t)std::max<int64_t>(c->np, 1);
 	const size_t neb = sizeof(double) * (size_t)c->neta;
 	for (int s = 0; s < 3; s++) {
-		CK(cudaMalloc(&c->d_p[s], npb));
-		CK(cudaMalloc(&c->d_eta[s], neb));
+		CK(MC_DEV_MALLOC(&c->d_p[s], npb));
+		CK(MC_DEV_MALLOC(&c->d_eta[s], neb));
 		CK(cudaMemsetAsync(c->d_p[s], 0, npb, c->stream));
 		CK(cudaMemsetAsync(c->d_eta[s], 0, neb, c->stream));
 	}
 	for (int s = 0; s < q; s++) {
 		double *a, *b, *d, *e;
-		CK(cudaMalloc(&a, npb)); CK(cudaMalloc(&b, npb));
-		CK(cudaMalloc(&d, neb)); CK(cudaMalloc(&e, neb));
+		CK(MC_DEV_MALLOC(&a, npb)); CK(MC_DEV_MALLOC(&b, npb));
+		CK(MC_DEV_MALLOC(&d, neb)); CK(MC_DEV_MALLOC(&e, neb));
 		c->d_up.push_back(a); c->d_vp.push_back(b);
 		c->d_ue.push_back(d); c->d_ve.push_back(e);
 	}
-	CK(cudaMalloc(&c->d_post, sizeof(double) * (size_t)c->I * K));
+	CK(MC_DEV_MALLOC(&c->d_post, sizeof(double) * (size_t)c->I * K));
 	CK(cudaMemsetAsync(c->d_post, 0, sizeof(double) * (size_t)c->I * K, c->stream));
-	CK(cudaMalloc(&c->d_IK, sizeof(int) * (size_t)c->I));
+	CK(MC_DEV_MALLOC(&c->d_IK, sizeof(int) * (size_t)c->I));
 	if (!c->admixture) {
-		CK(cudaMalloc(&c->d_lli, sizeof(double) * (size_t)c->I));
-		CK(cudaMalloc(&c->d_logp, npb));
+		CK(MC_DEV_MALLOC(&c->d_lli, sizeof(double) * (size_t)c->I));
+		CK(MC_DEV_MALLOC(&c->d_logp, npb));
 	}
 	int rc = make_plan(c);
 	if (rc)
@@ -1146,7 +1169,7 @@ template <typename T> static int init_scratch(mc_ctx *c, T *&buf, size_t &have, 
 		return MC_OK;
 	dfree(buf);
 	have = 0;
-	CK(cudaMalloc(&buf, sizeof(T) * want));
+	CK(MC_DEV_MALLOC(&buf, sizeof(T) * want));
 	have = want;
 	return MC_OK;
 }
