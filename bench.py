@@ -15,7 +15,8 @@ the reference's stop() needs it (em_alg.c:195-207).
 
   value      iterations/s with genotypes and parameters resident in HBM
   e2e        iterations/s of a whole fit driven through the C ABI from HOST
-             buffers: mc_set_data from pinned host memory (H2D of the genotype
+             buffers (a fresh context; the resident-data context is closed
+             first, so its device memory is back in the library's pool): mc_set_data from pinned host memory (H2D of the genotype
              codes) + mc_alloc_model + mc_set_params + `steps` x mc_em_step
              (8-byte D2H each) + mc_get_params + mc_get_posterior
   roofline   algorithmic bytes (I*L*P + 16*I*K + 16*K*T) of the
@@ -343,6 +344,9 @@ def main():
         eta_o = torch.empty(eta0.size, dtype=torch.float64).pin_memory().numpy()
         p_o = torch.empty(p0.size, dtype=torch.float64).pin_memory().numpy()
         post_o = torch.empty(eta0.size, dtype=torch.float64).pin_memory().numpy()
+        # the resident-data context is done; its device memory goes back to the
+        # library's pool, as it would between two fits of one process
+        ctx.close()
         ctx2 = Context(local)
         barrier()
         t0 = time.perf_counter()
