@@ -586,9 +586,23 @@ __global__ void k_admix_eta(const double *Apart, int n_tiles, long long Ipad,
 			if (i >= I)
 				continue;
 			const int k = x % K;
-			double acc = 0.0;
-			for (int t = 0; t < n_tiles; t++)
-				acc += Apart[((size_t)t * Ipad + i0) * K + x];
+			/* four partial sums (tiles t % 4), eight loads in flight: the
+			 * pass is a pure stream over Apart; the order is fixed */
+			const double *src = Apart + (size_t)i0 * K + x;
+			const size_t ts = (size_t)Ipad * K;
+			double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+			int t = 0;
+			for (; t + 8 <= n_tiles; t += 8) {
+				const double v0 = __ldg(src + (size_t)t * ts), v1 = __ldg(src + (size_t)(t + 1) * ts);
+				const double v2 = __ldg(src + (size_t)(t + 2) * ts), v3 = __ldg(src + (size_t)(t + 3) * ts);
+				const double v4 = __ldg(src + (size_t)(t + 4) * ts), v5 = __ldg(src + (size_t)(t + 5) * ts);
+				const double v6 = __ldg(src + (size_t)(t + 6) * ts), v7 = __ldg(src + (size_t)(t + 7) * ts);
+				a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+				a0 += v4; a1 += v5; a2 += v6; a3 += v7;
+			}
+			for (; t < n_tiles; t++)
+				a0 += __ldg(src + (size_t)t * ts);
+			const double acc = (a0 + a1) + (a2 + a3);
 			const double d = eta_f[(size_t)i * eta_stride + k] * acc;
 			D[(size_t)i * K + k] = d;
 			rows[x] = d;
