@@ -46,7 +46,7 @@ enum {
 	MC_ERR_UNSUPPORTED = 5	/* e.g. ploidy > 16 or > 254 alleles at a locus */
 };
 
-#define MC_ABI_VERSION 1
+#define MC_ABI_VERSION 2
 
 /* message of the last error raised through `ctx` (or creation, if ctx NULL) */
 const char *mc_last_error(const mc_ctx *ctx);
@@ -64,6 +64,25 @@ int mc_sync(mc_ctx *ctx);
 /* the CUDA ordinal and the cudaStream_t launches currently go to */
 int mc_ctx_device(const mc_ctx *ctx);
 void *mc_ctx_stream(const mc_ctx *ctx);
+
+/* Plan options, to be set before mc_alloc_model (they replace environment
+ * variables: a stray variable must not switch kernels).
+ *   MC_OPT_KERNEL  which genotype-streaming kernel the planner may pick:
+ *                  MC_KERNEL_AUTO    dense DMMA kernels (mc_dense.cuh) when no locus
+ *                                    has more than two observed alleles and K <= 16,
+ *                                    else the two-pass gather kernel (mc_admix3.cuh;
+ *                                    admixture, K <= 16, ploidy <= 8), else the
+ *                                    one-pass tile kernel
+ *                  MC_KERNEL_TILE    the one-pass tile kernel only
+ *                  MC_KERNEL_ADMIX3  never the dense kernels
+ *                  MC_KERNEL_DENSE   the dense kernels where they apply, else
+ *                                    the one-pass tile kernel
+ *                  The kernels sum in different orders, so results agree to
+ *                  rounding (1e-13 relative observed), not bit for bit.
+ *   MC_OPT_TIMING  non-zero: the planner prints its phases to stderr */
+enum { MC_OPT_KERNEL = 1, MC_OPT_TIMING = 2 };
+enum { MC_KERNEL_AUTO = 0, MC_KERNEL_TILE = 1, MC_KERNEL_ADMIX3 = 2, MC_KERNEL_DENSE = 3 };
+int mc_set_option(mc_ctx *ctx, int option, int value);
 
 /* ---- data: replaces dat->IL / ILM / uniquealleles as the path reads them
  *      (multiclust.h:223-250, read_file.c:633-663) ------------------------ */
@@ -199,8 +218,8 @@ typedef struct {
 	int32_t loci_per_warp, warps, groups;	/* tile = warps*groups*loci_per_warp loci */
 	int32_t n_tiles, n_chunks, n_units, grid, block;
 	int32_t indiv_per_block, ploidy_padded;
-	int32_t two_pass;	/* 2: the two-pass admixture kernel (mc_admix3.cuh) is in use,
-				 * 0: the one-pass tile kernel */
+	int32_t two_pass;	/* 3: the dense DMMA kernels (mc_dense.cuh), 2: the two-pass
+				 * admixture kernel (mc_admix3.cuh), 0: the one-pass tile kernel */
 	int32_t reserved;
 	int64_t smem_bytes;
 	int64_t algorithmic_bytes_em;	/* I*L*P + 16*I*K + 16*K*T */

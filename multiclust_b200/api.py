@@ -20,7 +20,7 @@ SYMBOLS = [
     "mc_qn_dots", "mc_accel_update", "mc_qn_update", "mc_project",
     "mc_copy_slot", "mc_em_step_local", "mc_exchange_buffer",
     "mc_em_step_finish", "mc_exchange_sum", "mc_get_plan", "mc_launch_count",
-    "mc_profile_enable", "mc_profile_read",
+    "mc_profile_enable", "mc_profile_read", "mc_set_option",
 ]
 
 
@@ -116,6 +116,7 @@ def load_library():
     L.mc_launch_count.argtypes = [vp]
     L.mc_profile_enable.argtypes = [vp, C.c_int]
     L.mc_profile_read.argtypes = [vp, C.POINTER(C.c_int64), dp]
+    L.mc_set_option.argtypes = [vp, C.c_int, C.c_int]
     _lib = L
     return L
 
@@ -151,6 +152,12 @@ class Context:
         if rc:
             raise McError("%s failed (%d): %s" % (
                 what, rc, self.lib.mc_last_error(self.h).decode()))
+
+    OPT_KERNEL, OPT_TIMING = 1, 2
+    KERNEL_AUTO, KERNEL_TILE, KERNEL_ADMIX3, KERNEL_DENSE = 0, 1, 2, 3
+
+    def set_option(self, option, value):
+        self._ck(self.lib.mc_set_option(self.h, int(option), int(value)), "mc_set_option")
 
     # -- data
     def set_stream(self, cuda_stream):

@@ -20,6 +20,7 @@
 #include "mc_cuda.h"
 #include "mc_kernels.cuh"
 #include "mc_admix3.cuh"
+#include "mc_dense.cuh"
 
 #define KH_MAX 6
 #define SMEM_LIMIT (227 * 1024)
@@ -78,6 +79,17 @@ struct mc_ctx {
 	int *d3_lt_ncol = nullptr, *d3_lc_first = nullptr;
 	unsigned short *d3_colinfo = nullptr, *d3_csc = nullptr, *d3_colstart = nullptr;
 	unsigned char *d3_codes = nullptr;
+	/* dense DMMA plan for biallelic data (mc_dense.cuh); used when `use_dn` */
+	bool use_dn = false;
+	bool layout_dn = false;		/* packed counts are built */
+	int dn_maxcode = -1;		/* largest allele code in the data, -1: not looked at yet */
+	DenseArgs dn;
+	int dn_NB = 1, dn_pbits = 1, grid_dn = 0;
+	unsigned char *d_dn_cnt = nullptr;
+	double *d_dn_pd = nullptr;
+	int *d_dn_lc_first = nullptr;
+	/* plan options (mc_set_option) */
+	int opt_kernel = 0, opt_timing = 0;
 	/* scratch of the admixture initialiser, kept between fits */
 	unsigned char *d_init_z = nullptr;
 	unsigned *d_init_N = nullptr, *d_init_h = nullptr;
@@ -202,7 +214,9 @@ static void free_plan(mc_ctx *c)
 	dfree(c->d_tiled); dfree(c->d_Apart); dfree(c->d_Npart);
 	dfree(c->d_llpart); dfree(c->d_xbuf); dfree(c->d_red);
 	dfree(c->d3_lc_first);
+	dfree(c->d_dn_pd); dfree(c->d_dn_lc_first);
 	c->use3 = false;
+	c->use_dn = false;
 }
 
 /* the admixture kernel's tile codes and entry lists depend on the data only,
@@ -213,6 +227,8 @@ static void free_layout3(mc_ctx *c)
 	dfree(c->d3_csc); dfree(c->d3_colstart);
 	dfree(c->d3_codes);
 	c->layout3 = false;
+	dfree(c->d_dn_cnt);
+	c->layout_dn = false;
 }
 
 static void free_model(mc_ctx *c)
@@ -239,6 +255,7 @@ static void free_data(mc_ctx *c)
 	c->init_z_n = c->init_N_n = c->init_h_n = 0;
 	dfree(c->d_nat); dfree(c->d_J); dfree(c->d_off);
 	c->I = 0;
+	c->dn_maxcode = -1;
 }
 
 extern "C" void mc_destroy(mc_ctx *c)
@@ -506,15 +523,14 @@ static int make_plan3(mc_ctx *c)
 	c->use3 = false;
 	if (!c->admixture || c->PP > 8 || c->K > 16 || c->T < 1)
 		return MC_OK;
-	if (const char *ev = getenv("MC_KERNEL"))
-		if (atoi(ev) == 1)
-			return MC_OK;	/* tuning knob: force the one-pass kernel */
+	if (c->opt_kernel == MC_KERNEL_TILE || c->opt_kernel == MC_KERNEL_DENSE)
+		return MC_OK;
 	const int K = c->K, KP = (K + 1) / 2, KR = 2 * KP, PP = c->PP, L = c->L;
 	const int LT = 8 / PP;
 	const int n_ltiles = (L + LT - 1) / LT;
 	const long long n_itiles = (c->I + A3_IT - 1) / A3_IT;
 	const int cap = A3_IT * 8;
-	const bool timing = getenv("MC_TIMING") != nullptr;
+	const bool timing = c->opt_timing != 0;
 	auto t_prev = std::chrono::steady_clock::now();
 	auto mark = [&](const char *what) {
 		if (!timing)
@@ -564,8 +580,10 @@ static int make_plan3(mc_ctx *c)
 			lt_ncol[lt] = (int)v.size();
 			ncm = std::max(ncm, (int)v.size());
 		}
-		if (ncm > A3_THREADS || ncm >= 255)
+		if (ncm > A3_THREADS || ncm >= 255) {
+			free_layout3(c);
 			return MC_OK;	/* more allele columns in a tile than lanes */
+		}
 		/* most frequent allele first; the lanes per column are chosen per
 		 * tile by k3_build_csc */
 		std::vector<unsigned short> colinfo((size_t)n_ltiles * ncm, 0);
@@ -604,8 +622,10 @@ static int make_plan3(mc_ctx *c)
 	const int PR = (max_tile_rows + 1) & ~1;
 	const size_t fixed = a3_smem_bytes(KP, true, 0, PR, ncolmax, cap) + 64;
 	const size_t smem_cap = (size_t)(228 * 1024) / A3_CTAS_PER_SM - 1024 - 64;
-	if (fixed + (size_t)max_tile_rows * KR * sizeof(double) > smem_cap)
+	if (fixed + (size_t)max_tile_rows * KR * sizeof(double) > smem_cap) {
+		free_layout3(c);	/* the one-pass kernel takes over: drop the multi-GB lists */
 		return MC_OK;
+	}
 	const long long budget_rows = (long long)((smem_cap - fixed) / (KR * sizeof(double)));
 	const long long total_rows = c->T;
 	const long long sms = (long long)c->num_sms * A3_CTAS_PER_SM;
@@ -749,20 +769,188 @@ static int launch_admix3(mc_ctx *c, int ll_only, const double *p, const double *
 	return MC_OK;
 }
 
+
+/* ------------------------------------------------ dense DMMA plan (mc_dense) */
+
+/* returns MC_OK with c->use_dn set when the kernels of mc_dense.cuh apply:
+ * no allele code above 1 anywhere (every locus has at most two observed
+ * alleles; a third slot can only be the phantom slot of read_file.c:527-530,
+ * which no copy carries), K <= 16, ploidy <= 15 */
+static int make_plan_dense(mc_ctx *c)
+{
+	c->use_dn = false;
+	if (c->opt_kernel != MC_KERNEL_AUTO && c->opt_kernel != MC_KERNEL_DENSE)
+		return MC_OK;
+	if (c->K > 16 || c->P > 15 || c->T < 1)
+		return MC_OK;
+	for (int l = 0; l < c->L; l++)
+		if (c->J[l] > 3)
+			return MC_OK;
+	if (c->dn_maxcode < 0) {
+		unsigned *d_m = nullptr, m = 0;
+		CK(MC_DEV_MALLOC(&d_m, sizeof(unsigned)));
+		CK(cudaMemsetAsync(d_m, 0, sizeof(unsigned), c->stream));
+		const long long n = c->I * (long long)c->L * c->P;
+		k_dense_maxcode<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->d_nat, n, d_m);
+		LAUNCH_CHECK("k_dense_maxcode");
+		CK(cudaMemcpyAsync(&m, d_m, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		cudaFree(d_m);
+		c->dn_maxcode = (int)m;
+	}
+	if (c->dn_maxcode > 1)
+		return MC_OK;
+
+	const int NB = c->K <= 8 ? 1 : 2;
+	const long long n_itiles = (c->I + DN_IT - 1) / DN_IT;
+	const int n_ltiles = (c->L + DN_TL - 1) / DN_TL;
+	if (n_itiles * n_ltiles > 0x7fffffffLL)
+		return MC_OK;
+	if (!c->layout_dn) {
+		CK(MC_DEV_MALLOC(&c->d_dn_cnt, (size_t)n_itiles * n_ltiles * DN_IT * 16));
+		k_dense_counts<<<grid_for(c, n_itiles * n_ltiles * DN_IT, 256), 256, 0, c->stream>>>(
+			c->d_nat, c->d_dn_cnt, c->I, c->L, c->P, (int)n_itiles, n_ltiles);
+		LAUNCH_CHECK("k_dense_counts");
+		c->layout_dn = true;
+	}
+	/* shared memory: fixed part, the rest holds the chunk's allele sums */
+	const size_t fixed = dn_smem_bytes(NB, DN_ADMIX_EM, 0) + 64;
+	const size_t smem_cap = (size_t)(228 * 1024) / DN_CTAS_PER_SM - 1024 - 64;
+	const long long budget = (long long)((smem_cap - fixed) / ((size_t)NB * 256 * sizeof(double)));
+	if (budget < 1)
+		return MC_OK;
+	const long long sms = (long long)c->num_sms * DN_CTAS_PER_SM;
+	const int nl_min = (int)((n_ltiles + budget - 1) / budget);
+	int best_nl = nl_min, best_ni = 1;
+	{
+		double best_eff = -1;
+		const int nl_max = (int)std::min<long long>(n_ltiles, std::max<long long>(nl_min, 2 * sms));
+		for (int nl = nl_min; nl <= nl_max; nl++) {
+			const long long cmax = std::min<long long>(n_itiles,
+				std::max<long long>(1, (4 * sms + nl - 1) / nl));
+			for (long long ni = 1; ni <= cmax; ni++) {
+				const long long units = ni * nl;
+				const long long rounds = (units + sms - 1) / sms;
+				/* ragged chunks: the longest unit sets the round's length */
+				const double lmax = (double)((n_ltiles + nl - 1) / nl) * nl / n_ltiles;
+				const double imax = (double)((n_itiles + ni - 1) / ni) * ni / n_itiles;
+				const double eff = (double)units / (double)(rounds * sms) / (lmax * imax)
+					- 0.02 * (double)nl / (double)std::max(nl_min, 1)
+					- 0.004 * (double)ni - 0.002 * (double)rounds;
+				if (eff > best_eff + 1e-12) {
+					best_eff = eff;
+					best_nl = nl;
+					best_ni = (int)ni;
+				}
+			}
+		}
+	}
+	std::vector<int> lc_first((size_t)best_nl + 1);
+	int max_chunk_tiles = 1;
+	for (int x = 0; x <= best_nl; x++)
+		lc_first[x] = (int)((long long)n_ltiles * x / best_nl);
+	for (int x = 0; x < best_nl; x++)
+		max_chunk_tiles = std::max(max_chunk_tiles, lc_first[x + 1] - lc_first[x]);
+
+	DenseArgs &a = c->dn;
+	memset(&a, 0, sizeof a);
+	a.K = c->K; a.L = c->L;
+	a.n_itiles = (int)n_itiles; a.n_ltiles = n_ltiles;
+	a.n_lchunks = best_nl; a.n_ichunks = best_ni; a.n_units = best_nl * best_ni;
+	a.max_chunk_tiles = max_chunk_tiles;
+	a.I = c->I; a.Ipad = n_itiles * DN_IT; a.T = c->T;
+	c->dn_NB = NB;
+	c->dn_pbits = c->P <= 1 ? 1 : c->P <= 3 ? 2 : c->P <= 7 ? 3 : 4;
+	c->grid_dn = (int)std::min<long long>(a.n_units, sms);
+	int rc;
+	if ((rc = upload(c, c->d_dn_lc_first, lc_first))) return rc;
+	CK(MC_DEV_MALLOC(&c->d_dn_pd, sizeof(double) * (size_t)n_ltiles * DN_TL * dn_pl(NB)));
+	a.lc_first = c->d_dn_lc_first; a.off = c->d_off; a.J = c->d_J;
+	a.cnt = c->d_dn_cnt; a.pd = c->d_dn_pd;
+	if ((rc = alloc_outputs(c, best_nl, best_ni, a.n_units, a.Ipad))) return rc;
+	a.Apart = c->d_Apart; a.Npart = c->d_Npart; a.llpart = c->d_llpart;
+	CK(cudaStreamSynchronize(c->stream));
+	c->use_dn = true;
+	return MC_OK;
+}
+
+typedef void (*dense_fn)(const DenseArgs);
+
+template <int NB, int MODE> static dense_fn pick_dn_bits(int pbits)
+{
+	switch (pbits) {
+	case 1: return dense_kernel<NB, 1, MODE>;
+	case 2: return dense_kernel<NB, 2, MODE>;
+	case 3: return dense_kernel<NB, 3, MODE>;
+	case 4: return dense_kernel<NB, 4, MODE>;
+	}
+	return nullptr;
+}
+
+static dense_fn pick_dn(int NB, int pbits, int mode)
+{
+	switch (mode) {
+	case DN_ADMIX_EM:
+		return NB == 1 ? pick_dn_bits<1, DN_ADMIX_EM>(pbits) : pick_dn_bits<2, DN_ADMIX_EM>(pbits);
+	case DN_ADMIX_LL:
+		return NB == 1 ? pick_dn_bits<1, DN_ADMIX_LL>(pbits) : pick_dn_bits<2, DN_ADMIX_LL>(pbits);
+	case DN_MIX_E:
+		return NB == 1 ? dense_kernel<1, 1, DN_MIX_E> : dense_kernel<2, 1, DN_MIX_E>;
+	case DN_MIX_M:
+		return NB == 1 ? dense_kernel<1, 1, DN_MIX_M> : dense_kernel<2, 1, DN_MIX_M>;
+	}
+	return nullptr;
+}
+
+/* `ptab`: the [K][T] table the dense p fragments are built from (p, or log p
+ * for the mixture E pass; nullptr for the mixture M pass) */
+static int launch_dense(mc_ctx *c, int mode, const double *ptab, const double *p,
+	const double *eta, long long eta_stride)
+{
+	dense_fn fn = pick_dn(c->dn_NB, c->dn_pbits, mode);
+	if (!fn)
+		return fail(c, MC_ERR_UNSUPPORTED, "no dense kernel for K=%d P=%d", c->K, c->P);
+	DenseArgs a = c->dn;
+	a.p = p; a.eta = eta; a.eta_stride = eta_stride;
+	if (ptab) {
+		const int K8 = 8 * c->dn_NB, npad = a.n_ltiles * DN_TL;
+		k_dense_p<<<grid_for(c, (long long)npad * K8 * 2, 256), 256, 0, c->stream>>>(ptab,
+			c->d_dn_pd, c->d_off, c->d_J, c->K, c->L, c->T, npad, dn_pl(c->dn_NB), K8);
+		LAUNCH_CHECK("k_dense_p");
+	}
+	const size_t smem = dn_smem_bytes(c->dn_NB, mode, a.max_chunk_tiles);
+	CK(cudaFuncSetAttribute((const void *)fn,
+		cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	if (c->profile) {
+		CK(cudaEventCreate(&e0));
+		CK(cudaEventCreate(&e1));
+		CK(cudaEventRecord(e0, c->stream));
+	}
+	fn<<<c->grid_dn, DN_THREADS, smem, c->stream>>>(a);
+	LAUNCH_CHECK("dense_kernel");
+	if (c->profile) {
+		CK(cudaEventRecord(e1, c->stream));
+		c->prof_events.push_back({ e0, e1 });
+	}
+	return MC_OK;
+}
+
 static int make_plan(mc_ctx *c)
 {
 	const int K = c->K;
+	{
+		const int rcd = make_plan_dense(c);
+		if (rcd || c->use_dn)
+			return rcd;
+	}
 	{
 		const int rc3 = make_plan3(c);
 		if (rc3 || c->use3)
 			return rc3;
 	}
-	int ks = 1, kh_max = KH_MAX;
-	if (const char *ev = getenv("MC_KH_MAX")) {	/* tuning knob */
-		const int v = atoi(ev);
-		if (v >= 1 && v <= KH_MAX)
-			kh_max = v;
-	}
+	int ks = 1;
+	const int kh_max = KH_MAX;
 	while ((K + ks - 1) / ks > kh_max && ks < 32)
 		ks <<= 1;
 	const int KH = (K + ks - 1) / ks;
@@ -1055,6 +1243,17 @@ static inline double *xb_N(mc_ctx *c) { return c->d_xbuf; }
 static inline double *xb_ll(mc_ctx *c) { return c->d_xbuf + c->np; }
 static inline double *xb_S(mc_ctx *c) { return c->d_xbuf + c->np + 1; }
 
+/* mixture E-step tail over the chunk partial sums in Apart */
+static int mix_tail(mc_ctx *c, const double *eta, double *vik, int ll_only)
+{
+	const long long blocks = (c->I + MT_ROWS - 1) / MT_ROWS;
+	k_mix_tail<<<(unsigned)std::min<long long>(blocks, (long long)c->num_sms * 16), 256,
+		sizeof(double) * MT_ROWS * c->K, c->stream>>>(c->d_Apart, c->act_tiles,
+		c->act_Ipad, c->I, c->K, eta, vik, c->d_lli, ll_only);
+	LAUNCH_CHECK("k_mix_tail");
+	return MC_OK;
+}
+
 extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 {
 	NEED_MODEL();
@@ -1063,7 +1262,10 @@ extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 	const int K = c->K;
 	int rc;
 	if (c->admixture) {
-		rc = c->use3
+		rc = c->use_dn
+			? launch_dense(c, DN_ADMIX_EM, c->d_p[from], c->d_p[from], c->d_eta[from],
+				c->per_indiv ? K : 0)
+			: c->use3
 			? launch_admix3(c, 0, c->d_p[from], c->d_eta[from], c->per_indiv ? K : 0)
 			: launch_tile(c, MODE_ADMIX_EM, c->d_p[from], c->d_eta[from],
 				c->per_indiv ? K : 0);
@@ -1088,13 +1290,12 @@ extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 		k_log_table<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_p[from],
 			c->d_logp, c->np, 1);
 		LAUNCH_CHECK("k_log_table");
-		if ((rc = launch_tile(c, MODE_MIX_E, c->d_logp, nullptr, 0))) return rc;
-		k_mix_post<<<grid_for(c, c->I, 128), 128, 0, c->stream>>>(c->d_Apart,
-			c->act_tiles, c->act_Ipad, c->I, K, c->d_eta[from], c->d_post,
-			c->d_lli, 0);
-		LAUNCH_CHECK("k_mix_post");
+		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_E, c->d_logp, nullptr, nullptr, 0)
+			: launch_tile(c, MODE_MIX_E, c->d_logp, nullptr, 0))) return rc;
+		if ((rc = mix_tail(c, c->d_eta[from], c->d_post, 0))) return rc;
 		if ((rc = reduce_vector(c, c->d_lli, c->I, xb_ll(c)))) return rc;
-		if ((rc = launch_tile(c, MODE_MIX_M, nullptr, c->d_post, K))) return rc;
+		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_M, nullptr, nullptr, c->d_post, K)
+			: launch_tile(c, MODE_MIX_M, nullptr, c->d_post, K))) return rc;
 		k_sum_chunks<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_Npart,
 			c->act_chunks, c->np, 0.0, xb_N(c));
 		LAUNCH_CHECK("k_sum_chunks");
@@ -1276,7 +1477,10 @@ extern "C" int mc_loglik(mc_ctx *c, int slot, double *ll)
 	CHECK_SLOT(slot);
 	int rc;
 	if (c->admixture) {
-		rc = c->use3
+		rc = c->use_dn
+			? launch_dense(c, DN_ADMIX_LL, c->d_p[slot], c->d_p[slot], c->d_eta[slot],
+				c->per_indiv ? c->K : 0)
+			: c->use3
 			? launch_admix3(c, 1, c->d_p[slot], c->d_eta[slot], c->per_indiv ? c->K : 0)
 			: launch_tile(c, MODE_ADMIX_LL, c->d_p[slot], c->d_eta[slot],
 				c->per_indiv ? c->K : 0);
@@ -1286,13 +1490,11 @@ extern "C" int mc_loglik(mc_ctx *c, int slot, double *ll)
 		k_log_table<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_p[slot],
 			c->d_logp, c->np, 0);
 		LAUNCH_CHECK("k_log_table");
-		if ((rc = launch_tile(c, MODE_MIX_E, c->d_logp, nullptr, 0))) return rc;
-		/* the posterior of the last E-step must survive: use the per-
-		 * individual ll buffer only, rows go through Apart in place */
-		k_mix_post<<<grid_for(c, c->I, 128), 128, 0, c->stream>>>(c->d_Apart,
-			c->act_tiles, c->act_Ipad, c->I, c->K, c->d_eta[slot],
-			c->d_Apart, c->d_lli, 1);
-		LAUNCH_CHECK("k_mix_post");
+		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_E, c->d_logp, nullptr, nullptr, 0)
+			: launch_tile(c, MODE_MIX_E, c->d_logp, nullptr, 0))) return rc;
+		/* the posterior of the last E-step must survive: only the per-
+		 * individual ll buffer is written */
+		if ((rc = mix_tail(c, c->d_eta[slot], nullptr, 1))) return rc;
 		if ((rc = reduce_vector(c, c->d_lli, c->I, xb_ll(c)))) return rc;
 	}
 	if (ll) {
@@ -1505,6 +1707,16 @@ extern "C" int mc_get_plan(const mc_ctx *c, mc_plan_info *o)
 		o->n_units = c->a3.n_units; o->grid = c->grid3; o->block = A3_THREADS;
 		o->indiv_per_block = A3_IT; o->smem_bytes = (int64_t)c->smem3;
 	}
+	if (c->use_dn) {	/* dense DMMA kernels: tiles are locus chunks */
+		o->two_pass = 3;
+		o->k_split = 1; o->k_per_lane = 8 * c->dn_NB;
+		o->loci_per_warp = DN_TL; o->warps = DN_THREADS / 32; o->groups = 1;
+		o->n_tiles = c->dn.n_lchunks; o->n_chunks = c->dn.n_ichunks;
+		o->n_units = c->dn.n_units; o->grid = c->grid_dn; o->block = DN_THREADS;
+		o->indiv_per_block = DN_IT;
+		o->smem_bytes = (int64_t)dn_smem_bytes(c->dn_NB,
+			c->admixture ? DN_ADMIX_EM : DN_MIX_M, c->dn.max_chunk_tiles);
+	}
 	const int64_t g = c->I * (int64_t)c->L * c->P;
 	o->algorithmic_bytes_em = g + 16 * c->I * (int64_t)c->K + 16 * (int64_t)c->K * c->T;
 	o->algorithmic_bytes_ll = g + 8 * c->I * (int64_t)c->K + 8 * (int64_t)c->K * c->T;
@@ -1541,4 +1753,21 @@ extern "C" int mc_profile_read(mc_ctx *c, int64_t *n, double *ms)
 	c->prof_n = 0;
 	c->prof_ms = 0;
 	return MC_OK;
+}
+
+extern "C" int mc_set_option(mc_ctx *c, int option, int value)
+{
+	if (!c)
+		return MC_ERR_ARG;
+	switch (option) {
+	case MC_OPT_KERNEL:
+		if (value < MC_KERNEL_AUTO || value > MC_KERNEL_DENSE)
+			return fail(c, MC_ERR_ARG, "mc_set_option: kernel %d out of range", value);
+		c->opt_kernel = value;
+		return MC_OK;
+	case MC_OPT_TIMING:
+		c->opt_timing = value != 0;
+		return MC_OK;
+	}
+	return fail(c, MC_ERR_ARG, "mc_set_option: unknown option %d", option);
 }

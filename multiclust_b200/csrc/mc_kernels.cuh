@@ -623,51 +623,6 @@ __global__ void k_admix_eta(const double *Apart, int n_tiles, long long Ipad,
 	}
 }
 
-/* mixture E-step tail (em_alg.c:828-882) / logL_mixture tail
- * (log_likelihood.c:203-228): a_ik = log eta_k + sum of log p               */
-__global__ void k_mix_post(const double *Apart, int n_tiles, long long Ipad,
-	long long I, int K, const double *eta, double *vik, double *ll_i,
-	int ll_only)
-{
-	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < I;
-		i += (long long)gridDim.x * blockDim.x) {
-		double mx = -INFINITY;
-		double *v = vik + (size_t)i * K;	/* scratch row when ll_only */
-		for (int k = 0; k < K; k++) {
-			double acc = 0.0;
-			for (int t = 0; t < n_tiles; t++)
-				acc += Apart[((size_t)t * Ipad + i) * K + k];
-			acc += log(eta[k]);
-			v[k] = acc;
-			if (acc > mx)
-				mx = acc;
-		}
-		if (!ll_only) {
-			double s = 0.0;
-			for (int k = 0; k < K; k++) {
-				v[k] = exp(v[k] - mx);
-				s += v[k];
-			}
-			for (int k = 0; k < K; k++)
-				v[k] /= s;
-			ll_i[i] = log(s) + mx;
-		} else {
-			double te = exp(mx), scale = 0.0, s = 0.0;
-			if (te == 0.0 || te == HUGE_VAL) {
-				scale = (te == HUGE_VAL) ? mx : -mx;
-				do {
-					scale *= 0.5;
-					te = exp(scale);
-				} while (te == HUGE_VAL);
-				scale = mx - scale;
-			}
-			for (int k = 0; k < K; k++)
-				s += exp(v[k] - scale);
-			ll_i[i] = log(s) + scale;
-		}
-	}
-}
-
 /* ------------------------------------------------------------------ */
 /* deterministic reductions: fixed grid, fixed tree                      */
 

@@ -240,3 +240,75 @@ def test_synthetic_generator_matches_host(orc, ctx, tmp_path):
     ctx.set_data_synth(I, L, sp)
     assert np.array_equal(ctx.get_J(), d["J"])
     assert np.array_equal(ctx.get_codes(), d["codes"])
+
+
+# ---- the dense DMMA kernels (mc_dense.cuh) and the planner's kernel choice ----
+
+DENSE_SHAPES = [
+    # I, L, K, jmax, miss_bp, P: biallelic everywhere
+    (45, 70, 8, 2, 0, 4),          # config-5 shaped
+    (300, 37, 5, 2, 300, 2),       # more than one tile of individuals, ragged locus tile, missing
+    (70, 530, 3, 2, 100, 1),       # haploid, many locus tiles
+    (64, 48, 12, 2, 200, 3),       # K > 8: two blocks of clusters, odd ploidy
+    (33, 40, 8, 2, 500, 6),        # hexaploid (3-bit counts)
+]
+
+
+@pytest.mark.parametrize("shape", DENSE_SHAPES)
+@pytest.mark.parametrize("admixture", [1, 0])
+def test_dense_kernels(orc, tmp_path, shape, admixture):
+    from multiclust_b200 import Context
+    c = Context(0)
+    try:
+        c.set_option(c.OPT_KERNEL, c.KERNEL_DENSE)
+        d, fit, eta, p = setup_pair(orc, c, tmp_path, shape, admixture=admixture)
+        assert c.plan()["two_pass"] == 3
+        ll_o = fit.log_likelihood(0)
+        assert abs(c.loglik(0) - ll_o) <= 1e-12 * abs(ll_o)
+        check_step(orc, c, fit, 0, 1)
+        check_step(orc, c, fit, 1, 1)
+        post = c.posterior()
+        assert abs(c.loglik(1) - fit.log_likelihood(1)) <= 1e-12 * abs(ll_o)
+        assert np.array_equal(post, c.posterior())
+    finally:
+        c.close()
+
+
+def test_dense_pooled_eta(orc, tmp_path):
+    from multiclust_b200 import Context
+    c = Context(0)
+    try:
+        d, fit, eta, p = setup_pair(orc, c, tmp_path, DENSE_SHAPES[1], admixture=1,
+                                    eta_constrained=1)
+        assert c.plan()["two_pass"] == 3
+        check_step(orc, c, fit, 0, 0)
+        check_step(orc, c, fit, 0, 1)
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("kernel,two_pass", [(1, 0), (2, 2), (3, 3), (0, 3)])
+def test_kernel_option(orc, tmp_path, kernel, two_pass):
+    """mc_set_option(MC_OPT_KERNEL): every kernel family gives the oracle's step
+    on biallelic data; the planner reports which one ran"""
+    from multiclust_b200 import Context
+    c = Context(0)
+    try:
+        c.set_option(c.OPT_KERNEL, kernel)
+        d, fit, eta, p = setup_pair(orc, c, tmp_path, DENSE_SHAPES[0], admixture=1)
+        assert c.plan()["two_pass"] == two_pass
+        check_step(orc, c, fit, 0, 1)
+    finally:
+        c.close()
+
+
+def test_multiallelic_data_never_dense(orc, tmp_path):
+    from multiclust_b200 import Context
+    c = Context(0)
+    try:
+        c.set_option(c.OPT_KERNEL, c.KERNEL_DENSE)
+        d, fit, eta, p = setup_pair(orc, c, tmp_path, SHAPES[0], admixture=1)
+        assert c.plan()["two_pass"] == 0      # falls back to the one-pass kernel
+        check_step(orc, c, fit, 0, 1)
+    finally:
+        c.close()
