@@ -24,10 +24,13 @@ typedef struct mc_comm mc_comm;
  * distinct devices and hold models of identical K and T */
 int mc_comm_create(mc_comm **comm, mc_ctx **ctxs, int n);
 void mc_comm_destroy(mc_comm *comm);
-/* all-gather of every context's exchange buffer over NVLink (ncclAllGather in
- * one group call, each on its context's stream) followed by the rank-order
- * sum of mc_exchange_sum on every context: afterwards all contexts hold
- * bit-identical totals.  Asynchronous with respect to the host. */
+/* Sum of every context's exchange buffer over NVLink as a deterministic
+ * reduce-scatter + all-gather: grouped ncclSend / ncclRecv move slice j of
+ * every buffer to device j, mc_exchange_sum_slice adds the copies in rank
+ * order, one in-place ncclAllGather returns the totals -- afterwards all
+ * contexts hold bit-identical totals, and the bytes per device do not grow
+ * with the number of devices.  Every call runs on its context's stream;
+ * asynchronous with respect to the host. */
 int mc_comm_exchange(mc_comm *comm);
 const char *mc_comm_last_error(const mc_comm *comm);
 

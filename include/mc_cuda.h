@@ -200,7 +200,10 @@ int mc_copy_slot(mc_ctx *ctx, int dst, int src);
  * mechanism; nothing to do for a single rank) and then calls
  * mc_em_step_finish, which normalises and projects p (and the pooled eta of
  * the mixture / -c models) into slot `to` on every rank identically.
- * mc_em_step == mc_em_step_local + mc_em_step_finish. */
+ * mc_em_step == mc_em_step_local + mc_em_step_finish.
+ * mc_em_step_local leaves the eta side of an admixture step (which needs no
+ * remote data) running on a second stream beside the caller's exchange;
+ * mc_em_step_finish joins it, so the pair must be called together. */
 int mc_em_step_local(mc_ctx *ctx, int from, int to);
 int mc_exchange_buffer(mc_ctx *ctx, void **dev_ptr, size_t *n_doubles);
 int mc_em_step_finish(mc_ctx *ctx, int to, double *ll);
@@ -210,6 +213,15 @@ int mc_em_step_finish(mc_ctx *ctx, int to, double *ll);
  * context's exchange buffer, so every rank computes bit-identical sums
  * whatever algorithm the collective library picked. */
 int mc_exchange_sum(mc_ctx *ctx, const void *gathered, int n_ranks);
+/* The same sum as a reduce-scatter + all-gather, whose traffic per rank does
+ * not grow with the number of ranks.  The exchange buffer has room for 64
+ * doubles beyond n_doubles (zero), so it can be cut into n_ranks <= 64 equal
+ * slices of m = ceil(n_doubles / n_ranks): every rank sends slice j to rank j
+ * (all-to-all), rank r adds the n_ranks copies of slice r it received (`parts`,
+ * DEVICE memory, [n_ranks][count], rank order) into its own buffer at `first`
+ * = r * m with this call, and the slices are all-gathered back in place. */
+int mc_exchange_sum_slice(mc_ctx *ctx, const void *parts, int n_ranks,
+	int64_t first, int64_t count);
 
 /* ---- introspection for bench / profiles --------------------------------- */
 

@@ -19,7 +19,7 @@ SYMBOLS = [
     "mc_get_posterior", "mc_partition", "mc_delta", "mc_step_dots",
     "mc_qn_dots", "mc_accel_update", "mc_qn_update", "mc_project",
     "mc_copy_slot", "mc_em_step_local", "mc_exchange_buffer",
-    "mc_em_step_finish", "mc_exchange_sum", "mc_get_plan", "mc_launch_count",
+    "mc_em_step_finish", "mc_exchange_sum", "mc_exchange_sum_slice", "mc_get_plan", "mc_launch_count",
     "mc_profile_enable", "mc_profile_read", "mc_set_option",
 ]
 
@@ -111,6 +111,7 @@ def load_library():
     L.mc_exchange_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mc_em_step_finish.argtypes = [vp, C.c_int, dp]
     L.mc_exchange_sum.argtypes = [vp, vp, C.c_int]
+    L.mc_exchange_sum_slice.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64]
     L.mc_get_plan.argtypes = [vp, C.POINTER(PlanInfo)]
     L.mc_launch_count.restype = C.c_int64
     L.mc_launch_count.argtypes = [vp]
@@ -251,13 +252,17 @@ class Context:
         return ll.value
 
     # the shard interface of multiclust_b200/sharding.py
+    def exchange_len(self):
+        return self.exchange_buffer()[1]
+
     def exchange_tensor(self):
-        """the exchange buffer viewed as a torch CUDA tensor (no copy)"""
+        """the exchange buffer (logical length + 64 doubles of zero padding)
+        viewed as a torch CUDA tensor (no copy)"""
         import torch
         ptr, n = self.exchange_buffer()
         if getattr(self, "_xt", None) is None or self._xt_key != (ptr, n):
             class _Arr:
-                __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8",
+                __cuda_array_interface__ = {"shape": (n + 64,), "typestr": "<f8",
                                             "data": (ptr, False), "version": 3}
             self._xt = torch.as_tensor(_Arr(), device="cuda")
             self._xt_key = (ptr, n)
@@ -265,6 +270,10 @@ class Context:
 
     def sum_gathered(self, gathered, world):
         self.exchange_sum(gathered.data_ptr(), world)
+
+    def sum_slices(self, parts, world, first, count):
+        self._ck(self.lib.mc_exchange_sum_slice(self.h, C.c_void_p(parts.data_ptr()), world,
+                                                first, count), "mc_exchange_sum_slice")
 
     def exchange_sum(self, gathered_ptr, n_ranks):
         self._ck(self.lib.mc_exchange_sum(self.h, C.c_void_p(gathered_ptr), n_ranks),

@@ -62,7 +62,7 @@ extern "C" int mc_comm_create(mc_comm **out, mc_ctx **ctxs, int n)
 	for (int r = 0; r < n; r++) {
 		double *g = nullptr;
 		cudaSetDevice(c->dev[r]);
-		if (cudaMalloc(&g, sizeof(double) * c->n_doubles * n) != cudaSuccess) {
+		if (cudaMalloc(&g, sizeof(double) * (c->n_doubles * n + 64)) != cudaSuccess) {
 			g_err = "mc_comm_create: cudaMalloc failed";
 			mc_comm_destroy(c);
 			return MC_ERR_NOMEM;
@@ -87,25 +87,80 @@ extern "C" void mc_comm_destroy(mc_comm *c)
 	delete c;
 }
 
+/* every NCCL call of one grouped operation; the group is always closed, the
+ * first error is the one reported */
+#define NCCL_IN_GROUP(call) do { ncclResult_t r_ = (call); \
+	if (r_ != ncclSuccess && first == ncclSuccess) first = r_; } while (0)
+
 extern "C" int mc_comm_exchange(mc_comm *c)
 {
 	if (!c)
 		return MC_ERR_ARG;
-	ncclResult_t nr = ncclGroupStart();
-	for (int r = 0; r < c->n && nr == ncclSuccess; r++) {
-		void *send = nullptr;
-		mc_exchange_buffer(c->ctx[r], &send, nullptr);
-		nr = ncclAllGather(send, c->gathered[r], c->n_doubles, ncclDouble,
-			c->nccl[r], (cudaStream_t)mc_ctx_stream(c->ctx[r]));
+	const int n = c->n;
+	std::vector<double *> x((size_t)n);
+	for (int r = 0; r < n; r++) {
+		void *ptr = nullptr;
+		const int rc = mc_exchange_buffer(c->ctx[r], &ptr, nullptr);
+		if (rc != MC_OK) {
+			c->err = mc_last_error(c->ctx[r]);
+			return rc;
+		}
+		x[r] = static_cast<double *>(ptr);
 	}
-	if (nr == ncclSuccess)
-		nr = ncclGroupEnd();
-	if (nr != ncclSuccess) {
-		c->err = std::string("ncclAllGather failed: ") + ncclGetErrorString(nr);
+	ncclResult_t first = ncclSuccess;
+	if (n <= 64) {
+		/* reduce-scatter + all-gather in rank order (include/mc_cuda.h,
+		 * mc_exchange_sum_slice): slice j of every buffer goes to device j */
+		const size_t m = (c->n_doubles + n - 1) / n;
+		NCCL_IN_GROUP(ncclGroupStart());
+		for (int r = 0; r < n; r++) {
+			cudaSetDevice(c->dev[r]);
+			cudaStream_t st = (cudaStream_t)mc_ctx_stream(c->ctx[r]);
+			for (int j = 0; j < n; j++) {
+				NCCL_IN_GROUP(ncclSend(x[r] + j * m, m, ncclDouble, j, c->nccl[r], st));
+				NCCL_IN_GROUP(ncclRecv(c->gathered[r] + j * m, m, ncclDouble, j, c->nccl[r], st));
+			}
+		}
+		NCCL_IN_GROUP(ncclGroupEnd());
+		if (first != ncclSuccess) {
+			c->err = std::string("NCCL all-to-all failed: ") + ncclGetErrorString(first);
+			return MC_ERR_CUDA;
+		}
+		for (int r = 0; r < n; r++) {
+			const int rc = mc_exchange_sum_slice(c->ctx[r], c->gathered[r], n,
+				(int64_t)(r * m), (int64_t)m);
+			if (rc) {
+				c->err = mc_last_error(c->ctx[r]);
+				return rc;
+			}
+		}
+		NCCL_IN_GROUP(ncclGroupStart());
+		for (int r = 0; r < n; r++) {
+			cudaSetDevice(c->dev[r]);
+			/* in place: the send buffer is the rank's own slice of the result */
+			NCCL_IN_GROUP(ncclAllGather(x[r] + r * m, x[r], m, ncclDouble, c->nccl[r],
+				(cudaStream_t)mc_ctx_stream(c->ctx[r])));
+		}
+		NCCL_IN_GROUP(ncclGroupEnd());
+		if (first != ncclSuccess) {
+			c->err = std::string("ncclAllGather failed: ") + ncclGetErrorString(first);
+			return MC_ERR_CUDA;
+		}
+		return MC_OK;
+	}
+	NCCL_IN_GROUP(ncclGroupStart());
+	for (int r = 0; r < n; r++) {
+		cudaSetDevice(c->dev[r]);
+		NCCL_IN_GROUP(ncclAllGather(x[r], c->gathered[r], c->n_doubles, ncclDouble,
+			c->nccl[r], (cudaStream_t)mc_ctx_stream(c->ctx[r])));
+	}
+	NCCL_IN_GROUP(ncclGroupEnd());
+	if (first != ncclSuccess) {
+		c->err = std::string("ncclAllGather failed: ") + ncclGetErrorString(first);
 		return MC_ERR_CUDA;
 	}
-	for (int r = 0; r < c->n; r++) {
-		const int rc = mc_exchange_sum(c->ctx[r], c->gathered[r], c->n);
+	for (int r = 0; r < n; r++) {
+		const int rc = mc_exchange_sum(c->ctx[r], c->gathered[r], n);
 		if (rc) {
 			c->err = mc_last_error(c->ctx[r]);
 			return rc;

@@ -30,6 +30,11 @@ static std::string g_create_error;
 struct mc_ctx {
 	int device = 0;
 	cudaStream_t own_stream = nullptr, stream = nullptr;
+	/* the eta side of an admixture step runs on a second stream, concurrently
+	 * with the caller's exchange of the allele sums (mc_em_step_local) */
+	cudaStream_t aux = nullptr;
+	cudaEvent_t ev_main = nullptr, ev_aux = nullptr;
+	bool aux_pending = false;
 	std::string err;
 	int64_t launches = 0;
 	int num_sms = 148;
@@ -190,6 +195,12 @@ extern "C" int mc_create(mc_ctx **out, int device)
 			device, cudaGetErrorString(e));
 	}
 	c->stream = c->own_stream;
+	if (cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess
+		|| cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming) != cudaSuccess
+		|| cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming) != cudaSuccess) {
+		delete c;
+		return fail(nullptr, MC_ERR_CUDA, "cannot create the auxiliary stream");
+	}
 	cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
 	{	/* keep freed device memory in the pool (see mc_dev_malloc) */
 		cudaMemPool_t pool;
@@ -270,6 +281,10 @@ extern "C" void mc_destroy(mc_ctx *c)
 		cudaEventDestroy(ev.first);
 		cudaEventDestroy(ev.second);
 	}
+	cudaStreamSynchronize(c->aux);
+	cudaEventDestroy(c->ev_main);
+	cudaEventDestroy(c->ev_aux);
+	cudaStreamDestroy(c->aux);
 	cudaStreamDestroy(c->own_stream);
 	delete c;
 }
@@ -508,10 +523,12 @@ static int alloc_outputs(mc_ctx *c, int n_tiles, int n_chunks, int n_units, long
 	CK(MC_DEV_MALLOC(&c->d_Apart, sizeof(double) * (size_t)n_tiles * Ipad * K));
 	CK(MC_DEV_MALLOC(&c->d_Npart, sizeof(double) * nN));
 	CK(MC_DEV_MALLOC(&c->d_llpart, sizeof(double) * (size_t)n_units));
-	CK(MC_DEV_MALLOC(&c->d_xbuf, sizeof(double) * ((size_t)K * c->T + 1 + K)));
+	/* + 64: room to cut the buffer into equal slices for up to 64 ranks */
+	const size_t xcap = (size_t)K * c->T + 1 + K + 64;
+	CK(MC_DEV_MALLOC(&c->d_xbuf, sizeof(double) * xcap));
 	CK(MC_DEV_MALLOC(&c->d_red, sizeof(double) * (size_t)RED_BLOCKS * 8));
 	CK(cudaMemsetAsync(c->d_Npart, 0, sizeof(double) * nN, c->stream));
-	CK(cudaMemsetAsync(c->d_xbuf, 0, sizeof(double) * ((size_t)K * c->T + 1 + K), c->stream));
+	CK(cudaMemsetAsync(c->d_xbuf, 0, sizeof(double) * xcap, c->stream));
 	return MC_OK;
 }
 
@@ -1243,6 +1260,16 @@ static inline double *xb_N(mc_ctx *c) { return c->d_xbuf; }
 static inline double *xb_ll(mc_ctx *c) { return c->d_xbuf + c->np; }
 static inline double *xb_S(mc_ctx *c) { return c->d_xbuf + c->np + 1; }
 
+/* the main stream waits for the eta side of the last mc_em_step_local */
+static int join_aux(mc_ctx *c)
+{
+	if (c->aux_pending) {
+		c->aux_pending = false;
+		CK(cudaStreamWaitEvent(c->stream, c->ev_aux, 0));
+	}
+	return MC_OK;
+}
+
 /* mixture E-step tail over the chunk partial sums in Apart */
 static int mix_tail(mc_ctx *c, const double *eta, double *vik, int ll_only)
 {
@@ -1278,14 +1305,27 @@ extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 		 * individuals; the streaming kernel is done with slot `from`, so
 		 * from == to (in-place EM) is safe */
 		const int er = eta_rows(K);
+		/* an individual-sharded fit exchanges the allele sums next; the eta
+		 * side needs no remote data and runs beside the exchange (a pooled
+		 * eta is part of the exchange and stays on the main stream) */
+		cudaStream_t es = c->stream;
+		if (c->per_indiv) {
+			CK(cudaEventRecord(c->ev_main, c->stream));
+			CK(cudaStreamWaitEvent(c->aux, c->ev_main, 0));
+			es = c->aux;
+		}
 		k_admix_eta<<<(unsigned)std::min<long long>((c->I + er - 1) / er,
-			(long long)c->num_sms * 16), 256, sizeof(double) * er * K, c->stream>>>(c->d_Apart,
+			(long long)c->num_sms * 16), 256, sizeof(double) * er * K, es>>>(c->d_Apart,
 			c->act_tiles, c->act_Ipad, c->I, K, c->d_eta[from],
 			c->per_indiv ? K : 0, c->d_eta[to], c->d_post, c->per_indiv,
 			c->do_proj, c->eta_lb, er);
 		LAUNCH_CHECK("k_admix_eta");
-		if (!c->per_indiv)	/* pooled eta: S_k = sum_i D_ik */
+		if (c->per_indiv) {
+			CK(cudaEventRecord(c->ev_aux, c->aux));
+			c->aux_pending = true;
+		} else {	/* pooled eta: S_k = sum_i D_ik */
 			if ((rc = reduce_columns(c, c->d_post, c->I, K, xb_S(c)))) return rc;
+		}
 	} else {
 		k_log_table<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_p[from],
 			c->d_logp, c->np, 1);
@@ -1324,11 +1364,29 @@ extern "C" int mc_exchange_sum(mc_ctx *c, const void *gathered, int n_ranks)
 	return MC_OK;
 }
 
+extern "C" int mc_exchange_sum_slice(mc_ctx *c, const void *parts, int n_ranks,
+	int64_t first, int64_t count)
+{
+	NEED_MODEL();
+	const int64_t cap = c->np + 1 + c->K + 64;
+	if (!parts || n_ranks < 1 || first < 0 || count < 0 || first + count > cap)
+		return fail(c, MC_ERR_ARG, "mc_exchange_sum_slice: bad arguments");
+	if (!count)
+		return MC_OK;
+	k_sum_chunks<<<grid_for(c, count, 256), 256, 0, c->stream>>>(
+		(const double *)parts, n_ranks, count, 0.0, c->d_xbuf + first);
+	LAUNCH_CHECK("k_sum_chunks");
+	return MC_OK;
+}
+
 extern "C" int mc_em_step_finish(mc_ctx *c, int to, double *ll)
 {
 	NEED_MODEL();
 	CHECK_SLOT(to);
 	const int K = c->K;
+	int rcj = join_aux(c);
+	if (rcj)
+		return rcj;
 	if (!c->per_indiv) {
 		k_update_eta_pooled<<<1, 32, 0, c->stream>>>(xb_S(c), c->d_eta[to], K,
 			c->do_proj, c->eta_lb);

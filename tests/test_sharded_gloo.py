@@ -22,12 +22,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 class OracleShard:
     """adapter: the four calls of a shard on top of the CPU oracle"""
 
-    def __init__(self, orc, J, codes, admixture, eta_constrained, K, eta, p):
+    def __init__(self, orc, J, codes, admixture, eta_constrained, K, eta, p, slices=True):
         self.fit = orc.Fit(J, codes, admixture=admixture, eta_constrained=eta_constrained)
         self.fit.alloc(K)
         self.fit.set_params(0, eta, p)
         self.K, self.T = K, self.fit.T
-        self.buf = torch.zeros(K * self.T + 1 + K, dtype=torch.float64)
+        self.n = K * self.T + 1 + K
+        self.buf = torch.zeros(self.n + 64, dtype=torch.float64)     # like mc_exchange_buffer
+        self.slices = slices
 
     def em_step_local(self, frm, to):
         self.fit.set_indices(0, frm, to)
@@ -35,25 +37,40 @@ class OracleShard:
         N, S = self.fit.sums()
         self.buf[:self.K * self.T] = torch.from_numpy(N)
         self.buf[self.K * self.T] = ll
-        self.buf[self.K * self.T + 1:] = torch.from_numpy(S)
+        self.buf[self.K * self.T + 1:self.n] = torch.from_numpy(S)
 
     def exchange_tensor(self):
         return self.buf
 
+    def exchange_len(self):
+        return self.n
+
+    def __getattr__(self, name):
+        # the slice path is offered only when asked for (both paths are tested)
+        if name == "sum_slices" and self.__dict__.get("slices"):
+            return self._sum_slices
+        raise AttributeError(name)
+
+    def _sum_slices(self, parts, world, first, count):
+        total = parts[:count].clone()
+        for r in range(1, world):          # rank order: deterministic
+            total += parts[r * count:(r + 1) * count]
+        self.buf[first:first + count] = total
+
     def sum_gathered(self, gathered, world):
-        n = self.buf.numel()
+        n = self.n
         total = gathered[:n].clone()
         for r in range(1, world):          # rank order: deterministic
             total += gathered[r * n:(r + 1) * n]
-        self.buf.copy_(total)
+        self.buf[:n] = total
 
     def em_step_finish(self, to):
         kt = self.K * self.T
-        self.fit.m_step_from_sums(self.buf[:kt].numpy(), self.buf[kt + 1:].numpy())
+        self.fit.m_step_from_sums(self.buf[:kt].numpy(), self.buf[kt + 1:self.n].numpy())
         return float(self.buf[kt])
 
 
-def _worker(rank, world, port, mcb_path, admixture, eta_constrained, K, out):
+def _worker(rank, world, port, mcb_path, admixture, eta_constrained, K, out, slices=True):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle import orc
@@ -68,7 +85,7 @@ def _worker(rank, world, port, mcb_path, admixture, eta_constrained, K, out):
     lo, hi = shard_bounds(I, world)[rank]
     eta_local = eta.reshape(I, K)[lo:hi].ravel() if per_indiv else eta
     shard = OracleShard(orc, d["J"], d["codes"][lo:hi], admixture, eta_constrained, K,
-                        eta_local, p)
+                        eta_local, p, slices=slices)
     gathered = torch.zeros(world * shard.buf.numel(), dtype=torch.float64)
     lls = []
     for it in range(3):
@@ -87,12 +104,14 @@ def free_port():
     return port
 
 
-@pytest.mark.parametrize("admixture,eta_constrained", [(1, 0), (1, 1), (0, 0)])
-def test_two_rank_step_equals_single(orc, tmp_path, admixture, eta_constrained):
-    K, world = 4, 2
+@pytest.mark.parametrize("admixture,eta_constrained,slices,world",
+                         [(1, 0, True, 2), (1, 1, True, 2), (0, 0, True, 2), (1, 0, False, 2),
+                          (1, 0, True, 3)])
+def test_two_rank_step_equals_single(orc, tmp_path, admixture, eta_constrained, slices, world):
+    K = 4
     d = gen_data(tmp_path, 41, 30, K=3, jmax=6, miss=300, P=2)
     mp.spawn(_worker, args=(world, free_port(), d["mcb_path"], admixture, eta_constrained, K,
-                            str(tmp_path)), nprocs=world, join=True)
+                            str(tmp_path), slices), nprocs=world, join=True)
     # the unsharded oracle
     I = d["I"]
     per_indiv = bool(admixture and not eta_constrained)
