@@ -45,6 +45,15 @@
 #define A3_THREADS 256		/* measured at C3: 256 x 2 CTAs/SM 26.7 ms, 512 x 1 30.3 ms */
 #endif
 #define A3_IT A3_THREADS	/* individuals per tile = pass-1 threads */
+#ifndef A3_NC
+#define A3_NC 16		/* allele copies per individual and tile (8 or 16): pass 1
+				 * runs A3_NC / 8 rounds of 8 copies, pass 2 walks lists of
+				 * A3_IT * A3_NC entries, so the per-tile costs (two barriers,
+				 * the fold, the staging) are paid once per A3_NC copies */
+#endif
+#define A3_PR 192		/* pitch of the k-major p tile in doubles: a compile-time
+				 * constant, so the K loads of a copy share one address
+				 * register (a tile has at most A3_PR allele rows) */
 #ifndef A3_CTAS_PER_SM
 #define A3_CTAS_PER_SM (512 / A3_THREADS)	/* CTAs sharing an SM (and its shared memory) */
 #endif
@@ -54,25 +63,29 @@ struct Admix3Args {
 	int K;
 	int n_itiles, n_ltiles, n_lchunks, n_ichunks, n_units;
 	long long I, Ipad, T;
-	int L, ncolmax, max_chunk_rows, PR;	/* PR: pitch of p_s rows (doubles) */
+	int L, ncolmax, max_chunk_rows;
 	/* per locus tile (static) */
 	const int *lt_ncol;		/* [n_ltiles] real allele columns */
 	const unsigned short *colinfo;	/* [n_ltiles][ncolmax] locus_in_tile << 8 | allele */
 	const int *lc_first;		/* [n_lchunks + 1] first locus tile of each chunk */
 	const int *off;			/* [L + 1] prefix sums of J */
 	/* data */
-	const unsigned char *codes;	/* [n_itiles][n_ltiles][A3_THREADS][8] */
+	const unsigned char *codes;	/* [n_itiles][n_ltiles][A3_THREADS][A3_NC] */
 	const unsigned short *csc;	/* [n_itiles][n_ltiles][cap] sorted entries */
-	const unsigned short *colstart;	/* [n_itiles][n_ltiles][3][csw], csw = ncolmax + 1
-					 * rounded up to a multiple of 8: first entry, first
-					 * lane, locus_in_tile << 8 | allele of every column */
-	int cap;			/* entries per tile: A3_IT * 8 */
+	const unsigned short *colstart;	/* [n_itiles][n_ltiles][3 csw + A3_THREADS / 2], csw =
+					 * ncolmax + 1 rounded up to a multiple of 8: first entry,
+					 * first lane, locus_in_tile << 8 | allele of every column,
+					 * then the column of every pass-2 lane as bytes (255: idle) */
+	int cap;			/* entries per tile: A3_IT * A3_NC */
 	/* parameters */
 	const double *p, *eta;
 	long long eta_stride;
 	/* outputs */
 	double *Apart;			/* [n_lchunks][Ipad][K] */
 	double *Npart;			/* [n_ichunks][K*T] */
+	double *Gacc;			/* [n_ichunks][T][2 KP]: the allele sums G_lj of every unit,
+					 * read-modified-written in L2 by the fold (each row belongs
+					 * to one CTA) */
 	double *llpart;			/* [n_units] */
 };
 
@@ -95,12 +108,12 @@ __global__ void k_allele_hist(const unsigned char *nat, long long I, int L, int 
 	}
 }
 
-/* natural [I][L][P] codes -> 8 bytes per (tile, individual): LT = 8 / PP loci
- * x PP copies, thread-major inside a tile */
+/* natural [I][L][P] codes -> A3_NC bytes per (tile, individual): LT = A3_NC / PP
+ * loci x PP copies, thread-major inside a tile */
 __global__ void k3_build_codes(const unsigned char *nat, unsigned char *codes,
 	long long I, int L, int P, int PP, int n_itiles, int n_ltiles)
 {
-	const int LT = 8 / PP;
+	const int LT = A3_NC / PP;
 	const long long n = (long long)n_itiles * n_ltiles * A3_THREADS;
 	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
 		x += (long long)gridDim.x * blockDim.x) {
@@ -108,12 +121,15 @@ __global__ void k3_build_codes(const unsigned char *nat, unsigned char *codes,
 		const long long r = x / A3_THREADS;
 		const int lt = (int)(r % n_ltiles);
 		const long long i = (r / n_ltiles) * A3_IT + t;
-		unsigned char b[8];
-		for (int q = 0; q < 8; q++) {
-			const int l = lt * LT + q / PP, a = q % PP;
-			b[q] = (i < I && l < L && a < P) ? nat[((size_t)i * L + l) * P + a] : 255;
+		for (int h = 0; h < A3_NC / 8; h++) {
+			unsigned char b[8];
+			for (int q = 0; q < 8; q++) {
+				const int l = lt * LT + (h * 8 + q) / PP, a = q % PP;
+				b[q] = (i < I && l < L && a < P) ? nat[((size_t)i * L + l) * P + a] : 255;
+			}
+			*reinterpret_cast<uint2 *>(codes + (size_t)x * A3_NC + h * 8)
+				= *reinterpret_cast<uint2 *>(b);
 		}
-		*reinterpret_cast<uint2 *>(codes + (size_t)x * 8) = *reinterpret_cast<uint2 *>(b);
 	}
 }
 
@@ -132,8 +148,8 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 	unsigned short *csc, unsigned short *colstart)
 {
 	extern __shared__ unsigned char sm3[];
-	unsigned char *cd = sm3;				/* [A3_IT][8] */
-	int *cnt = reinterpret_cast<int *>(sm3 + (size_t)A3_IT * 8);	/* [ncolmax] */
+	unsigned char *cd = sm3;				/* [A3_IT][A3_NC] */
+	int *cnt = reinterpret_cast<int *>(sm3 + (size_t)A3_IT * A3_NC);	/* [ncolmax] */
 	int *lane_first = cnt + ncolmax;				/* [ncolmax + 1] */
 	/* carriers of every column as a bit mask over the tile's individuals: the
 	 * sweeps below then visit carriers only (a sixth of the individuals at
@@ -145,10 +161,11 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 	const unsigned short *ci = colinfo + (size_t)lt * ncolmax;
 	unsigned short *out = csc + (size_t)blockIdx.x * cap;
 	const int csw = ((ncolmax + 1 + 7) / 8) * 8;
-	unsigned short *cs = colstart + (size_t)blockIdx.x * 3 * csw;
-	const uint2 *src = reinterpret_cast<const uint2 *>(codes) + (size_t)blockIdx.x * A3_THREADS;
+	unsigned short *cs = colstart + (size_t)blockIdx.x * (3 * csw + A3_THREADS / 2);
+	const uint2 *src = reinterpret_cast<const uint2 *>(codes)
+		+ (size_t)blockIdx.x * A3_THREADS * (A3_NC / 8);
 
-	for (int x = threadIdx.x; x < A3_IT; x += blockDim.x)
+	for (int x = threadIdx.x; x < A3_IT * (A3_NC / 8); x += blockDim.x)
 		reinterpret_cast<uint2 *>(cd)[x] = src[x];
 	__syncthreads();
 	for (int x = threadIdx.x; x < ncol * MW; x += blockDim.x) {
@@ -156,7 +173,7 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 		const int ll = ci[c] >> 8, j = ci[c] & 0xff;
 		unsigned m = 0;
 		for (int b = 0; b < 32; b++) {
-			const unsigned char *pc = cd + (w * 32 + b) * 8 + ll * PP;
+			const unsigned char *pc = cd + (w * 32 + b) * A3_NC + ll * PP;
 			bool has = false;
 			for (int a = 0; a < PP; a++)
 				has |= pc[a] == j;
@@ -206,6 +223,30 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 			cs[2 * csw + c] = c < ncol ? ci[c] : 0;
 	}
 	__syncthreads();
+	/* the column of every pass-2 lane, two lanes per 16-bit word */
+	for (int x = threadIdx.x; x < A3_THREADS / 2; x += blockDim.x) {
+		unsigned v = 0;
+		for (int h = 0; h < 2; h++) {
+			const int ln = 2 * x + h;
+			int col = 255;
+			if (ln < lane_first[ncol]) {
+				int lo = 0, hi = ncol - 1;	/* last column with lane_first <= ln */
+				while (lo < hi) {
+					const int mid = (lo + hi + 1) >> 1;
+					if (lane_first[mid] <= ln)
+						lo = mid;
+					else
+						hi = mid - 1;
+				}
+				col = lo;
+				/* columns without entries own no lane: step to the owner */
+				while (lane_first[col + 1] <= ln)
+					col++;
+			}
+			v |= (unsigned)col << (8 * h);
+		}
+		cs[3 * csw + x] = (unsigned short)v;
+	}
 	for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
 		const int ll = ci[c] >> 8, j = ci[c] & 0xff;
 		const int n = cnt[c], start = cs[c];
@@ -233,7 +274,7 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 				const int ii = w * 32 + __ffs((int)mm) - 1;
 				int cn = 0, first = 0;
 				for (int a = PP - 1; a >= 0; a--)
-					if (cd[ii * 8 + ll * PP + a] == j) {
+					if (cd[ii * A3_NC + ll * PP + a] == j) {
 						cn++;
 						first = a;
 					}
@@ -307,22 +348,39 @@ __device__ __forceinline__ unsigned a3_lds_u16(unsigned addr)
 	return v;
 }
 
+/* log-likelihood terms of sums that are zero, subnormal or not finite (never
+ * seen in a healthy fit); out of line to keep pass 1 short */
+__device__ __noinline__ double a3_slow_ll(double t0, double t1)
+{
+	return log(t0) + log(t1);
+}
+
 /* 16-byte pieces per eta row in shared memory: an odd number, so that the rows
  * of 8 individuals with different i % 8 start in 8 different bank groups */
 template <int KP> struct A3Row { static constexpr int NP = KP | 1; };
 
 /* bytes of dynamic shared memory; the host planner uses the same formula */
-static inline size_t a3_smem_bytes(int KP, bool em, int max_chunk_rows, int PR,
-	int ncolmax, int cap)
+static inline size_t a3_smem_bytes(int KP, bool em, int ncolmax, int cap)
 {
 	const int KR = 2 * KP, NP = KP | 1;
-	size_t d = (size_t)KR * PR + 16;
+	const size_t csw = ((size_t)ncolmax + 1 + 7) / 8 * 8;
+	size_t d = (size_t)KR * A3_PR + 16;
 	if (em)
-		d += (size_t)max_chunk_rows * KR + (size_t)A3_IT * NP * 2 + 8 * (size_t)A3_IT
-			+ (size_t)A3_THREADS * KR;
+		d += (size_t)A3_IT * NP * 2 + (size_t)A3_NC * A3_IT + (size_t)A3_THREADS * KR;
 	return d * sizeof(double)
-		+ ((em ? (size_t)cap : 0) + 6 * ((size_t)(ncolmax + 1 + 7) / 8 * 8)) * sizeof(unsigned short)
-		+ 16 * sizeof(int);
+		+ ((em ? (size_t)cap : 0) + 2 * (3 * csw + A3_THREADS / 2)) * sizeof(unsigned short)
+		+ 2 * 16 * sizeof(int);
+}
+
+/* L2-only accesses of the allele sums: a row is read-modified-written by one
+ * CTA for a whole launch, but by different threads from tile to tile */
+__device__ __forceinline__ double2 a3_ldcg2(const double *p)
+{
+	return __ldcg(reinterpret_cast<const double2 *>(p));
+}
+__device__ __forceinline__ void a3_stcg2(double *p, double2 v)
+{
+	__stcg(reinterpret_cast<double2 *>(p), v);
 }
 
 /* MODE 0: E+M step, MODE 1: log likelihood only */
@@ -331,26 +389,29 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 {
 	constexpr int KR = 2 * KP;
 	constexpr int NP = A3Row<KP>::NP;
-	constexpr int LT = 8 / PP;
+	constexpr int LT = A3_NC / PP;		/* loci per tile */
+	constexpr int LH = 8 / PP;		/* loci per round of 8 copies */
+	constexpr int NH = A3_NC / 8;		/* rounds of pass 1 */
+	constexpr int PR = A3_PR;
 	constexpr bool EM = (MODE == 0);
 	extern __shared__ __align__(128) double smem3d[];
 	const int t = threadIdx.x, lane = t & 31;
-	const int PR = a.PR;
 	const int csw = ((a.ncolmax + 1 + 7) / 8) * 8;	/* colstart row, 16-byte multiple */
+	const int cstn = 3 * csw + A3_THREADS / 2;	/* shorts of one tile's column tables */
 
 	/* eta rows first: the xor rotation needs them aligned to their size */
 	double *eta_s = smem3d;						/* [A3_IT][2 NP] */
-	double *w_s = eta_s + (EM ? (size_t)A3_IT * NP * 2 : 0);	/* [8][A3_IT] */
-	double *part_s = w_s + (EM ? 8 * (size_t)A3_IT : 0);		/* [A3_THREADS][KR] */
-	double *B_s = part_s + (EM ? (size_t)A3_THREADS * KR : 0);	/* [max_chunk_rows][KR] */
-	double *p_s = B_s + (EM ? (size_t)a.max_chunk_rows * KR : 0);	/* [KR][PR] */
+	double *w_s = eta_s + (EM ? (size_t)A3_IT * NP * 2 : 0);	/* [A3_NC][A3_IT] */
+	double *part_s = w_s + (EM ? (size_t)A3_NC * A3_IT : 0);	/* [A3_THREADS][KR] */
+	double *p_s = part_s + (EM ? (size_t)A3_THREADS * KR : 0);	/* [KR][PR] */
 	double *red = p_s + (size_t)KR * PR;				/* [16] */
 	unsigned short *csc_s = reinterpret_cast<unsigned short *>(red + 16);	/* [cap] */
-	unsigned short *cst2_s = csc_s + (EM ? a.cap : 0);		/* [2][3][csw]: first entry, first
-									 * lane, locus/allele per column;
-									 * two tiles (the fold still reads
-									 * one while the next one lands) */
-	int *rb_s = reinterpret_cast<int *>(cst2_s + 6 * csw);		/* [2][8] row bases */
+	unsigned short *cst2_s = csc_s + (EM ? a.cap : 0);		/* [2][cstn]: first entry, first
+									 * lane, locus/allele per column,
+									 * column per lane; two tiles (the
+									 * fold still reads one while the
+									 * next one lands) */
+	int *rb_s = reinterpret_cast<int *>(cst2_s + 2 * cstn);		/* [2][16] row bases */
 	const unsigned eta_sa = (unsigned)__cvta_generic_to_shared(eta_s);
 	const unsigned w_sa = (unsigned)__cvta_generic_to_shared(w_s);
 	const unsigned csc_sa = (unsigned)__cvta_generic_to_shared(csc_s);
@@ -364,23 +425,34 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 		const int lend = lt1 * LT < a.L ? lt1 * LT : a.L;
 		const int row0 = a.off[l0];
 		const int chunk_rows = a.off[lend] - row0;
+		double *G_u = EM ? a.Gacc + ((size_t)r * a.T + row0) * KR : nullptr;
 		double prod = 1.0, ll_slow = 0.0;
 		long long esum = 0;
 		double e[KR], A[EM ? KR : 1];
 
 		__syncthreads();
 		if (EM)
-			for (int x = t; x < chunk_rows * KR; x += A3_THREADS)
-				B_s[x] = 0.0;
+			for (int x = t; x < chunk_rows * KP; x += A3_THREADS)
+				a3_stcg2(G_u + 2 * (size_t)x, make_double2(0.0, 0.0));
 
 		/* what the NEXT tile needs, fetched one tile ahead: the thread's
-		 * 8 allele codes and its pass-2 / fold assignments in registers,
-		 * the p rows and the entry lists by cp.async */
-		uint2 cw_n = make_uint2(0xffffffffu, 0xffffffffu);
+		 * allele codes in registers, the p rows and the entry lists by cp.async */
+		uint2 cw_n[NH];
 		int tro_n = 0;	/* first allele row of the tile inside the chunk */
+#pragma unroll
+		for (int h = 0; h < NH; h++)
+			cw_n[h] = make_uint2(0xffffffffu, 0xffffffffu);
 		auto fetch_regs = [&](long long it, int lt) {
 			const size_t tix = (size_t)it * a.n_ltiles + lt;
-			cw_n = __ldg(reinterpret_cast<const uint2 *>(a.codes) + tix * A3_THREADS + t);
+			const uint2 *src = reinterpret_cast<const uint2 *>(a.codes)
+				+ (tix * A3_THREADS + t) * NH;
+			if (NH == 2) {
+				const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src));
+				cw_n[0] = make_uint2(v.x, v.y);
+				cw_n[NH - 1] = make_uint2(v.z, v.w);
+			} else {
+				cw_n[0] = __ldg(src);
+			}
 			tro_n = __ldg(a.off + lt * LT) - row0;
 		};
 		auto stage_p = [&](int lt, int buf) {
@@ -397,16 +469,16 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					p_s[(size_t)k * PR + row] = 0.0;
 			}
 			if (t < LT)
-				rb_s[buf * 8 + t] = lf + t < a.L ? a.off[lf + t] - trow0 : 0;
+				rb_s[buf * 16 + t] = lf + t < a.L ? a.off[lf + t] - trow0 : 0;
 			a3_cp_async_commit();
 		};
 		auto stage_lists = [&](long long it, int lt, int buf) {
 			const size_t tix = (size_t)it * a.n_ltiles + lt;
-			unsigned short *cst_s = cst2_s + buf * 3 * csw;
-			if (t * 8 < a.cap)
-				a3_cp_async16(csc_s + t * 8, a.csc + tix * a.cap + t * 8);
-			if (t * 8 < 3 * csw)
-				a3_cp_async16(cst_s + t * 8, a.colstart + tix * 3 * csw + t * 8);
+			unsigned short *cst_s = cst2_s + buf * cstn;
+			for (int x = t * 8; x < a.cap; x += A3_THREADS * 8)
+				a3_cp_async16(csc_s + x, a.csc + tix * a.cap + x);
+			if (t * 8 < cstn)
+				a3_cp_async16(cst_s + t * 8, a.colstart + tix * cstn + t * 8);
 			a3_cp_async_commit();
 		};
 
@@ -441,14 +513,17 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 			}
 
 			for (int lt = lt0; lt < lt1; lt++, buf ^= 1) {
-				const uint2 cw = cw_n;
+				uint2 cwa[NH];
+#pragma unroll
+				for (int h = 0; h < NH; h++)
+					cwa[h] = cw_n[h];
 				const int tro = tro_n;
 				const bool last = lt + 1 == lt1;
 				const long long itn = last ? it + 1 : it;
 				const int ltn = last ? lt0 : lt + 1;
 				const bool more = itn < it1;
-				const int *rb = rb_s + buf * 8;
-				const unsigned short *cst_s = cst2_s + buf * 3 * csw;
+				const int *rb = rb_s + buf * 16;
+				const unsigned short *cst_s = cst2_s + buf * cstn;
 
 				if (more)
 					fetch_regs(itn, ltn);
@@ -460,18 +535,24 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 				 * the previous tile's pass 2; its entry lists are only needed
 				 * after pass 1 */
 
-				/* ---- pass 1: tmp, w, A, log likelihood ---- */
+				/* ---- pass 1: tmp, w, A, log likelihood; rounds of 8 copies ---- */
+#pragma unroll 1
+				for (int hh = 0; hh < NH; hh++) {
+				const uint2 cw = (NH == 2 && hh) ? cwa[NH - 1] : cwa[0];
+				const int *rbh = rb + hh * LH;
 				double pr[2][KR];
 				bool valid[2];
+				unsigned codes_q[2];
 				auto load_row = [&](int q, int z) {
 					const unsigned code = ((q < 4 ? cw.x : cw.y) >> ((q & 3) * 8)) & 0xffu;
+					codes_q[z] = code;
 					valid[z] = code != 255u;
 					/* a missing copy reads the locus's first row: same
 					 * bank window as the lanes that carry an allele */
-					const int row = rb[q / PP] + (valid[z] ? (int)code : 0);
+					const int row = rbh[q / PP] + (valid[z] ? (int)code : 0);
 #pragma unroll
 					for (int k = 0; k < KR; k++)
-						pr[z][k] = p_s[(size_t)k * PR + row];
+						pr[z][k] = p_s[k * PR + row];
 				};
 				load_row(0, 0);
 				double tprev = 1.0;
@@ -492,7 +573,26 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 #pragma unroll
 						for (int k = 0; k < KR; k++)
 							A[k] = fma(pr[z][k], wgt, A[k]);
-						w_s[(size_t)q * A3_IT + t] = wgt;
+						/* pass 2 meets an (individual, allele) pair once, at its
+						 * first copy: that slot carries w times the number of
+						 * copies of the allele at this locus */
+						double wst = wgt;
+						if (PP == 2) {
+							if ((q & 1) == 0) {
+								const unsigned nxt = ((q + 1 < 4 ? cw.x : cw.y)
+									>> (((q + 1) & 3) * 8)) & 0xffu;
+								wst = nxt == codes_q[z] ? wgt + wgt : wgt;
+							}
+						} else if (PP > 2) {
+							int n = 1;
+#pragma unroll
+							for (int q2 = q + 1; q2 < 8; q2++)
+								if (q2 / PP == q / PP)
+									n += (((q2 < 4 ? cw.x : cw.y) >> ((q2 & 3) * 8)) & 0xffu)
+										== codes_q[z];
+							wst = wgt * (double)n;
+						}
+						w_s[(size_t)(hh * 8 + q) * A3_IT + t] = wst;
 					}
 					if (z == 0) {
 						tprev = tmp;
@@ -512,9 +612,10 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 							prod = __hiloint2double((hp & 0x000fffff) | 0x3ff00000,
 								__double2loint(prod));
 						} else {
-							ll_slow += log(tprev) + log(tmp);
+							ll_slow += a3_slow_ll(tprev, tmp);
 						}
 					}
+				}
 				}
 				if (EM)
 					a3_cp_async_wait<0>();
@@ -532,15 +633,10 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 #pragma unroll
 				for (int k = 0; k < KR; k++)
 					g[k] = 0.0;
-				/* the lane's column: first-lane table of this tile (binary search;
-				 * trailing entries repeat the number of lanes in use) */
-				int col = 0;
-#pragma unroll
-				for (int step = 128; step >= 1; step >>= 1)
-					if (col + step < csw - 1 && (int)cst_s[csw + col + step] <= t)
-						col += step;
-				const int lane0c = cst_s[csw + col], lane1c = cst_s[csw + col + 1];
-				if (t < lane1c) {
+				/* the lane's column, from the tile's lane table */
+				const int col = (cst_s[3 * csw + (t >> 1)] >> ((t & 1) * 8)) & 0xff;
+				if (col != 255) {
+					const int lane0c = cst_s[csw + col], lane1c = cst_s[csw + col + 1];
 					const int S2 = (lane1c - lane0c) * 2;	/* list stride, bytes */
 					const unsigned wb = w_sa + (unsigned)(cst_s[2 * csw + col] >> 8)
 						* (PP * A3_IT * 8);
@@ -548,7 +644,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					unsigned x = csc_sa + 2u * (cst_s[col] + (t - lane0c));
 					/* ids run two trips ahead and weights one, and nothing is
 					 * computed from a load in the trip that issues it: the warp
-					 * issues in order, so a multiply on a fresh load would hold
+					 * issues in order, so an operation on a fresh load would hold
 					 * the accumulation of the current entry back */
 					auto w_addr = [&](unsigned en) {
 						return wb + ((en >> 9) & 7) * (A3_IT * 8) + (en & (A3_IT - 1)) * 8;
@@ -558,7 +654,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					double w0 = x < xe ? a3_lds_f64(w_addr(e0)) : 0.0;
 					while (x < xe) {
 						const unsigned rm = eta_sa + (e0 & (A3_IT - 1)) * (NP * 16);
-						const double wc = w0 * (double)((e0 >> 12) + 1);
+						const double wc = w0;
 						const unsigned e2 = x + 2 * S2 < xe ? a3_lds_u16(x + 2 * S2) : 0u;
 						double2 v[KP];
 #pragma unroll
@@ -587,13 +683,17 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 				else
 					a3_cp_async_commit();
 
-				/* ---- fold: thread <-> (column, piece), lanes in order ---- */
+				/* ---- fold: thread <-> (column, piece), lanes in order; the
+				 * column's running sum lives in L2 ---- */
 				for (int f = t; f < a.ncolmax * KP; f += A3_THREADS) {
 					const int cc = f / KP, pc = f - cc * KP;
 					const int lane0 = cst_s[csw + cc], S = cst_s[csw + cc + 1] - lane0;
 					if (S <= 0)
 						continue;
 					const unsigned info = cst_s[2 * csw + cc];
+					double *dst = G_u + (size_t)(tro + rb[info >> 8] + (int)(info & 0xff)) * KR
+						+ 2 * pc;
+					const double2 old = a3_ldcg2(dst);
 					const double2 *src = reinterpret_cast<const double2 *>(
 						part_s + (size_t)lane0 * KR + 2 * pc);
 					/* four independent partial sums keep four loads in flight */
@@ -614,12 +714,10 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 						acc.x += v0.x;
 						acc.y += v0.y;
 					}
-					double2 *dst = reinterpret_cast<double2 *>(B_s + (size_t)(tro
-						+ rb[info >> 8] + (int)(info & 0xff)) * KR + 2 * pc);
-					double2 v = *dst;
+					double2 v = old;
 					v.x += (acc.x + a1.x) + (a2.x + a3.x);
 					v.y += (acc.y + a1.y) + (a2.y + a3.y);
-					*dst = v;
+					a3_stcg2(dst, v);
 				}
 			}
 			if (EM) {
@@ -639,7 +737,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 			for (int x = t; x < chunk_rows * a.K; x += A3_THREADS) {
 				const int k = x / chunk_rows, row = x - k * chunk_rows;
 				const size_t gx = (size_t)k * a.T + row0 + row;
-				Np[gx] = B_s[(size_t)row * KR + k] * __ldg(a.p + gx);
+				Np[gx] = __ldcg(G_u + (size_t)row * KR + k) * __ldg(a.p + gx);
 			}
 		}
 		/* ---- log likelihood of the unit ---- */

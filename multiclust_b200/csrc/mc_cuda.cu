@@ -77,11 +77,11 @@ struct mc_ctx {
 	bool use3 = false;
 	bool layout3 = false;		/* codes / lists / column tables are built */
 	int l3_ncolmax = 0, l3_max_tile_rows = 0;
-	std::vector<int> l3_lt_rows;	/* allele rows per locus tile (host) */
 	Admix3Args a3;
 	int KP3 = 0, grid3 = 0;
 	size_t smem3 = 0, smem3_ll = 0;
 	int *d3_lt_ncol = nullptr, *d3_lc_first = nullptr;
+	double *d3_Gacc = nullptr;
 	unsigned short *d3_colinfo = nullptr, *d3_csc = nullptr, *d3_colstart = nullptr;
 	unsigned char *d3_codes = nullptr;
 	/* dense DMMA plan for biallelic data (mc_dense.cuh); used when `use_dn` */
@@ -224,7 +224,7 @@ static void free_plan(mc_ctx *c)
 	dfree(c->d_group_rowbase); dfree(c->d_group_rows); dfree(c->d_tile_rows);
 	dfree(c->d_tiled); dfree(c->d_Apart); dfree(c->d_Npart);
 	dfree(c->d_llpart); dfree(c->d_xbuf); dfree(c->d_red);
-	dfree(c->d3_lc_first);
+	dfree(c->d3_lc_first); dfree(c->d3_Gacc);
 	dfree(c->d_dn_pd); dfree(c->d_dn_lc_first);
 	c->use3 = false;
 	c->use_dn = false;
@@ -543,10 +543,10 @@ static int make_plan3(mc_ctx *c)
 	if (c->opt_kernel == MC_KERNEL_TILE || c->opt_kernel == MC_KERNEL_DENSE)
 		return MC_OK;
 	const int K = c->K, KP = (K + 1) / 2, KR = 2 * KP, PP = c->PP, L = c->L;
-	const int LT = 8 / PP;
+	const int LT = A3_NC / PP;
 	const int n_ltiles = (L + LT - 1) / LT;
 	const long long n_itiles = (c->I + A3_IT - 1) / A3_IT;
-	const int cap = A3_IT * 8;
+	const int cap = A3_IT * A3_NC;
 	const bool timing = c->opt_timing != 0;
 	auto t_prev = std::chrono::steady_clock::now();
 	auto mark = [&](const char *what) {
@@ -580,11 +580,9 @@ static int make_plan3(mc_ctx *c)
 		std::vector<int> lt_ncol((size_t)n_ltiles);
 		std::vector<std::vector<std::pair<unsigned, unsigned short>>> cols((size_t)n_ltiles);
 		int ncm = 1, mtr = 1;
-		c->l3_lt_rows.assign((size_t)n_ltiles, 0);
 		for (int lt = 0; lt < n_ltiles; lt++) {
 			const int lf = lt * LT, le = std::min(L, lf + LT);
-			c->l3_lt_rows[lt] = c->off[le] - c->off[lf];
-			mtr = std::max(mtr, c->l3_lt_rows[lt]);
+			mtr = std::max(mtr, c->off[le] - c->off[lf]);
 			auto &v = cols[lt];
 			for (int l = lf; l < le; l++)
 				for (int j = 0; j < c->J[l]; j++)
@@ -613,16 +611,16 @@ static int make_plan3(mc_ctx *c)
 		if ((rc = upload(c, c->d3_colinfo, colinfo))) return rc;
 		const size_t ntile = (size_t)n_itiles * n_ltiles;
 		mark("column order + uploads");
-		CK(MC_DEV_MALLOC(&c->d3_codes, ntile * A3_THREADS * 8));
+		CK(MC_DEV_MALLOC(&c->d3_codes, ntile * A3_THREADS * A3_NC));
 		CK(MC_DEV_MALLOC(&c->d3_csc, ntile * cap * sizeof(unsigned short)));
-		CK(MC_DEV_MALLOC(&c->d3_colstart, ntile * 3 * (size_t)((ncm + 1 + 7) / 8 * 8)
-			* sizeof(unsigned short)));
+		CK(MC_DEV_MALLOC(&c->d3_colstart, ntile * (3 * (size_t)((ncm + 1 + 7) / 8 * 8)
+			+ A3_THREADS / 2) * sizeof(unsigned short)));
 		mark("cudaMalloc codes/lists");
 		k3_build_codes<<<grid_for(c, (long long)ntile * A3_THREADS, 256), 256, 0, c->stream>>>(
 			c->d_nat, c->d3_codes, c->I, L, c->P, PP, (int)n_itiles, n_ltiles);
 		LAUNCH_CHECK("k3_build_codes");
 		mark("k3_build_codes");
-		const size_t bsm = (size_t)A3_IT * 8 + sizeof(int) * (2 * (size_t)ncm + 1)
+		const size_t bsm = (size_t)A3_IT * A3_NC + sizeof(int) * (2 * (size_t)ncm + 1)
 			+ sizeof(unsigned) * (size_t)ncm * (A3_IT / 32);
 		k3_build_csc<<<(unsigned)ntile, 128, bsm, c->stream>>>(c->d3_codes, PP, n_ltiles,
 			ncm, cap, c->d3_lt_ncol, c->d3_colinfo, c->d3_csc, c->d3_colstart);
@@ -633,79 +631,47 @@ static int make_plan3(mc_ctx *c)
 		c->layout3 = true;
 	}
 	const int ncolmax = c->l3_ncolmax, max_tile_rows = c->l3_max_tile_rows;
-	const std::vector<int> &lt_rows = c->l3_lt_rows;
 
-	/* shared memory: fixed part, the rest holds the chunk's accumulators */
-	const int PR = (max_tile_rows + 1) & ~1;
-	const size_t fixed = a3_smem_bytes(KP, true, 0, PR, ncolmax, cap) + 64;
+	/* shared memory holds the tile only; the chunk's allele sums live in L2 */
+	c->smem3 = a3_smem_bytes(KP, true, ncolmax, cap);
+	c->smem3_ll = a3_smem_bytes(KP, false, ncolmax, cap);
 	const size_t smem_cap = (size_t)(228 * 1024) / A3_CTAS_PER_SM - 1024 - 64;
-	if (fixed + (size_t)max_tile_rows * KR * sizeof(double) > smem_cap) {
+	if (c->smem3 + 64 > smem_cap || max_tile_rows > A3_PR) {
 		free_layout3(c);	/* the one-pass kernel takes over: drop the multi-GB lists */
 		return MC_OK;
 	}
-	const long long budget_rows = (long long)((smem_cap - fixed) / (KR * sizeof(double)));
-	const long long total_rows = c->T;
 	const long long sms = (long long)c->num_sms * A3_CTAS_PER_SM;
-	const int nl_min = (int)((total_rows + budget_rows - 1) / budget_rows);
 
-	/* locus chunks x individual chunks: fill the persistent grid evenly; more
-	 * locus chunks cost A_ik partial sums, more individual chunks cost N sums */
-	auto split_loci = [&](int want, std::vector<int> &first, int &max_rows) {
-		int n = want;
-		for (;;) {
-			const double target = (double)total_rows / n;
-			first.assign(1, 0);
-			long long rows = 0;
-			bool ok = true;
-			max_rows = 1;
-			for (int lt = 0; lt < n_ltiles; lt++) {
-				if (rows > 0 && (rows + lt_rows[lt] > budget_rows
-					|| (rows + lt_rows[lt] / 2.0 > target && (int)first.size() < n))) {
-					first.push_back(lt);
-					rows = 0;
-				}
-				rows += lt_rows[lt];
-				if (rows > budget_rows)
-					ok = false;
-				max_rows = std::max<long long>(max_rows, rows);
-			}
-			first.push_back(n_ltiles);
-			if (ok)
-				break;
-			n++;
-		}
-	};
-	std::vector<int> lc_first;
-	int max_chunk_rows = 1, n_ichunks = 1;
+	/* locus chunks x individual chunks: fill the persistent grid evenly.  More
+	 * locus chunks cost A_ik partial sums (written once, read once: 16 bytes per
+	 * individual, cluster and chunk against ~1e-11 s per allele copy of the
+	 * kernel itself), more individual chunks cost allele-sum buffers */
+	int n_lchunks = 1, n_ichunks = 1;
 	{
-		double best_eff = -1;
-		std::vector<int> first;
-		int mr = 1, last_n = -1;
-		const int nl_max = (int)std::min<long long>(n_ltiles, std::max<long long>(nl_min, 2 * sms));
-		for (int want = nl_min; want <= nl_max; want++) {
-			split_loci(want, first, mr);
-			const int nl = (int)first.size() - 1;	/* what the split really gives */
-			if (nl == last_n)
-				continue;
-			last_n = nl;
+		double best_eff = -1e30;
+		const int nl_max = (int)std::min<long long>(n_ltiles, 2 * sms);
+		for (int nl = 1; nl <= nl_max; nl++) {
+			const double apart = (double)nl * K * 16.0 / ((double)L * c->P * 64.0);
+			const double lmax = (double)((n_ltiles + nl - 1) / nl) * nl / n_ltiles;
 			const long long cmax = std::min<long long>(n_itiles,
 				std::max<long long>(1, (4 * sms + nl - 1) / nl));
 			for (long long cc = 1; cc <= cmax; cc++) {
 				const long long units = cc * nl;
 				const long long rounds = (units + sms - 1) / sms;
-				const double eff = (double)units / (double)(rounds * sms)
-					- 0.02 * (double)nl / (double)std::max(nl_min, 1)
-					- 0.004 * (double)cc - 0.002 * (double)rounds;
+				const double imax = (double)((n_itiles + cc - 1) / cc) * cc / n_itiles;
+				const double eff = (double)units / (double)(rounds * sms) / (lmax * imax)
+					- apart - 0.004 * (double)cc - 0.002 * (double)rounds;
 				if (eff > best_eff + 1e-12) {
 					best_eff = eff;
-					lc_first = first;
-					max_chunk_rows = mr;
+					n_lchunks = nl;
 					n_ichunks = (int)cc;
 				}
 			}
 		}
 	}
-	const int n_lchunks = (int)lc_first.size() - 1;
+	std::vector<int> lc_first((size_t)n_lchunks + 1);
+	for (int x = 0; x <= n_lchunks; x++)
+		lc_first[x] = (int)((long long)n_ltiles * x / n_lchunks);
 
 	Admix3Args &a = c->a3;
 	memset(&a, 0, sizeof a);
@@ -713,10 +679,8 @@ static int make_plan3(mc_ctx *c)
 	a.n_itiles = (int)n_itiles; a.n_ltiles = n_ltiles; a.n_lchunks = n_lchunks;
 	a.n_ichunks = n_ichunks; a.n_units = n_lchunks * n_ichunks;
 	a.I = c->I; a.Ipad = n_itiles * A3_IT; a.T = c->T; a.L = L;
-	a.ncolmax = ncolmax; a.max_chunk_rows = max_chunk_rows; a.PR = PR; a.cap = cap;
+	a.ncolmax = ncolmax; a.max_chunk_rows = 0; a.cap = cap;
 	c->KP3 = KP;
-	c->smem3 = a3_smem_bytes(KP, true, max_chunk_rows, PR, ncolmax, cap);
-	c->smem3_ll = a3_smem_bytes(KP, false, max_chunk_rows, PR, ncolmax, cap);
 	c->grid3 = (int)std::min<long long>(a.n_units, sms);
 
 	int rc;
@@ -725,7 +689,9 @@ static int make_plan3(mc_ctx *c)
 	 a.lc_first = c->d3_lc_first; a.off = c->d_off;
 	a.codes = c->d3_codes; a.csc = c->d3_csc; a.colstart = c->d3_colstart;
 	if ((rc = alloc_outputs(c, n_lchunks, n_ichunks, a.n_units, a.Ipad))) return rc;
+	CK(MC_DEV_MALLOC(&c->d3_Gacc, sizeof(double) * (size_t)n_ichunks * c->T * KR));
 	a.Apart = c->d_Apart; a.Npart = c->d_Npart; a.llpart = c->d_llpart;
+	a.Gacc = c->d3_Gacc;
 	CK(cudaStreamSynchronize(c->stream));
 	mark("partial-sum buffers");
 	c->use3 = true;
@@ -1760,7 +1726,7 @@ extern "C" int mc_get_plan(const mc_ctx *c, mc_plan_info *o)
 	if (c->use3) {	/* two-pass admixture kernel: tiles are locus chunks */
 		o->two_pass = 2;
 		o->k_split = 1; o->k_per_lane = 2 * c->KP3;
-		o->loci_per_warp = 8 / c->PP; o->warps = A3_THREADS / 32; o->groups = 1;
+		o->loci_per_warp = A3_NC / c->PP; o->warps = A3_THREADS / 32; o->groups = 1;
 		o->n_tiles = c->a3.n_lchunks; o->n_chunks = c->a3.n_ichunks;
 		o->n_units = c->a3.n_units; o->grid = c->grid3; o->block = A3_THREADS;
 		o->indiv_per_block = A3_IT; o->smem_bytes = (int64_t)c->smem3;
