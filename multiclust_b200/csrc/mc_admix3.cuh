@@ -373,14 +373,41 @@ static inline size_t a3_smem_bytes(int KP, bool em, int ncolmax, int cap)
 }
 
 /* L2-only accesses of the allele sums: a row is read-modified-written by one
- * CTA for a whole launch, but by different threads from tile to tile */
-__device__ __forceinline__ double2 a3_ldcg2(const double *p)
+ * CTA for a whole launch, but by different threads from tile to tile.  The rows
+ * (K x T doubles per individual chunk, tens of MB) are marked evict-last and
+ * the genotype codes / entry lists that stream through evict-first, so the
+ * sums stay in the 126 MB L2 between two visits instead of going to HBM and
+ * back once per tile of individuals. */
+__device__ __forceinline__ unsigned long long a3_policy_keep()
 {
-	return __ldcg(reinterpret_cast<const double2 *>(p));
+	unsigned long long pol;
+	asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
 }
-__device__ __forceinline__ void a3_stcg2(double *p, double2 v)
+__device__ __forceinline__ unsigned long long a3_policy_stream()
 {
-	__stcg(reinterpret_cast<double2 *>(p), v);
+	unsigned long long pol;
+	asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ double2 a3_ldcg2(const double *p, unsigned long long pol)
+{
+	double2 v;
+	asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+		: "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol) : "memory");
+	return v;
+}
+__device__ __forceinline__ void a3_stcg2(double *p, double2 v, unsigned long long pol)
+{
+	asm volatile("st.global.cg.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;"
+		:: "l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void a3_cp_async16_stream(void *smem_dst, const void *gsrc,
+	unsigned long long pol)
+{
+	const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;"
+		:: "r"(s), "l"(gsrc), "l"(pol));
 }
 
 /* MODE 0: E+M step, MODE 1: log likelihood only */
@@ -415,6 +442,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 	const unsigned eta_sa = (unsigned)__cvta_generic_to_shared(eta_s);
 	const unsigned w_sa = (unsigned)__cvta_generic_to_shared(w_s);
 	const unsigned csc_sa = (unsigned)__cvta_generic_to_shared(csc_s);
+	const unsigned long long pol_keep = a3_policy_keep(), pol_stream = a3_policy_stream();
 
 	for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
 		const int c = u % a.n_lchunks, r = u / a.n_lchunks;
@@ -433,7 +461,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 		__syncthreads();
 		if (EM)
 			for (int x = t; x < chunk_rows * KP; x += A3_THREADS)
-				a3_stcg2(G_u + 2 * (size_t)x, make_double2(0.0, 0.0));
+				a3_stcg2(G_u + 2 * (size_t)x, make_double2(0.0, 0.0), pol_keep);
 
 		/* what the NEXT tile needs, fetched one tile ahead: the thread's
 		 * allele codes in registers, the p rows and the entry lists by cp.async */
@@ -447,7 +475,9 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 			const uint2 *src = reinterpret_cast<const uint2 *>(a.codes)
 				+ (tix * A3_THREADS + t) * NH;
 			if (NH == 2) {
-				const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src));
+				uint4 v;
+				asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+					: "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src), "l"(pol_stream));
 				cw_n[0] = make_uint2(v.x, v.y);
 				cw_n[NH - 1] = make_uint2(v.z, v.w);
 			} else {
@@ -476,9 +506,9 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 			const size_t tix = (size_t)it * a.n_ltiles + lt;
 			unsigned short *cst_s = cst2_s + buf * cstn;
 			for (int x = t * 8; x < a.cap; x += A3_THREADS * 8)
-				a3_cp_async16(csc_s + x, a.csc + tix * a.cap + x);
+				a3_cp_async16_stream(csc_s + x, a.csc + tix * a.cap + x, pol_stream);
 			if (t * 8 < cstn)
-				a3_cp_async16(cst_s + t * 8, a.colstart + tix * cstn + t * 8);
+				a3_cp_async16_stream(cst_s + t * 8, a.colstart + tix * cstn + t * 8, pol_stream);
 			a3_cp_async_commit();
 		};
 
@@ -693,7 +723,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					const unsigned info = cst_s[2 * csw + cc];
 					double *dst = G_u + (size_t)(tro + rb[info >> 8] + (int)(info & 0xff)) * KR
 						+ 2 * pc;
-					const double2 old = a3_ldcg2(dst);
+					const double2 old = a3_ldcg2(dst, pol_keep);
 					const double2 *src = reinterpret_cast<const double2 *>(
 						part_s + (size_t)lane0 * KR + 2 * pc);
 					/* four independent partial sums keep four loads in flight */
@@ -717,7 +747,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					double2 v = old;
 					v.x += (acc.x + a1.x) + (a2.x + a3.x);
 					v.y += (acc.y + a1.y) + (a2.y + a3.y);
-					a3_stcg2(dst, v);
+					a3_stcg2(dst, v, pol_keep);
 				}
 			}
 			if (EM) {

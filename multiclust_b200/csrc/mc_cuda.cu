@@ -16,6 +16,7 @@
 #include <chrono>
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include "mc_cuda.h"
 #include "mc_kernels.cuh"
@@ -35,6 +36,7 @@ struct mc_ctx {
 	cudaStream_t aux = nullptr;
 	cudaEvent_t ev_main = nullptr, ev_aux = nullptr;
 	bool aux_pending = false;
+	bool fused_step = false;	/* mc_em_step: local + finish without an exchange */
 	std::string err;
 	int64_t launches = 0;
 	int num_sms = 148;
@@ -93,6 +95,9 @@ struct mc_ctx {
 	unsigned char *d_dn_cnt = nullptr;
 	double *d_dn_pd = nullptr;
 	int *d_dn_lc_first = nullptr;
+	/* kernels whose dynamic shared-memory limit has been raised (set once per
+	 * kernel and size, not on every launch) */
+	std::vector<std::pair<const void *, size_t>> smem_attr;
 	/* plan options (mc_set_option) */
 	int opt_kernel = 0, opt_timing = 0;
 	/* scratch of the admixture initialiser, kept between fits */
@@ -109,6 +114,14 @@ struct mc_ctx {
 	int64_t prof_n = 0;
 	double prof_ms = 0;
 };
+
+/* NVTX range around an ABI call (visible in Nsight Systems / ncu --nvtx;
+ * a few nanoseconds when no tool is attached) */
+struct NvtxRange {
+	explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+	~NvtxRange() { nvtxRangePop(); }
+};
+#define NVTX_FN() NvtxRange nvtx_range_(__func__)
 
 /* ---------------------------------------------------------------- errors */
 
@@ -346,6 +359,7 @@ static int set_dims(mc_ctx *c, int64_t I, int32_t L, int32_t P, const int32_t *J
 extern "C" int mc_set_data(mc_ctx *c, int64_t I, int32_t L, int32_t P,
 	const int32_t *J, const uint8_t *codes)
 {
+	NVTX_FN();
 	if (!c || !J || !codes)
 		return fail(c, MC_ERR_ARG, "mc_set_data: null argument");
 	CK(cudaSetDevice(c->device));
@@ -362,6 +376,7 @@ extern "C" int mc_set_data(mc_ctx *c, int64_t I, int32_t L, int32_t P,
 extern "C" int mc_set_data_synth(mc_ctx *c, int64_t I, int32_t L,
 	const mcs_params *g, int64_t i_first)
 {
+	NVTX_FN();
 	if (!c || !g)
 		return fail(c, MC_ERR_ARG, "mc_set_data_synth: null argument");
 	if (g->jmax < 2 || g->jmax > 254 || g->ploidy < 1 || g->ploidy > 16 || g->K < 1)
@@ -509,6 +524,21 @@ static int upload(mc_ctx *c, T *&dst, const std::vector<T> &src)
 	CK(MC_DEV_MALLOC(&dst, sizeof(T) * std::max<size_t>(src.size(), 1)));
 	CK(cudaMemcpyAsync(dst, src.data(), sizeof(T) * src.size(),
 		cudaMemcpyHostToDevice, c->stream));
+	return MC_OK;
+}
+
+static int raise_smem_limit(mc_ctx *c, const void *fn, size_t smem)
+{
+	for (auto &e : c->smem_attr)
+		if (e.first == fn) {
+			if (e.second >= smem)
+				return MC_OK;
+			CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			e.second = smem;
+			return MC_OK;
+		}
+	CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	c->smem_attr.push_back({ fn, smem });
 	return MC_OK;
 }
 
@@ -735,8 +765,11 @@ static int launch_admix3(mc_ctx *c, int ll_only, const double *p, const double *
 	Admix3Args a = c->a3;
 	a.p = p; a.eta = eta; a.eta_stride = eta_stride;
 	const size_t smem = ll_only ? c->smem3_ll : c->smem3;
-	CK(cudaFuncSetAttribute((const void *)fn,
-		cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	{
+		const int rca = raise_smem_limit(c, (const void *)fn, smem);
+		if (rca)
+			return rca;
+	}
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	if (c->profile) {
 		CK(cudaEventCreate(&e0));
@@ -902,8 +935,11 @@ static int launch_dense(mc_ctx *c, int mode, const double *ptab, const double *p
 		LAUNCH_CHECK("k_dense_p");
 	}
 	const size_t smem = dn_smem_bytes(c->dn_NB, mode, a.max_chunk_tiles);
-	CK(cudaFuncSetAttribute((const void *)fn,
-		cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	{
+		const int rca = raise_smem_limit(c, (const void *)fn, smem);
+		if (rca)
+			return rca;
+	}
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	if (c->profile) {
 		CK(cudaEventCreate(&e0));
@@ -1032,6 +1068,7 @@ static int make_plan(mc_ctx *c)
 extern "C" int mc_alloc_model(mc_ctx *c, int32_t K, int admixture,
 	int eta_constrained, int q, double eta_lb, double p_lb, int do_projection)
 {
+	NVTX_FN();
 	if (!c)
 		return MC_ERR_ARG;
 	if (!c->I)
@@ -1179,8 +1216,11 @@ static int launch_tile(mc_ctx *c, int mode, const double *p, const double *eta,
 		return fail(c, MC_ERR_UNSUPPORTED, "no kernel for KH=%d PP=%d", c->KH, c->PP);
 	TileArgs ta = c->ta;
 	ta.p = p; ta.eta = eta; ta.eta_stride = eta_stride;
-	CK(cudaFuncSetAttribute((const void *)fn,
-		cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_em));
+	{
+		const int rca = raise_smem_limit(c, (const void *)fn, c->smem_em);
+		if (rca)
+			return rca;
+	}
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	if (c->profile) {
 		CK(cudaEventCreate(&e0));
@@ -1199,6 +1239,11 @@ static int launch_tile(mc_ctx *c, int mode, const double *p, const double *eta,
 /* sum d_llpart[0..n) (or any vector) into *out on the device */
 static int reduce_vector(mc_ctx *c, const double *x, long long n, double *out)
 {
+	if (n <= 16 * RED_THREADS) {	/* short: the final stage alone, same fixed order per n */
+		k_colsum_final<<<1, RED_THREADS, 0, c->stream>>>(x, (int)n, 1, out);
+		LAUNCH_CHECK("k_colsum_final");
+		return MC_OK;
+	}
 	k_colsum_partial<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(x, n, 1, 1, c->d_red);
 	LAUNCH_CHECK("k_colsum_partial");
 	k_colsum_final<<<1, RED_THREADS, 0, c->stream>>>(c->d_red, RED_BLOCKS, 1, out);
@@ -1249,6 +1294,7 @@ static int mix_tail(mc_ctx *c, const double *eta, double *vik, int ll_only)
 
 extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 {
+	NVTX_FN();
 	NEED_MODEL();
 	CHECK_SLOT(from);
 	CHECK_SLOT(to);
@@ -1263,9 +1309,11 @@ extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 			: launch_tile(c, MODE_ADMIX_EM, c->d_p[from], c->d_eta[from],
 				c->per_indiv ? K : 0);
 		if (rc) return rc;
-		k_sum_chunks<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_Npart,
-			c->act_chunks, c->np, 0.0, xb_N(c));
-		LAUNCH_CHECK("k_sum_chunks");
+		if (!c->fused_step) {
+			k_sum_chunks<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_Npart,
+				c->act_chunks, c->np, 0.0, xb_N(c));
+			LAUNCH_CHECK("k_sum_chunks");
+		}
 		if ((rc = reduce_vector(c, c->d_llpart, c->act_units, xb_ll(c)))) return rc;
 		/* eta side: D_ik = eta_ik * A_ik needs only this context's
 		 * individuals; the streaming kernel is done with slot `from`, so
@@ -1302,9 +1350,11 @@ extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 		if ((rc = reduce_vector(c, c->d_lli, c->I, xb_ll(c)))) return rc;
 		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_M, nullptr, nullptr, c->d_post, K)
 			: launch_tile(c, MODE_MIX_M, nullptr, c->d_post, K))) return rc;
-		k_sum_chunks<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_Npart,
-			c->act_chunks, c->np, 0.0, xb_N(c));
-		LAUNCH_CHECK("k_sum_chunks");
+		if (!c->fused_step) {
+			k_sum_chunks<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_Npart,
+				c->act_chunks, c->np, 0.0, xb_N(c));
+			LAUNCH_CHECK("k_sum_chunks");
+		}
 		if ((rc = reduce_columns(c, c->d_post, c->I, K, xb_S(c)))) return rc;
 	}
 	return MC_OK;
@@ -1333,6 +1383,7 @@ extern "C" int mc_exchange_sum(mc_ctx *c, const void *gathered, int n_ranks)
 extern "C" int mc_exchange_sum_slice(mc_ctx *c, const void *parts, int n_ranks,
 	int64_t first, int64_t count)
 {
+	NVTX_FN();
 	NEED_MODEL();
 	const int64_t cap = c->np + 1 + c->K + 64;
 	if (!parts || n_ranks < 1 || first < 0 || count < 0 || first + count > cap)
@@ -1347,6 +1398,7 @@ extern "C" int mc_exchange_sum_slice(mc_ctx *c, const void *parts, int n_ranks,
 
 extern "C" int mc_em_step_finish(mc_ctx *c, int to, double *ll)
 {
+	NVTX_FN();
 	NEED_MODEL();
 	CHECK_SLOT(to);
 	const int K = c->K;
@@ -1358,17 +1410,20 @@ extern "C" int mc_em_step_finish(mc_ctx *c, int to, double *ll)
 			c->do_proj, c->eta_lb);
 		LAUNCH_CHECK("k_update_eta_pooled");
 	}
-	const double *N = xb_N(c);
-	if (!c->admixture) {
-		/* pseudo-count p_lower_bound on every slot (em_alg.c:972) */
-		k_sum_chunks<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(xb_N(c), 1,
-			c->np, c->p_lb, c->d_Npart);
-		LAUNCH_CHECK("k_sum_chunks");
-		N = c->d_Npart;
-	}
-	k_update_p<<<grid_for(c, (long long)K * c->L, 128), 128, 0, c->stream>>>(
-		N, c->d_p[to], c->d_J, c->d_off, K, c->L, c->T, c->do_proj, c->p_lb);
+	/* the mixture adds the pseudo-count p_lower_bound to every slot
+	 * (em_alg.c:972).  A whole step on one context (mc_em_step) reads the
+	 * chunk sums directly; a split step reads the exchanged totals */
+	const double add = c->admixture ? 0.0 : c->p_lb;
+	if (c->fused_step)
+		k_update_p<<<grid_for(c, (long long)K * c->L, 128), 128, 0, c->stream>>>(
+			c->d_Npart, c->act_chunks, c->np, add, c->d_p[to], c->d_J, c->d_off, K,
+			c->L, c->T, c->do_proj, c->p_lb);
+	else
+		k_update_p<<<grid_for(c, (long long)K * c->L, 128), 128, 0, c->stream>>>(
+			xb_N(c), 1, 0, add, c->d_p[to], c->d_J, c->d_off, K, c->L, c->T,
+			c->do_proj, c->p_lb);
 	LAUNCH_CHECK("k_update_p");
+	c->fused_step = false;
 	if (ll) {
 		CK(cudaMemcpyAsync(ll, xb_ll(c), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
@@ -1439,6 +1494,7 @@ static int init_checks(mc_ctx *c, int slot, const void *arg)
 
 extern "C" int mc_init_admixture_local(mc_ctx *c, int slot, const uint8_t *z)
 {
+	NVTX_FN();
 	int rc = init_checks(c, slot, z);
 	if (rc)
 		return rc;
@@ -1454,6 +1510,7 @@ extern "C" int mc_init_admixture_local(mc_ctx *c, int slot, const uint8_t *z)
 extern "C" int mc_init_admixture_rand_local(mc_ctx *c, int slot, const uint32_t *hist,
 	int64_t n_blocks, int64_t block_draws)
 {
+	NVTX_FN();
 	int rc = init_checks(c, slot, hist);
 	if (rc)
 		return rc;
@@ -1489,14 +1546,20 @@ extern "C" int mc_init_admixture_rand(mc_ctx *c, int slot, const uint32_t *hist,
 
 extern "C" int mc_em_step(mc_ctx *c, int from, int to, double *ll)
 {
+	if (!c)
+		return MC_ERR_ARG;
+	c->fused_step = true;	/* nobody exchanges the allele sums in between */
 	int rc = mc_em_step_local(c, from, to);
-	if (rc)
+	if (rc) {
+		c->fused_step = false;
 		return rc;
+	}
 	return mc_em_step_finish(c, to, ll);
 }
 
 extern "C" int mc_loglik(mc_ctx *c, int slot, double *ll)
 {
+	NVTX_FN();
 	NEED_MODEL();
 	CHECK_SLOT(slot);
 	int rc;
@@ -1577,6 +1640,7 @@ extern "C" int mc_partition(mc_ctx *c, int32_t *I_K, int32_t *count_K)
 
 extern "C" int mc_delta(mc_ctx *c, int which, int pair, int slot_t, int slot_f)
 {
+	NVTX_FN();
 	NEED_MODEL();
 	CHECK_PAIR(pair);
 	CHECK_SLOT(slot_t);
@@ -1598,6 +1662,7 @@ static int fetch_small(mc_ctx *c, double *dst, int off, int n)
 
 extern "C" int mc_step_dots(mc_ctx *c, int pair, double eta_part[3], double p_part[3])
 {
+	NVTX_FN();
 	NEED_MODEL();
 	CHECK_PAIR(pair);
 	double z[3] = { 0, 0, 0 };
@@ -1619,6 +1684,7 @@ extern "C" int mc_step_dots(mc_ctx *c, int pair, double eta_part[3], double p_pa
 
 extern "C" int mc_qn_dots(mc_ctx *c, int q1, int q2, double eta_part[2], double p_part[2])
 {
+	NVTX_FN();
 	NEED_MODEL();
 	CHECK_PAIR(q1);
 	CHECK_PAIR(q2);
@@ -1658,6 +1724,7 @@ extern "C" int mc_project(mc_ctx *c, int slot)
 
 extern "C" int mc_accel_update(mc_ctx *c, int qn1, int slot_t, int slot_p, int pair, double s)
 {
+	NVTX_FN();
 	NEED_MODEL();
 	CHECK_PAIR(pair);
 	CHECK_SLOT(slot_t);
@@ -1676,6 +1743,7 @@ extern "C" int mc_accel_update(mc_ctx *c, int qn1, int slot_t, int slot_p, int p
 extern "C" int mc_qn_update(mc_ctx *c, int slot_t, int slot_p, int uindex,
 	int delta_index, const double *Ainv, const double *cutu)
 {
+	NVTX_FN();
 	NEED_MODEL();
 	CHECK_SLOT(slot_t);
 	CHECK_SLOT(slot_p);

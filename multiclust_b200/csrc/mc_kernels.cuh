@@ -690,9 +690,12 @@ __global__ void k_sum_chunks(const double *Npart, int n_chunks, long long n,
 }
 
 /* p side of both M-steps (em_alg.c:706-752, 965-1010): normalise each (k,l)
- * row of the count sums and project */
-__global__ void k_update_p(const double *N, double *p_t, const int *J,
-	const int *off, int K, int L, long long T, int do_proj, double lb)
+ * row of the count sums and project.  The sums arrive as n_chunks partial
+ * vectors (added in chunk order, exactly like k_sum_chunks) plus the mixture's
+ * pseudo-count `add` on every slot (em_alg.c:972). */
+__global__ void k_update_p(const double *N, int n_chunks, long long chunk_stride,
+	double add, double *p_t, const int *J, const int *off, int K, int L, long long T,
+	int do_proj, double lb)
 {
 	const long long n = (long long)K * L;
 	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
@@ -702,10 +705,16 @@ __global__ void k_update_p(const double *N, double *p_t, const int *J,
 		double *row = p_t + (size_t)k * T + off[l];
 		const int Jl = J[l];
 		double s = 0.0;
+		for (int j = 0; j < Jl; j++) {
+			double t = 0.0;
+			for (int c = 0; c < n_chunks; c++)
+				t += nr[(size_t)c * chunk_stride + j];
+			const double v = add + t;
+			row[j] = v;
+			s += v;
+		}
 		for (int j = 0; j < Jl; j++)
-			s += nr[j];
-		for (int j = 0; j < Jl; j++)
-			row[j] = nr[j] / s;
+			row[j] = row[j] / s;
 		if (do_proj)
 			project_row(row, Jl, lb);
 	}

@@ -117,6 +117,7 @@ int make_options(options **out)
 	opt->n_repeat = 1;
 	opt->write_files = 1;
 	opt->n_gpus = 1;
+	opt->fits_per_gpu = 1;
 	*out = opt;
 	return NO_ERROR;
 }
@@ -224,6 +225,7 @@ void fprint_usage(FILE *fp, const char *cmd)
 "  --device <d>  first CUDA device ordinal (default 0)\n"
 "  --gpus <n>    shard the individuals of one fit over n devices (NCCL exchange)\n"
 "  --shard-fits  with --gpus: deal whole fits (K, initialisation) to the devices\n"
+"  --fits-per-gpu <m>  with --shard-fits: m fits in flight on every device\n"
 "  --trace <f>   write every log likelihood at full precision to <f>\n"
 "  --timing      wall-clock seconds of every phase on stderr\n"
 "  --dump <pre>  binary parameters before / after every fit to <pre>.K*.init*.bin\n"
@@ -332,6 +334,11 @@ int parse_options(options *opt, data *dat, int argc, const char **argv)
 				goto bad_arg;
 			break;
 		case 'f':
+			if (!strncmp(name, "fi", 2)) {	/* --fits-per-gpu */
+				if (read_int_arg(argc, argv, ++i, 1, &opt->fits_per_gpu))
+					goto bad_arg;
+				break;
+			}
 			if (!strncmp(name, "fo", 2))
 				return unsupported(argv[i], "output format of imputed data");
 			if (++i >= argc)
@@ -878,7 +885,7 @@ int main(int argc, const char **argv)
 			FILE_OPEN_ERROR, opt->trace_file);
 		goto done;
 	}
-	if (opt->shard_fits && opt->n_gpus > 1) {
+	if (opt->shard_fits && (opt->n_gpus > 1 || opt->fits_per_gpu > 1)) {
 		err = estimate_model_sharded(opt, dat, mod);
 		if (!err && opt->parallel)
 			printf("%f\n", mod->max_logL);

@@ -98,6 +98,10 @@ struct _options {
 	int shard_fits;			/* --shard-fits: with --gpus N, deal whole fits
 					 * (K, initialisation) to the devices instead of
 					 * sharding the individuals of one fit */
+	int fits_per_gpu;		/* --fits-per-gpu M: fits in flight on every device
+					 * (one host thread, context and stream each): the
+					 * launch latency of one small fit hides behind the
+					 * kernels of the others */
 };
 
 struct _indiv {

@@ -24,8 +24,10 @@
  *      loop uses.  A fit that cannot be a new maximum (its log likelihood does
  *      not exceed every earlier fit of the same worker) does not keep its
  *      parameters.
- * One host thread and one mc_ctx per device (the C ABI's rule), the genotype
- * codes replicated on every device, no collective.  The reference's two
+ * One host thread and one mc_ctx per worker (the C ABI's rule); a device may
+ * carry several workers (--fits-per-gpu), each with its own stream, so that the
+ * launch latency of one small fit hides behind the kernels of the others.  The
+ * genotype codes are replicated for every worker, no collective.  The reference's two
  * exit(0) conditions (NaN, log-likelihood decrease; em_alg.c:113-121) are
  * recorded by the worker and raised by the master when the replay reaches
  * that fit, so everything an aborted sequential run would have written
@@ -141,7 +143,8 @@ static void *worker_main(void *arg)
 		mod->Ainv = calloc((size_t)opt->q * opt->q, sizeof(double));
 		mod->cutu = calloc((size_t)opt->q, sizeof(double));
 	}
-	if (mc_create(&mod->gpus[0], opt->device + w->rank)) {
+	/* workers r, r + n_gpus, ... share device r % n_gpus */
+	if (mc_create(&mod->gpus[0], opt->device + w->rank % opt->n_gpus)) {
 		err = mmessage(ERROR_MSG, GPU_ERROR, "%s\n", mc_last_error(NULL));
 	} else if (mc_set_data(mod->gpus[0], dat.I, dat.L, dat.ploidy,
 			dat.uniquealleles, dat.codes)) {
@@ -283,7 +286,9 @@ int estimate_model_sharded(options *opt, data *dat, model *mod)
 		}
 	*mod->rng = rng;
 
-	pool.n_workers = opt->n_gpus < pool.n_jobs ? opt->n_gpus : pool.n_jobs;
+	pool.n_workers = opt->n_gpus * opt->fits_per_gpu;
+	if (pool.n_workers > pool.n_jobs)
+		pool.n_workers = pool.n_jobs;
 	pthread_mutex_init(&pool.lock, NULL);
 	pthread_cond_init(&pool.cond, NULL);
 	workers = calloc((size_t)pool.n_workers, sizeof *workers);
