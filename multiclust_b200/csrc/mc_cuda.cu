@@ -876,7 +876,8 @@ static int make_plan_dense(mc_ctx *c)
 	a.max_chunk_tiles = max_chunk_tiles;
 	a.I = c->I; a.Ipad = n_itiles * DN_IT; a.T = c->T;
 	c->dn_NB = NB;
-	c->dn_pbits = c->P <= 1 ? 1 : c->P <= 3 ? 2 : c->P <= 7 ? 3 : 4;
+	/* largest allele count the log-likelihood powers must handle */
+	c->dn_pbits = c->P <= 1 ? 1 : c->P <= 3 ? 2 : c->P == 4 ? 4 : c->P <= 7 ? 7 : 15;
 	c->grid_dn = (int)std::min<long long>(a.n_units, sms);
 	int rc;
 	if ((rc = upload(c, c->d_dn_lc_first, lc_first))) return rc;
@@ -892,13 +893,14 @@ static int make_plan_dense(mc_ctx *c)
 
 typedef void (*dense_fn)(const DenseArgs);
 
-template <int NB, int MODE> static dense_fn pick_dn_bits(int pbits)
+template <int NB, int MODE> static dense_fn pick_dn_bits(int pmax)
 {
-	switch (pbits) {
+	switch (pmax) {
 	case 1: return dense_kernel<NB, 1, MODE>;
 	case 2: return dense_kernel<NB, 2, MODE>;
-	case 3: return dense_kernel<NB, 3, MODE>;
 	case 4: return dense_kernel<NB, 4, MODE>;
+	case 7: return dense_kernel<NB, 7, MODE>;
+	case 15: return dense_kernel<NB, 15, MODE>;
 	}
 	return nullptr;
 }

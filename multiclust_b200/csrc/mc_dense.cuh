@@ -169,23 +169,35 @@ __device__ __noinline__ double dn_slow_ll(double t0, double t1, unsigned c0, uns
 	return s;
 }
 
-/* m^c for a mantissa m in [1, 2) and a count c < 2^PBITS */
-template <int PBITS> __device__ __forceinline__ double dn_pow(double m, unsigned c)
+/* m^c for a mantissa m in [1, 2) and a count c <= PMAX (the ploidy) */
+template <int PMAX> __device__ __forceinline__ double dn_pow(double m, unsigned c)
 {
 	double r = (c & 1u) ? m : 1.0;
-	if (PBITS >= 2) {
+	if (PMAX >= 2) {
 		const double m2 = m * m;
 		r = (c & 2u) ? r * m2 : r;
-		if (PBITS >= 3) {
+		if (PMAX >= 4) {
 			const double m4 = m2 * m2;
-			r = (c & 4u) ? r * m4 : r;
-			if (PBITS >= 4) {
-				const double m8 = m4 * m4;
-				r = (c & 8u) ? r * m8 : r;
+			if (PMAX == 4) {	/* c = 4 is the only count with bit 2 set */
+				r = (c & 4u) ? m4 : r;
+			} else {
+				r = (c & 4u) ? r * m4 : r;
+				if (PMAX >= 8) {
+					const double m8 = m4 * m4;
+					r = (c & 8u) ? r * m8 : r;
+				}
 			}
 		}
 	}
 	return r;
+}
+
+/* a count 0..15 as a double.  The conversion instruction runs on the
+ * conversion pipe, which is idle here; the integer-bits-plus-DADD form would
+ * put it on the FP64 pipe, the kernel's bottleneck (measured: +9 % time). */
+__device__ __forceinline__ double dn_count(unsigned c)
+{
+	return (double)c;
 }
 
 /* bytes of dynamic shared memory; the host planner uses the same formula */
@@ -203,7 +215,7 @@ static inline size_t dn_smem_bytes(int NB, int mode, int max_chunk_tiles)
 	return d * sizeof(double) + (size_t)2 * DN_IT * 16;
 }
 
-template <int NB, int PBITS, int MODE>
+template <int NB, int PMAX, int MODE>
 __global__ void __launch_bounds__(DN_THREADS, DN_CTAS_PER_SM) dense_kernel(const DenseArgs a)
 {
 	constexpr int KB = 2 * NB;		/* inner chunks of 4 clusters */
@@ -301,116 +313,126 @@ __global__ void __launch_bounds__(DN_THREADS, DN_CTAS_PER_SM) dense_kernel(const
 
 				const unsigned char *cts = ct + (size_t)buf * DN_IT * 16;
 				const double *pts = pt + (size_t)buf * DN_TL * PL;
-				double G[HAS_G ? 4 : 1][NB][2];
-				if (HAS_G) {
-#pragma unroll
-					for (int lq = 0; lq < 4; lq++)
-#pragma unroll
-						for (int nb = 0; nb < NB; nb++)
-							G[lq][nb][0] = G[lq][nb][1] = 0.0;
-				}
+				/* One locus quad at a time; inside it every phase runs over the
+				 * four groups of 8 individuals, so four independent dependency
+				 * chains are in flight (the warp issues in order). */
 #pragma unroll
 				for (int lq = 0; lq < 4; lq++) {
-					/* p fragments of the locus quad, shared by the four groups */
-					double Bp[HAS_TMP ? KB : 1], BpT[HAS_A ? 2 : 1][NB];
-					if (HAS_TMP) {
+					double G[HAS_G ? 2 : 1][NB][2];	/* two chains: h = 0, 1 */
+					if (HAS_G) {
 #pragma unroll
-						for (int kb = 0; kb < KB; kb++)
-							Bp[kb] = pts[(4 * lq + (r >> 1)) * PL + 2 * (4 * kb + q) + (r & 1)];
-					}
-					if (HAS_A) {
-#pragma unroll
-						for (int al = 0; al < 2; al++)
+						for (int h = 0; h < 2; h++)
 #pragma unroll
 							for (int nb = 0; nb < NB; nb++)
-								BpT[al][nb] = pts[(4 * lq + q) * PL + 2 * (8 * nb + r) + al];
+								G[h][nb][0] = G[h][nb][1] = 0.0;
 					}
-#pragma unroll
-					for (int g = 0; g < 4; g++) {
-						if (MODE == DN_MIX_M) {
-							/* the B fragment straight from the counts: individual
-							 * 4h + q of the group, column r = locus r / 2, allele r % 2 */
-#pragma unroll
-							for (int h = 0; h < 2; h++) {
-								const unsigned cb = cts[(w * 32 + 8 * g + 4 * h + q) * 16
-									+ 4 * lq + (r >> 1)];
-								const double wv = (double)((cb >> ((r & 1) * 4)) & 15u);
-#pragma unroll
-								for (int nb = 0; nb < NB; nb++)
-									dn_mma(G[lq][nb][0], G[lq][nb][1], AeT[g][h][nb], wv);
-							}
-							continue;
-						}
-						const unsigned cb = cts[(w * 32 + 8 * g + r) * 16 + 4 * lq + q];
-						const unsigned c0 = cb & 15u, c1 = cb >> 4;
-						double w0, w1;
-						if (MODE == DN_MIX_E) {
-							w0 = (double)c0;
-							w1 = (double)c1;
-						} else {
-							double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-							for (int kb = 0; kb < KB; kb++)
-								dn_mma(t0, t1, Ae[g][kb], Bp[kb]);
-							/* log likelihood: mantissas multiplied up, exponents
-							 * summed as integers, one log per unit */
-							const int h0 = __double2hiint(t0), h1 = __double2hiint(t1);
-							const bool ok0 = (unsigned)(h0 - 0x00100000) < 0x7fe00000u;
-							const bool ok1 = (unsigned)(h1 - 0x00100000) < 0x7fe00000u;
-							const unsigned f0 = ok0 ? c0 : 0u, f1 = ok1 ? c1 : 0u;
-							const double m0 = __hiloint2double((h0 & 0x000fffff) | 0x3ff00000,
-								__double2loint(t0));
-							const double m1 = __hiloint2double((h1 & 0x000fffff) | 0x3ff00000,
-								__double2loint(t1));
-							prod[g] *= dn_pow<PBITS>(m0, f0) * dn_pow<PBITS>(m1, f1);
-							const int hp = __double2hiint(prod[g]);
-							esum += (int)f0 * ((h0 >> 20) - 1023) + (int)f1 * ((h1 >> 20) - 1023)
-								+ ((hp >> 20) - 1023);
-							prod[g] = __hiloint2double((hp & 0x000fffff) | 0x3ff00000,
-								__double2loint(prod[g]));
-							if ((c0 && !ok0) || (c1 && !ok1))	/* zero, subnormal, inf, nan */
-								ll_slow += dn_slow_ll(t0, t1, ok0 ? 0u : c0, ok1 ? 0u : c1);
-							if (MODE == DN_ADMIX_LL)
-								continue;
-							w0 = c0 ? (double)c0 * mc_rcp(t0) : 0.0;
-							w1 = c1 ? (double)c1 * mc_rcp(t1) : 0.0;
-						}
-						/* A_ik += sum over the quad's loci of w_a p_a */
-#pragma unroll
-						for (int nb = 0; nb < NB; nb++) {
-							dn_mma(CA[g][nb][0], CA[g][nb][1], w0, BpT[0][nb]);
-							dn_mma(CA[g][nb][0], CA[g][nb][1], w1, BpT[1][nb]);
-						}
-						if (MODE == DN_ADMIX_EM)
-							/* the 8 x 8 block of w is transposed through the warp's
-							 * scratch: element (row, col) at row * 8 + (col ^ (row & 2 ? 4 : 0)) */
-							*reinterpret_cast<double2 *>(ws_w + g * 64 + r * 8 + ((2 * q) ^ ((r & 2) << 1)))
-								= make_double2(w0, w1);
-					}
-					if (MODE == DN_ADMIX_EM) {
-						__syncwarp();
+					if (MODE == DN_MIX_M) {
+						/* the B fragment straight from the counts: individual
+						 * 4h + q of the group, column r = locus r / 2, allele r % 2 */
 #pragma unroll
 						for (int g = 0; g < 4; g++)
 #pragma unroll
 							for (int h = 0; h < 2; h++) {
-								const int row = 4 * h + q;
-								const double wv = ws_w[g * 64 + row * 8 + (r ^ ((row & 2) << 1))];
+								const unsigned cb = cts[(w * 32 + 8 * g + 4 * h + q) * 16
+									+ 4 * lq + (r >> 1)];
+								const double wv = dn_count((cb >> ((r & 1) * 4)) & 15u);
 #pragma unroll
 								for (int nb = 0; nb < NB; nb++)
-									dn_mma(G[lq][nb][0], G[lq][nb][1], AeT[g][h][nb], wv);
+									dn_mma(G[h][nb][0], G[h][nb][1], AeT[g][h][nb], wv);
 							}
-						__syncwarp();	/* the next quad overwrites the scratch */
+					} else {
+						/* p fragments of the locus quad, shared by the four groups */
+						double Bp[HAS_TMP ? KB : 1], BpT[HAS_A ? 2 : 1][NB];
+						if (HAS_TMP) {
+#pragma unroll
+							for (int kb = 0; kb < KB; kb++)
+								Bp[kb] = pts[(4 * lq + (r >> 1)) * PL + 2 * (4 * kb + q) + (r & 1)];
+						}
+						if (HAS_A) {
+#pragma unroll
+							for (int al = 0; al < 2; al++)
+#pragma unroll
+								for (int nb = 0; nb < NB; nb++)
+									BpT[al][nb] = pts[(4 * lq + q) * PL + 2 * (8 * nb + r) + al];
+						}
+						/* group after group: the DMMAs of one group (16 clocks of the
+						 * pipe each) are spaced by its own element-wise work, which
+						 * keeps the in-order warp issuing while the pipe is busy */
+#pragma unroll
+						for (int g = 0; g < 4; g++) {
+							const unsigned cb = cts[(w * 32 + 8 * g + r) * 16 + 4 * lq + q];
+							const unsigned c0 = cb & 15u, c1 = cb >> 4;
+							double w0, w1;
+							if (MODE == DN_MIX_E) {
+								w0 = dn_count(c0);
+								w1 = dn_count(c1);
+							} else {
+								double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+								for (int kb = 0; kb < KB; kb++)
+									dn_mma(t0, t1, Ae[g][kb], Bp[kb]);
+								/* log likelihood: mantissas multiplied up, exponents
+								 * summed as integers, one log per unit */
+								const int h0 = __double2hiint(t0), h1 = __double2hiint(t1);
+								const bool ok0 = (unsigned)(h0 - 0x00100000) < 0x7fe00000u;
+								const bool ok1 = (unsigned)(h1 - 0x00100000) < 0x7fe00000u;
+								const unsigned f0 = ok0 ? c0 : 0u, f1 = ok1 ? c1 : 0u;
+								const double m0 = __hiloint2double((h0 & 0x000fffff) | 0x3ff00000,
+									__double2loint(t0));
+								const double m1 = __hiloint2double((h1 & 0x000fffff) | 0x3ff00000,
+									__double2loint(t1));
+								prod[g] *= dn_pow<PMAX>(m0, f0) * dn_pow<PMAX>(m1, f1);
+								const int hp = __double2hiint(prod[g]);
+								esum += (int)f0 * ((h0 >> 20) - 1023) + (int)f1 * ((h1 >> 20) - 1023)
+									+ ((hp >> 20) - 1023);
+								prod[g] = __hiloint2double((hp & 0x000fffff) | 0x3ff00000,
+									__double2loint(prod[g]));
+								if ((c0 && !ok0) || (c1 && !ok1))	/* zero, subnormal, inf, nan */
+									ll_slow += dn_slow_ll(t0, t1, ok0 ? 0u : c0, ok1 ? 0u : c1);
+								if (MODE == DN_ADMIX_LL)
+									continue;
+								w0 = c0 ? dn_count(c0) * mc_rcp(t0) : 0.0;
+								w1 = c1 ? dn_count(c1) * mc_rcp(t1) : 0.0;
+							}
+							/* A_ik += sum over the quad's loci of w_a p_a */
+#pragma unroll
+							for (int nb = 0; nb < NB; nb++) {
+								dn_mma(CA[g][nb][0], CA[g][nb][1], w0, BpT[0][nb]);
+								dn_mma(CA[g][nb][0], CA[g][nb][1], w1, BpT[1][nb]);
+							}
+							if (MODE == DN_ADMIX_EM)
+								/* the 8 x 8 block of w is transposed through the warp's
+								 * scratch: element (row, col) at row * 8 + (col ^ (row & 2 ? 4 : 0)) */
+								*reinterpret_cast<double2 *>(ws_w + g * 64 + r * 8
+									+ ((2 * q) ^ ((r & 2) << 1))) = make_double2(w0, w1);
+						}
+						if (MODE == DN_ADMIX_EM) {
+							__syncwarp();
+#pragma unroll
+							for (int g = 0; g < 4; g++)
+#pragma unroll
+								for (int h = 0; h < 2; h++) {
+									const int row = 4 * h + q;
+									const double wv = ws_w[g * 64 + row * 8 + (r ^ ((row & 2) << 1))];
+#pragma unroll
+									for (int nb = 0; nb < NB; nb++)
+										dn_mma(G[h][nb][0], G[h][nb][1], AeT[g][h][nb], wv);
+								}
+							__syncwarp();	/* the next quad overwrites the scratch */
+						}
+					}
+					/* the warp's G fragment of this quad goes to the fold scratch */
+					if (HAS_G) {
+#pragma unroll
+						for (int nb = 0; nb < NB; nb++)
+							*reinterpret_cast<double2 *>(scr + (((size_t)w * NB + nb) * 4 + lq) * 64
+								+ lane * 2) = make_double2(G[0][nb][0] + G[1][nb][0],
+								G[0][nb][1] + G[1][nb][1]);
 					}
 				}
 				if (!HAS_G)
 					continue;
 				/* ---- the warps' G fragments, added in warp order ---- */
-#pragma unroll
-				for (int nb = 0; nb < NB; nb++)
-#pragma unroll
-					for (int lq = 0; lq < 4; lq++)
-						*reinterpret_cast<double2 *>(scr + (((size_t)w * NB + nb) * 4 + lq) * 64 + lane * 2)
-							= make_double2(G[lq][nb][0], G[lq][nb][1]);
 				__syncthreads();
 #pragma unroll
 				for (int nb = 0; nb < NB; nb++) {

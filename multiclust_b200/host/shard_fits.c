@@ -37,6 +37,7 @@
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "multiclust.h"
 
@@ -70,7 +71,15 @@ typedef struct {
 	fit_pool *pool;
 	int rank;
 	pthread_t thread;
+	double t_ready, t_done;		/* --timing: context + data up, last fit finished */
 } fit_worker;
+
+static double now_s(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 static void job_release(fit_job *job)
 {
@@ -151,6 +160,7 @@ static void *worker_main(void *arg)
 		err = mmessage(ERROR_MSG, GPU_ERROR, "%s\n", mc_last_error(mod->gpus[0]));
 	}
 	mod->gpu = mod->gpus[0];
+	w->t_ready = now_s();
 
 	/* jobs are dealt round-robin, so a worker sees its jobs in run order */
 	for (int j = w->rank; j < pool->n_jobs; j += pool->n_workers) {
@@ -223,6 +233,7 @@ static void *worker_main(void *arg)
 		pthread_cond_broadcast(&pool->cond);
 		pthread_mutex_unlock(&pool->lock);
 	}
+	w->t_done = now_s();
 	if (K_alloc)
 		free_model_data(mod, opt);
 	if (mod->gpus[0])
@@ -286,6 +297,7 @@ int estimate_model_sharded(options *opt, data *dat, model *mod)
 		}
 	*mod->rng = rng;
 
+	const double t_start = now_s();
 	pool.n_workers = opt->n_gpus * opt->fits_per_gpu;
 	if (pool.n_workers > pool.n_jobs)
 		pool.n_workers = pool.n_jobs;
@@ -374,6 +386,18 @@ int estimate_model_sharded(options *opt, data *dat, model *mod)
 	}
 	for (int r = 0; r < pool.n_workers; r++)
 		pthread_join(workers[r].thread, NULL);
+	if (opt->timing) {
+		double ready = 0, done = 0;
+		for (int r = 0; r < pool.n_workers; r++) {
+			if (workers[r].t_ready - t_start > ready)
+				ready = workers[r].t_ready - t_start;
+			if (workers[r].t_done - t_start > done)
+				done = workers[r].t_done - t_start;
+		}
+		fprintf(stderr, "timing (s): %d workers on %d devices: contexts + data up after "
+			"%.3f, %d fits done after %.3f (fits phase %.3f)\n", pool.n_workers,
+			opt->n_gpus, ready, pool.n_jobs, done, done - ready);
+	}
 	for (j = 0; j < pool.n_jobs; j++)
 		job_release(&pool.jobs[j]);
 	free(workers);

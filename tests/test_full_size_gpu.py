@@ -122,3 +122,92 @@ def test_mid_size_against_oracle(orc, tmp_path):
     assert np.max(np.abs(eg - eo)) < 1e-11 and np.max(np.abs(pg - po)) < 1e-11
     assert np.max(np.abs(ctx.posterior() - fit.posterior())) < 1e-9
     ctx.close()
+
+
+# ---- the biallelic configurations at full size (dense DMMA kernels) ----
+
+def _start(ctx, K, per_indiv, seed):
+    rng = np.random.default_rng(seed)
+    J = ctx.get_J()
+    T = int(J.sum())
+    eta = rng.random((ctx.I if per_indiv else 1, K)) + 0.1
+    eta /= eta.sum(axis=1, keepdims=True)
+    p = rng.random((K, T)) + 0.1
+    seg = np.repeat(np.arange(len(J)), J)
+    for k in range(K):
+        p[k] /= np.bincount(seg, weights=p[k], minlength=len(J))[seg]
+    return eta.ravel(), p.ravel(), J, seg
+
+
+def test_config2_full_size_properties():
+    """BASELINE configs[1]: mixture, I=10k, L=5k biallelic, K=5, diploid.  Properties:
+    EM ascent, loglik == next step's value, rows on the simplex, posterior rows sum
+    to one, determinism."""
+    from multiclust_b200 import Context, SynthParams
+    I2, L2, K2 = 10000, 5000, 5
+    ctx = Context(0)
+    try:
+        ctx.set_data_synth(I2, L2, SynthParams(seed=20261018, K=K2, jmax=2, miss_bp=0, ploidy=2))
+        lb = min(1e-8, 0.5 / I2 / 2)
+        ctx.alloc_model(K2, admixture=0, q=0, eta_lb=lb, p_lb=lb)
+        assert ctx.plan()["two_pass"] == 3
+        eta0, p0, J, seg = _start(ctx, K2, False, 5)
+        runs = []
+        for rep in range(2):
+            ctx.set_params(0, eta0, p0)
+            pre = ctx.loglik(0)
+            lls = [ctx.em_step(0, 0) for _ in range(4)]
+            runs.append((pre, lls, ctx.get_params(0), ctx.posterior()))
+        pre, lls, (eta, p), v = runs[0]
+        assert np.all(np.isfinite(lls))
+        assert abs(pre - lls[0]) <= 1e-12 * abs(pre)
+        assert all(b > a for a, b in zip(lls, lls[1:]))
+        assert abs(eta.sum() - 1.0) < 1e-12 and eta.min() >= lb
+        p = p.reshape(K2, -1)
+        rows = np.stack([np.bincount(seg, weights=p[k], minlength=len(J)) for k in range(K2)])
+        assert np.max(np.abs(rows[:, J > 0] - 1.0)) < 1e-12 and p.min() >= lb
+        assert np.max(np.abs(v.sum(axis=1) - 1.0)) < 1e-12
+        assert runs[1][1] == lls and np.array_equal(runs[1][2][1], runs[0][2][1])
+        assert np.array_equal(runs[1][3], v)
+    finally:
+        ctx.close()
+
+
+def test_config5_share_properties():
+    """one GPU's share of BASELINE configs[4] (I=1M / 8 = 125k tetraploid individuals,
+    L=50k biallelic loci, K=8) on the dense kernels: EM ascent, loglik == next step's
+    value, simplex rows, sum_k D_ik = non-missing copies, determinism."""
+    from multiclust_b200 import Context, SynthParams
+    I5, L5, K5, P5 = 125000, 50000, 8, 4
+    ctx = Context(0)
+    try:
+        ctx.set_data_synth(I5, L5, SynthParams(seed=20261018, K=K5, jmax=2, miss_bp=100, ploidy=P5))
+        lb = min(1e-8, 0.5 / (8 * I5) / P5)
+        ctx.alloc_model(K5, admixture=1, q=0, eta_lb=lb, p_lb=lb)
+        assert ctx.plan()["two_pass"] == 3
+        eta0, p0, J, seg = _start(ctx, K5, True, 9)
+        runs = []
+        for rep in range(2):
+            ctx.set_params(0, eta0, p0)
+            pre = ctx.loglik(0)
+            lls = [ctx.em_step(0, 0) for _ in range(3)]
+            runs.append((pre, lls, ctx.get_params(0), ctx.posterior()))
+        pre, lls, (eta, p), D = runs[0]
+        assert np.all(np.isfinite(lls))
+        assert abs(pre - lls[0]) <= 1e-12 * abs(pre)
+        assert all(b > a for a, b in zip(lls, lls[1:]))
+        eta = eta.reshape(I5, K5)
+        assert np.max(np.abs(eta.sum(axis=1) - 1.0)) < 1e-12 and eta.min() >= lb
+        p = p.reshape(K5, -1)
+        rows = np.stack([np.bincount(seg, weights=p[k], minlength=len(J)) for k in range(K5)])
+        assert np.max(np.abs(rows[:, J > 0] - 1.0)) < 1e-12 and p.min() >= lb
+        # every non-missing copy is shared out completely (checked on a slice: the
+        # natural codes of the whole share are 25 GB)
+        D = D.reshape(I5, K5)
+        assert np.max(np.abs(D.sum(axis=1) - np.round(D.sum(axis=1)))) < 1e-6
+        assert D.sum(axis=1).max() <= L5 * P5 + 1e-6
+        assert runs[1][1] == lls
+        assert np.array_equal(runs[1][2][0], runs[0][2][0])
+        assert np.array_equal(runs[1][2][1], runs[0][2][1])
+    finally:
+        ctx.close()

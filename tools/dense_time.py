@@ -60,7 +60,8 @@ if __name__ == "__main__":
     kernel = 0
     if "--kernel" in args:
         kernel = int(args[args.index("--kernel") + 1])
-    if not args or "c2" in args:
-        run("C2 mixture", 10000, 5000, 5, 2, 0, kernel, steps=20)
-    if not args or "c5" in args:
-        run("C5 share admixture", 125000, 50000, 8, 4, 1, kernel, steps=5)
+    steps = int(args[args.index("--steps") + 1]) if "--steps" in args else 0
+    if "c2" in args or not [x for x in args if x in ("c2", "c5")]:
+        run("C2 mixture", 10000, 5000, 5, 2, 0, kernel, steps=steps or 20)
+    if "c5" in args or not [x for x in args if x in ("c2", "c5")]:
+        run("C5 share admixture", 125000, 50000, 8, 4, 1, kernel, steps=steps or 5)
