@@ -138,6 +138,26 @@ int mc_init_admixture_rand(mc_ctx *ctx, int slot, const uint32_t *hist,
 int mc_init_admixture_rand_local(mc_ctx *ctx, int slot, const uint32_t *hist,
 	int64_t n_blocks, int64_t block_draws);
 
+/* random_initialize_mixture (rnd_init.c:192-339) with the I*K*L distance work
+ * on the device.  The host draws the K distinct centre
+ * individuals from its rand() stream (rnd_init.c:205-217; K draws plus
+ * re-draws on collision) and hands over their genotype rows: center_codes is
+ * a HOST array [K][L][P]; center_idx[k] is the centre's row among THIS
+ * context's individuals, or -1 when it lives in another shard.  Every
+ * individual joins the nearest centre by the L1 distance of the allele counts
+ * (integers: the strict "smaller wins, first on ties" rule is exact), a centre
+ * keeps its own cluster; then eta_k = (1 + n_k) / (I + K) and p_klj
+ * proportional to 1 + (K - k) S_klj, row-normalised, go to `slot` (no
+ * projection, like the reference).  The _local / _finish pair splits the call
+ * for individual-sharded fits exactly like mc_em_step: the counts and cluster
+ * sizes are summed over ranks through the exchange buffer in between;
+ * I_total is the number of individuals over all shards.  K == 1: everybody in
+ * cluster 0, the centre arguments may be NULL. */
+int mc_init_mixture(mc_ctx *ctx, int slot, const int32_t *center_idx,
+	const uint8_t *center_codes);
+int mc_init_mixture_local(mc_ctx *ctx, const int32_t *center_idx, const uint8_t *center_codes);
+int mc_init_mixture_finish(mc_ctx *ctx, int slot, int64_t I_total);
+
 /* ---- the hot path ------------------------------------------------------ */
 
 /* E-step on slot `from`, M-step (+ simplex projection) into slot `to`;
@@ -159,6 +179,11 @@ int mc_read_ll(mc_ctx *ctx, double *ll);
 /* Posterior sums of the last E-step: D_ik = sum_{l,j} d_iklj (admixture, what
  * write_file.c:359-381,446-459,525-543 reduce diklm to) or v_ik (mixture). */
 int mc_get_posterior(mc_ctx *ctx, double *out);
+/* Sums of the posterior rows (D_ik or v_ik) over the individuals of every
+ * sampling locale, the numerators of the popq tables (write_file.c:446-459,
+ * 658-666): `locale` is a HOST array [I] of 0..n_locales-1 for this context's
+ * individuals, `out` a HOST array [n_locales][K].  Fixed summation order. */
+int mc_locale_sums(mc_ctx *ctx, const int32_t *locale, int32_t n_locales, double *out);
 /* argmax partition on device (write_file.c:350-382, 582-600) */
 int mc_partition(mc_ctx *ctx, int32_t *I_K, int32_t *count_K);
 

@@ -15,8 +15,8 @@ SYMBOLS = [
     "mc_last_error", "mc_abi_version", "mc_create", "mc_destroy",
     "mc_set_stream", "mc_sync", "mc_ctx_device", "mc_ctx_stream", "mc_set_data", "mc_set_data_synth",
     "mc_get_dims", "mc_get_J", "mc_get_codes", "mc_alloc_model", "mc_eta_len",
-    "mc_set_params", "mc_get_params", "mc_init_admixture", "mc_init_admixture_local", "mc_init_admixture_rand", "mc_init_admixture_rand_local", "mc_em_step", "mc_loglik", "mc_read_ll",
-    "mc_get_posterior", "mc_partition", "mc_delta", "mc_step_dots",
+    "mc_set_params", "mc_get_params", "mc_init_admixture", "mc_init_admixture_local", "mc_init_admixture_rand", "mc_init_admixture_rand_local", "mc_init_mixture", "mc_init_mixture_local", "mc_init_mixture_finish", "mc_em_step", "mc_loglik", "mc_read_ll",
+    "mc_get_posterior", "mc_partition", "mc_locale_sums", "mc_delta", "mc_step_dots",
     "mc_qn_dots", "mc_accel_update", "mc_qn_update", "mc_project",
     "mc_copy_slot", "mc_em_step_local", "mc_exchange_buffer",
     "mc_em_step_finish", "mc_exchange_sum", "mc_exchange_sum_slice", "mc_get_plan", "mc_launch_count",
@@ -94,11 +94,15 @@ def load_library():
     L.mc_init_admixture_local.argtypes = [vp, C.c_int, vp]
     L.mc_init_admixture_rand.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int64]
     L.mc_init_admixture_rand_local.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int64]
+    L.mc_init_mixture.argtypes = [vp, C.c_int, vp, vp]
+    L.mc_init_mixture_local.argtypes = [vp, vp, vp]
+    L.mc_init_mixture_finish.argtypes = [vp, C.c_int, C.c_int64]
     L.mc_em_step.argtypes = [vp, C.c_int, C.c_int, dp]
     L.mc_loglik.argtypes = [vp, C.c_int, dp]
     L.mc_read_ll.argtypes = [vp, dp]
     L.mc_get_posterior.argtypes = [vp, vp]
     L.mc_partition.argtypes = [vp, vp, vp]
+    L.mc_locale_sums.argtypes = [vp, vp, C.c_int32, vp]
     L.mc_delta.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.mc_step_dots.argtypes = [vp, C.c_int, dp, dp]
     L.mc_qn_dots.argtypes = [vp, C.c_int, C.c_int, dp, dp]
@@ -231,6 +235,14 @@ class Context:
         self._ck(self.lib.mc_init_admixture_rand(self.h, slot, _ptr(hist), hist.shape[0],
                                                  int(block_draws)), "mc_init_admixture_rand")
 
+    def init_mixture(self, slot, center_idx, center_codes):
+        """mixture initialiser with the distance work on the device; the host
+        draws the centres"""
+        ci = np.ascontiguousarray(center_idx, dtype=np.int32)
+        cc = np.ascontiguousarray(center_codes, dtype=np.uint8)
+        assert ci.size == self.K and cc.size == self.K * self.L * self.P
+        self._ck(self.lib.mc_init_mixture(self.h, slot, _ptr(ci), _ptr(cc)), "mc_init_mixture")
+
     # -- hot path
     def em_step(self, frm=0, to=0):
         ll = C.c_double()
@@ -294,6 +306,14 @@ class Context:
         cnt = np.empty(self.K, dtype=np.int32)
         self._ck(self.lib.mc_partition(self.h, _ptr(ik), _ptr(cnt)), "mc_partition")
         return ik, cnt
+
+    def locale_sums(self, locale, n_locales):
+        locale = np.ascontiguousarray(locale, dtype=np.int32)
+        assert locale.size == self.I
+        out = np.empty((n_locales, self.K))
+        self._ck(self.lib.mc_locale_sums(self.h, _ptr(locale), n_locales, _ptr(out)),
+                 "mc_locale_sums")
+        return out
 
     def delta(self, which, pair, slot_t, slot_f):
         self._ck(self.lib.mc_delta(self.h, which, pair, slot_t, slot_f), "mc_delta")

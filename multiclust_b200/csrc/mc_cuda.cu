@@ -1546,6 +1546,76 @@ extern "C" int mc_init_admixture_rand(mc_ctx *c, int slot, const uint32_t *hist,
 	return rc;
 }
 
+/* mixture initialiser (rnd_init.c:192-339): nearest-centre assignment of this
+ * context's individuals and the cluster's allele counts, left in the exchange
+ * buffer [K*T counts | - | K cluster sizes] */
+extern "C" int mc_init_mixture_local(mc_ctx *c, const int32_t *center_idx,
+	const uint8_t *center_codes)
+{
+	NVTX_FN();
+	NEED_MODEL();
+	if (c->admixture)
+		return fail(c, MC_ERR_STATE, "mc_init_mixture: not a mixture model");
+	if (c->K > 1 && (!center_idx || !center_codes))
+		return fail(c, MC_ERR_ARG, "mc_init_mixture: null argument");
+	const int K = c->K;
+	const size_t np = (size_t)std::max<int64_t>(c->np, 1), row = (size_t)c->L * c->P;
+	int rc = init_scratch(c, c->d_init_N, c->init_N_n, np);
+	if (rc)
+		return rc;
+	unsigned char *d_cent = nullptr;
+	int *d_cidx = nullptr;
+	unsigned *d_nk = nullptr;
+	CK(MC_DEV_MALLOC(&d_cent, std::max<size_t>(row * K, 1)));
+	CK(MC_DEV_MALLOC(&d_cidx, sizeof(int) * K));
+	CK(MC_DEV_MALLOC(&d_nk, sizeof(unsigned) * K));
+	std::vector<int> none((size_t)K, -1);
+	CK(cudaMemcpyAsync(d_cidx, K > 1 ? center_idx : none.data(), sizeof(int) * K,
+		cudaMemcpyHostToDevice, c->stream));
+	if (K > 1)
+		CK(cudaMemcpyAsync(d_cent, center_codes, row * K, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemsetAsync(d_nk, 0, sizeof(unsigned) * K, c->stream));
+	CK(cudaMemsetAsync(c->d_init_N, 0, sizeof(unsigned) * np, c->stream));
+	const unsigned grid = (unsigned)std::min<long long>(std::max<long long>(c->I, 1),
+		(long long)c->num_sms * 32);
+	k_mix_assign<<<grid, 128, 0, c->stream>>>(c->d_nat, d_cent, d_cidx, c->I, c->L, c->P, K,
+		c->d_IK, d_nk);
+	LAUNCH_CHECK("k_mix_assign");
+	k_mix_init_counts<<<grid, 128, 0, c->stream>>>(c->d_nat, c->d_IK, c->I, c->L, c->P,
+		c->d_off, c->T, c->d_init_N);
+	LAUNCH_CHECK("k_mix_init_counts");
+	k_u32_to_f64<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_init_N, xb_N(c), c->np);
+	LAUNCH_CHECK("k_u32_to_f64");
+	k_u32_to_f64<<<1, 32, 0, c->stream>>>(d_nk, xb_S(c), K);
+	LAUNCH_CHECK("k_u32_to_f64");
+	CK(cudaStreamSynchronize(c->stream));	/* the host arrays are the caller's again */
+	cudaFree(d_cent); cudaFree(d_cidx); cudaFree(d_nk);
+	return MC_OK;
+}
+
+extern "C" int mc_init_mixture_finish(mc_ctx *c, int slot, int64_t I_total)
+{
+	NEED_MODEL();
+	CHECK_SLOT(slot);
+	if (c->admixture)
+		return fail(c, MC_ERR_STATE, "mc_init_mixture: not a mixture model");
+	k_mix_init_finish<<<grid_for(c, (long long)c->K * c->L, 128), 128, 0, c->stream>>>(xb_N(c),
+		xb_S(c), c->d_eta[slot], c->d_p[slot], c->d_J, c->d_off, c->K, c->L, c->T, I_total);
+	LAUNCH_CHECK("k_mix_init_finish");
+	return MC_OK;
+}
+
+extern "C" int mc_init_mixture(mc_ctx *c, int slot, const int32_t *center_idx,
+	const uint8_t *center_codes)
+{
+	int rc = mc_init_mixture_local(c, center_idx, center_codes);
+	if (rc)
+		return rc;
+	rc = mc_init_mixture_finish(c, slot, c->I);
+	CK(cudaStreamSynchronize(c->stream));
+	return rc;
+}
+
 extern "C" int mc_em_step(mc_ctx *c, int from, int to, double *ll)
 {
 	if (!c)
@@ -1609,6 +1679,29 @@ extern "C" int mc_get_posterior(mc_ctx *c, double *out)
 	CK(cudaMemcpyAsync(out, c->d_post, sizeof(double) * (size_t)c->I * c->K,
 		cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
+	return MC_OK;
+}
+
+extern "C" int mc_locale_sums(mc_ctx *c, const int32_t *locale, int32_t n_locales, double *out)
+{
+	NEED_MODEL();
+	if (!locale || !out || n_locales < 1)
+		return fail(c, MC_ERR_ARG, "mc_locale_sums: bad arguments");
+	const int n = n_locales * c->K;
+	const int blocks = (int)((c->I + LS_ROWS - 1) / LS_ROWS);
+	int *d_loc = nullptr;
+	double *d_part = nullptr, *d_out = nullptr;
+	CK(MC_DEV_MALLOC(&d_loc, sizeof(int) * (size_t)c->I));
+	CK(MC_DEV_MALLOC(&d_part, sizeof(double) * (size_t)blocks * n));
+	CK(MC_DEV_MALLOC(&d_out, sizeof(double) * (size_t)n));
+	CK(cudaMemcpyAsync(d_loc, locale, sizeof(int) * (size_t)c->I, cudaMemcpyHostToDevice, c->stream));
+	k_locale_partial<<<blocks, 256, 0, c->stream>>>(c->d_post, d_loc, c->I, c->K, n_locales, d_part);
+	LAUNCH_CHECK("k_locale_partial");
+	k_locale_final<<<(n + 127) / 128, 128, 0, c->stream>>>(d_part, blocks, n, d_out);
+	LAUNCH_CHECK("k_locale_final");
+	CK(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	cudaFree(d_loc); cudaFree(d_part); cudaFree(d_out);
 	return MC_OK;
 }
 

@@ -856,6 +856,40 @@ __global__ void k_partition(const double *post, long long I, int K, int *I_K)
 	}
 }
 
+/* sums of the posterior rows over the individuals of every sampling locale
+ * (write_file.c:446-459, 658-666: the popq tables).  Block b owns LS_ROWS
+ * consecutive individuals; thread (locale, k) adds its block's rows in index
+ * order, a second kernel adds the block sums in block order: deterministic. */
+#define LS_ROWS 256
+__global__ void k_locale_partial(const double *post, const int *locale, long long I, int K,
+	int n_loc, double *part /* [blocks][n_loc * K] */)
+{
+	__shared__ int loc_s[LS_ROWS];
+	const long long i0 = (long long)blockIdx.x * LS_ROWS;
+	const int rows = (int)(I - i0 < LS_ROWS ? I - i0 : LS_ROWS);
+	for (int x = threadIdx.x; x < rows; x += blockDim.x)
+		loc_s[x] = locale[i0 + x];
+	__syncthreads();
+	for (int x = threadIdx.x; x < n_loc * K; x += blockDim.x) {
+		const int n = x / K, k = x - n * K;
+		double s = 0.0;
+		for (int j = 0; j < rows; j++)
+			if (loc_s[j] == n)
+				s += post[(size_t)(i0 + j) * K + k];
+		part[(size_t)blockIdx.x * n_loc * K + x] = s;
+	}
+}
+
+__global__ void k_locale_final(const double *part, int blocks, int n, double *out)
+{
+	for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) {
+		double s = 0.0;
+		for (int b = 0; b < blocks; b++)
+			s += part[(size_t)b * n + x];
+		out[x] = s;
+	}
+}
+
 /* ------------------------------------------------------------------ */
 /* admixture initialiser (rnd_init.c:456-482): hard assignment counts     */
 
@@ -938,6 +972,133 @@ __global__ void k_rand_assign(const unsigned *hist, long long n_blocks, long lon
 			if (++f == 31)
 				f = 0;
 		}
+	}
+}
+
+/* ------------------------------------------------------------------ */
+/* mixture initialiser (rnd_init.c:192-339) on the device                 */
+
+/* L1 distance between the allele-count vectors of two genotypes at one locus
+ * (rnd_init.c:238-247), from the codes: sum_j |n_a(j) - n_b(j)| over the
+ * alleles either of them carries.  Integer, so the comparison below is exact. */
+__device__ __forceinline__ int locus_distance(const unsigned char *ca, const unsigned char *cb, int P)
+{
+	int d = 0;
+	for (int x = 0; x < P; x++) {
+		if (ca[x] == MC_MISSING)
+			continue;
+		bool first = true;
+		for (int y = 0; y < x; y++)
+			first &= ca[y] != ca[x];
+		if (!first)
+			continue;
+		int na = 0, nb = 0;
+		for (int y = 0; y < P; y++) {
+			na += ca[y] == ca[x];
+			nb += cb[y] == ca[x];
+		}
+		d += abs(na - nb);
+	}
+	for (int x = 0; x < P; x++) {	/* alleles only b carries */
+		if (cb[x] == MC_MISSING)
+			continue;
+		bool first = true, in_a = false;
+		int nb = 0;
+		for (int y = 0; y < x; y++)
+			first &= cb[y] != cb[x];
+		for (int y = 0; y < P; y++) {
+			in_a |= ca[y] == cb[x];
+			nb += cb[y] == cb[x];
+		}
+		if (first && !in_a)
+			d += nb;
+	}
+	return d;
+}
+
+/* nearest centre of every individual, strictly smaller distance wins, centres
+ * keep their own cluster (rnd_init.c:220-258); one CTA per individual, threads
+ * stride over the loci; also counts the cluster sizes */
+__global__ void k_mix_assign(const unsigned char *nat, const unsigned char *centers,
+	const int *center_idx, long long I, int L, int P, int K, int *part, unsigned *nk)
+{
+	__shared__ int red[32];
+	const size_t row = (size_t)L * P;
+	for (long long i = blockIdx.x; i < I; i += gridDim.x) {
+		int mine = -1;		/* a centre keeps the first cluster it is the centre of */
+		for (int k = K - 1; k >= 0; k--)
+			if (center_idx[k] == i)
+				mine = k;
+		long long best = -1;
+		int bk = 0;
+		if (K > 1 && !(mine == 0)) {
+			for (int k = 0; k < K; k++) {
+				if (mine == k) {	/* uniform over the block */
+					bk = k;
+					break;
+				}
+				int d = 0;
+				for (int l = threadIdx.x; l < L; l += blockDim.x)
+					d += locus_distance(nat + (size_t)i * row + (size_t)l * P,
+						centers + (size_t)k * row + (size_t)l * P, P);
+				for (int m = 16; m >= 1; m >>= 1)
+					d += __shfl_xor_sync(0xffffffffu, d, m);
+				__syncthreads();
+				if ((threadIdx.x & 31) == 0)
+					red[threadIdx.x >> 5] = d;
+				__syncthreads();
+				long long tot = 0;
+				for (int w = 0; w < (int)(blockDim.x >> 5); w++)
+					tot += red[w];
+				if (best < 0 || tot < best) {
+					best = tot;
+					bk = k;
+				}
+			}
+		}
+		if (threadIdx.x == 0) {
+			part[i] = bk;
+			atomicAdd(&nk[bk], 1u);
+		}
+		__syncthreads();
+	}
+}
+
+/* allele counts of every cluster (rnd_init.c:296-318): every observed copy adds one */
+__global__ void k_mix_init_counts(const unsigned char *nat, const int *part, long long I,
+	int L, int P, const int *off, long long T, unsigned *N /* [K][T] */)
+{
+	for (long long i = blockIdx.x; i < I; i += gridDim.x) {
+		const int k = part[i];
+		for (int l = threadIdx.x; l < L; l += blockDim.x) {
+			const unsigned char *c = nat + ((size_t)i * L + l) * P;
+			for (int ap = 0; ap < P; ap++)
+				if (c[ap] != MC_MISSING)
+					atomicAdd(&N[(size_t)k * T + off[l] + c[ap]], 1u);
+		}
+	}
+}
+
+/* eta_k = (1 + n_k) / (I + K); p_klj = (1 + (K - k) S_klj) / sum_j (...)
+ * (rnd_init.c:274-338), from the summed counts */
+__global__ void k_mix_init_finish(const double *S, const double *nk, double *eta_t, double *p_t,
+	const int *J, const int *off, int K, int L, long long T, long long I_total)
+{
+	const long long n = (long long)K * L;
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		const int k = (int)(x / L), l = (int)(x % L);
+		const double *sr = S + (size_t)k * T + off[l];
+		double *row = p_t + (size_t)k * T + off[l];
+		double sum = 0.0;
+		for (int m = 0; m < J[l]; m++) {
+			row[m] = 1.0 + (K - k) * sr[m];
+			sum += row[m];
+		}
+		for (int m = 0; m < J[l]; m++)
+			row[m] /= sum;
+		if (l == 0)
+			eta_t[k] = (1.0 + nk[k]) / (double)(I_total + K);
 	}
 }
 

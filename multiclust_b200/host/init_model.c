@@ -81,68 +81,22 @@ static int random_initialize_admixture(options *opt, data *dat, model *mod)
 	return NO_ERROR;
 }
 
-/* L1 distance between the allele-count vectors of two individuals at all loci
- * (rnd_init.c:238-247), computed from the codes: at one locus it is
- * sum_j |n_a(j) - n_b(j)| over the alleles either of them carries */
-static double count_distance(const data *dat, int a, int b)
-{
-	const int P = dat->ploidy, L = dat->L;
-	const uint8_t *ca = dat->codes + (size_t)a * L * P;
-	const uint8_t *cb = dat->codes + (size_t)b * L * P;
-	double d = 0;
-
-	for (int l = 0; l < L; l++, ca += P, cb += P) {
-		for (int x = 0; x < P; x++) {
-			int first = 1, na = 0, nb = 0;
-			if (ca[x] == MC_CODE_MISSING)
-				continue;
-			for (int y = 0; y < x; y++)
-				if (ca[y] == ca[x])
-					first = 0;
-			if (!first)
-				continue;
-			for (int y = 0; y < P; y++) {
-				na += ca[y] == ca[x];
-				nb += cb[y] == ca[x];
-			}
-			d += abs(na - nb);
-		}
-		for (int x = 0; x < P; x++) {	/* alleles only b carries */
-			int first = 1, nb = 0, in_a = 0;
-			if (cb[x] == MC_CODE_MISSING)
-				continue;
-			for (int y = 0; y < x; y++)
-				if (cb[y] == cb[x])
-					first = 0;
-			for (int y = 0; y < P; y++) {
-				in_a |= ca[y] == cb[x];
-				nb += cb[y] == cb[x];
-			}
-			if (first && !in_a)
-				d += nb;
-		}
-	}
-	return d;
-}
-
-/* rnd_init.c:192-339 */
+/* rnd_init.c:192-339.  The host draws the K distinct centre individuals from
+ * the rand() stream; the nearest-centre assignment (I * K * L distance work),
+ * the cluster counts and the starting parameters are made on the device
+ * (mc_init_mixture). */
 static int random_initialize_mixture(options *opt, data *dat, model *mod)
 {
 	const int K = mod->K, I = dat->I, L = dat->L, P = dat->ploidy;
-	const int64_t T = mod->T;
+	const size_t row = (size_t)L * P;
 	int *center = malloc(sizeof *center * (size_t)K);
-	double *eta = calloc((size_t)K, sizeof *eta);
-	double *p = calloc((size_t)K * (T ? T : 1), sizeof *p);
-	int *part = malloc(sizeof *part * (size_t)I);
+	int32_t *local = malloc(sizeof *local * (size_t)K);
+	uint8_t *rows = malloc(row * (size_t)K > 0 ? row * (size_t)K : 1);
 
 	(void)opt;
-	if (!center || !eta || !p || !part)
+	if (!center || !local || !rows)
 		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "initial parameters\n");
-
-	if (K == 1) {
-		for (int i = 0; i < I; i++)
-			part[i] = 0;
-	} else {
+	if (K > 1) {
 		/* K distinct random centres, re-drawing on collision (205-217) */
 		for (int k = 0; k < K; k++) {
 			int again;
@@ -156,66 +110,30 @@ static int random_initialize_mixture(options *opt, data *dat, model *mod)
 						break;
 					}
 			} while (again);
-		}
-		/* nearest centre, strictly smaller distance wins (220-258) */
-		for (int i = 0; i < I; i++) {
-			double best = INFINITY;
-			part[i] = 0;
-			if (i == center[0])
-				continue;
-			for (int k = 0; k < K; k++) {
-				double d;
-				if (i == center[k]) {
-					part[i] = k;
-					break;
-				}
-				d = count_distance(dat, i, center[k]);
-				if (d < best) {
-					part[i] = k;
-					best = d;
-				}
-			}
+			memcpy(rows + (size_t)k * row, dat->codes + (size_t)center[k] * row, row);
 		}
 	}
-
-	/* eta_k = (1 + n_k) / (I + K)  (274-293) */
-	for (int k = 0; k < K; k++)
-		eta[k] = 1;
-	for (int i = 0; i < I; i++)
-		eta[part[i]]++;
-	for (int k = 0; k < K; k++)
-		eta[k] /= I + K;
-
-	/* p_klj proportional to 1 + (K - k) S_klj with S_klj the allele count of
-	 * cluster k: the reference's accumulation sits inside its k loop
-	 * (296-318), so row k is reset at pass k and then receives its members'
-	 * counts on passes k..K-1.  Counts are integers: the closed form is
-	 * bit-identical to the repeated additions. */
-	for (int i = 0; i < I; i++) {
-		const uint8_t *c = dat->codes + (size_t)i * L * P;
-		double *row = p + (size_t)part[i] * T;
-		for (int l = 0; l < L; l++)
-			for (int a = 0; a < P; a++)
-				if (c[l * P + a] != MC_CODE_MISSING)
-					row[dat->allele_off[l] + c[l * P + a]] += 1;
-	}
-	for (int k = 0; k < K; k++)
-		for (int l = 0; l < L; l++) {
-			double *row = p + (size_t)k * T + dat->allele_off[l];
-			double sum = 0.0;
-			for (int m = 0; m < dat->uniquealleles[l]; m++) {
-				row[m] = 1.0 + (K - k) * row[m];
-				sum += row[m];
-			}
-			for (int m = 0; m < dat->uniquealleles[l]; m++)
-				row[m] /= sum;
+	for (int r = 0; r < mod->n_gpus; r++) {
+		for (int k = 0; k < K; k++) {
+			const int64_t i = K > 1 ? center[k] - mod->row_first[r] : -1;
+			local[k] = (K > 1 && i >= 0 && center[k] < mod->row_first[r + 1]) ? (int32_t)i : -1;
 		}
-	for (int r = 0; r < mod->n_gpus; r++)	/* eta_k and p are replicated */
-		GPU(mc_set_params(mod->gpus[r], mod->tindex, eta, p));
+		if (mod->n_gpus == 1)
+			GPU(mc_init_mixture(mod->gpus[r], mod->tindex, local, rows));
+		else
+			GPU(mc_init_mixture_local(mod->gpus[r], local, rows));
+	}
+	if (mod->n_gpus > 1) {
+		/* counts and cluster sizes are summed over devices first */
+		if (mc_comm_exchange(mod->comm) != MC_OK)
+			return mmessage(ERROR_MSG, GPU_ERROR, "%s\n",
+				mc_comm_last_error(mod->comm));
+		for (int r = 0; r < mod->n_gpus; r++)
+			GPU(mc_init_mixture_finish(mod->gpus[r], mod->tindex, I));
+	}
 	free(center);
-	free(eta);
-	free(p);
-	free(part);
+	free(local);
+	free(rows);
 	return NO_ERROR;
 }
 

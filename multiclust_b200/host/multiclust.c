@@ -170,12 +170,12 @@ void free_model_data(model *mod, options *opt)
 {
 	(void)opt;
 	free(mod->count_K);
-	free(mod->eta_host); free(mod->p_host); free(mod->post_host);
+	free(mod->eta_host); free(mod->p_host); free(mod->post_host); free(mod->popq_host);
 	if (mod->comm)
 		mc_comm_destroy(mod->comm);
 	mod->comm = NULL;
 	mod->count_K = NULL;
-	mod->eta_host = mod->p_host = mod->post_host = NULL;
+	mod->eta_host = mod->p_host = mod->post_host = mod->popq_host = NULL;
 }
 
 void free_model(model *mod, options *opt)

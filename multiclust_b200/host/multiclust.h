@@ -157,6 +157,7 @@ struct _model {
 	int64_t eta_len;		/* I*K or K */
 	/* host copies fetched for the writers */
 	double *eta_host, *p_host, *post_host;
+	double *popq_host;		/* [numpops][K] locale sums of the posterior (device) */
 	FILE *trace;			/* --trace */
 	mcr_state *rng;			/* the rand() stream of the initialisers */
 	int no_exit;			/* 1: record the reference's exit(0) conditions in

@@ -53,7 +53,7 @@ typedef struct {
 	char *trace;			/* --trace text of the fit */
 	size_t trace_len;
 	/* kept only when the fit may be a new maximum */
-	double *eta, *p, *post;
+	double *eta, *p, *post, *popq;
 	int *I_K, *count_K;
 } fit_job;
 
@@ -83,9 +83,9 @@ static double now_s(void)
 
 static void job_release(fit_job *job)
 {
-	free(job->eta); free(job->p); free(job->post);
+	free(job->eta); free(job->p); free(job->post); free(job->popq);
 	free(job->I_K); free(job->count_K); free(job->trace);
-	job->eta = job->p = job->post = NULL;
+	job->eta = job->p = job->post = job->popq = NULL;
 	job->I_K = job->count_K = NULL;
 	job->trace = NULL;
 }
@@ -218,7 +218,8 @@ static void *worker_main(void *arg)
 					job->eta = mod->eta_host;
 					job->p = mod->p_host;
 					job->post = mod->post_host;
-					mod->eta_host = mod->p_host = mod->post_host = NULL;
+					job->popq = mod->popq_host;
+					mod->eta_host = mod->p_host = mod->post_host = mod->popq_host = NULL;
 					job->I_K = malloc(sizeof(int) * (size_t)dat.I);
 					job->count_K = malloc(sizeof(int) * (size_t)job->K);
 					memcpy(job->I_K, dat.I_K, sizeof(int) * (size_t)dat.I);
@@ -258,11 +259,12 @@ static int write_best_from_job(options *opt, data *dat, model *mod, void *ctx)
 	mod->eta_host = job->eta;
 	mod->p_host = job->p;
 	mod->post_host = job->post;
+	mod->popq_host = job->popq;
 	dat->I_K = job->I_K;
 	memcpy(mod->count_K, job->count_K, sizeof(int) * (size_t)job->K);
 	err = write_result_files_public(opt, dat, mod);
 	dat->I_K = I_K;
-	mod->eta_host = mod->p_host = mod->post_host = NULL;
+	mod->eta_host = mod->p_host = mod->post_host = mod->popq_host = NULL;
 	return err;
 }
 

@@ -32,6 +32,35 @@ int gather_state(options *opt, data *dat, model *mod, int slot, double *eta,
 	return NO_ERROR;
 }
 
+/* numerators of the popq tables (write_file.c:446-459, 658-666): the
+ * posterior rows summed over the individuals of every locale, on the device
+ * (mc_locale_sums); the shards of an individual-sharded fit are added in rank
+ * order */
+static int locale_sums(data *dat, model *mod)
+{
+	const size_t n = (size_t)dat->numpops * mod->K;
+	int *loc = malloc(sizeof *loc * (size_t)dat->I);
+	double *part = malloc(sizeof *part * (n ? n : 1));
+
+	free(mod->popq_host);
+	mod->popq_host = calloc(n ? n : 1, sizeof(double));
+	if (!loc || !part || !mod->popq_host) {
+		free(loc);
+		free(part);
+		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "popq table\n");
+	}
+	for (int i = 0; i < dat->I; i++)
+		loc[i] = dat->idv[i].locale;
+	for (int r = 0; r < mod->n_gpus; r++) {
+		GPU(mc_locale_sums(mod->gpus[r], loc + mod->row_first[r], dat->numpops, part));
+		for (size_t x = 0; x < n; x++)
+			mod->popq_host[x] += part[x];
+	}
+	free(loc);
+	free(part);
+	return NO_ERROR;
+}
+
 /* parameters of slot pindex and the posterior sums of the last E-step */
 int fetch_results(options *opt, data *dat, model *mod)
 {
@@ -44,8 +73,11 @@ int fetch_results(options *opt, data *dat, model *mod)
 	mod->post_host = malloc(sizeof(double) * (size_t)dat->I * mod->K);
 	if (!mod->eta_host || !mod->p_host || !mod->post_host)
 		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "result buffers\n");
-	return gather_state(opt, dat, mod, mod->pindex, mod->eta_host, mod->p_host,
-		mod->post_host);
+	{
+		int err = gather_state(opt, dat, mod, mod->pindex, mod->eta_host, mod->p_host,
+			mod->post_host);
+		return err ? err : locale_sums(dat, mod);
+	}
 }
 
 /* "<path>/<file>" or the -o prefix, followed by a formatted tail */
@@ -161,13 +193,10 @@ static int write_popq(options *opt, data *dat, model *mod, const char *tail,
 		free(q);
 		return FILE_OPEN_ERROR;
 	}
-	for (int k = 0; k < mod->K; k++) {
-		for (int i = 0; i < dat->I; i++)
-			q[(size_t)dat->idv[i].locale * mod->K + k]
-				+= mod->post_host[(size_t)i * mod->K + k];
+	for (int k = 0; k < mod->K; k++)
 		for (int n = 0; n < dat->numpops; n++)
-			q[(size_t)n * mod->K + k] /= scale * dat->i_p[n];
-	}
+			q[(size_t)n * mod->K + k] = mod->popq_host[(size_t)n * mod->K + k]
+				/ (scale * dat->i_p[n]);
 	for (int n = 0; n < dat->numpops; n++) {
 		fprintf(fp, "%s:\t", dat->pops[n]);
 		for (int k = 0; k < mod->K; k++)

@@ -312,3 +312,60 @@ def test_multiallelic_data_never_dense(orc, tmp_path):
         check_step(orc, c, fit, 0, 1)
     finally:
         c.close()
+
+
+def test_locale_sums_and_mixture_init(orc, tmp_path):
+    """mc_locale_sums (popq numerators) and mc_init_mixture (nearest-centre start)
+    against numpy restatements of write_file.c:446-459 / rnd_init.c:220-338"""
+    from multiclust_b200 import Context
+    I, L, K, P = 75, 33, 4, 2
+    d = gen_data(tmp_path, I, L, K=3, jmax=5, miss=400, P=P)
+    codes, J = d["codes"], d["J"]
+    off = np.concatenate([[0], np.cumsum(J)])
+    T = int(J.sum())
+    c = Context(0)
+    try:
+        c.set_data(J, codes)
+        c.alloc_model(K, admixture=0, q=0)
+        centers = np.array([17, 3, 60, 41], dtype=np.int32)
+        c.init_mixture(0, centers, codes[centers])
+        eta, p = c.get_params(0)
+        # numpy restatement
+        cnt = np.zeros((I, T))
+        for i in range(I):
+            for l in range(L):
+                for a in range(P):
+                    if codes[i, l, a] != 255:
+                        cnt[i, off[l] + codes[i, l, a]] += 1
+        part = np.zeros(I, dtype=int)
+        for i in range(I):
+            if i == centers[0]:
+                continue
+            best = np.inf
+            for k in range(K):
+                if i == centers[k]:
+                    part[i] = k
+                    break
+                dist = np.abs(cnt[i] - cnt[centers[k]]).sum()
+                if dist < best:
+                    best, part[i] = dist, k
+        eta_r = (1.0 + np.bincount(part, minlength=K)) / (I + K)
+        p_r = np.zeros((K, T))
+        for k in range(K):
+            S = cnt[part == k].sum(axis=0)
+            row = 1.0 + (K - k) * S
+            for l in range(L):
+                a, b = off[l], off[l + 1]
+                if b > a:
+                    p_r[k, a:b] = row[a:b] / row[a:b].sum()
+        assert np.array_equal(eta, eta_r)
+        assert np.max(np.abs(p - p_r.ravel())) < 1e-15
+        # locale sums of the posterior after one step
+        c.em_step(0, 0)
+        post = c.posterior()
+        locale = (np.arange(I) * 7 % 5).astype(np.int32)
+        got = c.locale_sums(locale, 5)
+        ref = np.stack([post[locale == n].sum(axis=0) for n in range(5)])
+        assert np.max(np.abs(got - ref)) < 1e-12
+    finally:
+        c.close()
