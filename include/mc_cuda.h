@@ -79,8 +79,12 @@ void *mc_ctx_stream(const mc_ctx *ctx);
  *                                    the one-pass tile kernel
  *                  The kernels sum in different orders, so results agree to
  *                  rounding (1e-13 relative observed), not bit for bit.
- *   MC_OPT_TIMING  non-zero: the planner prints its phases to stderr */
-enum { MC_OPT_KERNEL = 1, MC_OPT_TIMING = 2 };
+ *   MC_OPT_TIMING  non-zero: the planner prints its phases to stderr
+ *   MC_OPT_GRAPH   (default 1) mc_em_step and mc_loglik replay their launch
+ *                  sequence as a CUDA graph from the third call of a slot
+ *                  (pair) on: a small fit is launch-bound.  Same kernels, same
+ *                  results.  Off while mc_profile_enable is on. */
+enum { MC_OPT_KERNEL = 1, MC_OPT_TIMING = 2, MC_OPT_GRAPH = 3 };
 enum { MC_KERNEL_AUTO = 0, MC_KERNEL_TILE = 1, MC_KERNEL_ADMIX3 = 2, MC_KERNEL_DENSE = 3 };
 int mc_set_option(mc_ctx *ctx, int option, int value);
 

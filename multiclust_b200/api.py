@@ -158,7 +158,7 @@ class Context:
             raise McError("%s failed (%d): %s" % (
                 what, rc, self.lib.mc_last_error(self.h).decode()))
 
-    OPT_KERNEL, OPT_TIMING = 1, 2
+    OPT_KERNEL, OPT_TIMING, OPT_GRAPH = 1, 2, 3
     KERNEL_AUTO, KERNEL_TILE, KERNEL_ADMIX3, KERNEL_DENSE = 0, 1, 2, 3
 
     def set_option(self, option, value):

@@ -98,6 +98,14 @@ struct mc_ctx {
 	/* kernels whose dynamic shared-memory limit has been raised (set once per
 	 * kernel and size, not on every launch) */
 	std::vector<std::pair<const void *, size_t>> smem_attr;
+	/* whole steps replayed as CUDA graphs (mc_em_step / mc_loglik on one
+	 * context): a small fit is launch-bound, and a graph launch costs one
+	 * submission instead of five to twelve */
+	cudaGraphExec_t g_step[9] = {}, g_ll[3] = {};
+	int64_t g_step_n[9] = {}, g_ll_n[3] = {};	/* kernels inside each graph */
+	int g_step_seen[9] = {}, g_ll_seen[3] = {};
+	bool graphs_ok = true;
+	int opt_graph = 1;
 	/* plan options (mc_set_option) */
 	int opt_kernel = 0, opt_timing = 0;
 	/* scratch of the admixture initialiser, kept between fits */
@@ -231,8 +239,26 @@ extern "C" int mc_create(mc_ctx **out, int device)
 	return MC_OK;
 }
 
+static void free_graphs(mc_ctx *c)
+{
+	for (int x = 0; x < 9; x++) {
+		if (c->g_step[x])
+			cudaGraphExecDestroy(c->g_step[x]);
+		c->g_step[x] = nullptr;
+		c->g_step_seen[x] = 0;
+	}
+	for (int x = 0; x < 3; x++) {
+		if (c->g_ll[x])
+			cudaGraphExecDestroy(c->g_ll[x]);
+		c->g_ll[x] = nullptr;
+		c->g_ll_seen[x] = 0;
+	}
+	c->graphs_ok = true;
+}
+
 static void free_plan(mc_ctx *c)
 {
+	free_graphs(c);
 	dfree(c->d_slot_locus); dfree(c->d_slot_off); dfree(c->d_slot_J);
 	dfree(c->d_group_rowbase); dfree(c->d_group_rows); dfree(c->d_tile_rows);
 	dfree(c->d_tiled); dfree(c->d_Apart); dfree(c->d_Npart);
@@ -527,6 +553,42 @@ static int upload(mc_ctx *c, T *&dst, const std::vector<T> &src)
 	return MC_OK;
 }
 
+/* Split of a launch into (locus chunks) x (individual chunks) = units for the
+ * persistent grid, by an estimate of the launch time in microseconds:
+ *   rounds x (tiles of the longest unit x t_tile + t_unit)
+ *   + the traffic of the per-chunk partial sums (A_ik: one [I][K] block per
+ *     locus chunk, written once and read once; allele sums: one [K][T] block
+ *     per individual chunk, zeroed, flushed and summed) at ~5 TB/s.
+ * Small problems end up with one tile per CTA (the kernel is latency-bound
+ * there), large ones with one unit per CTA slot. */
+static void choose_chunks(long long n_ltiles, long long n_itiles, long long sms, double t_tile,
+	double apart_us_per_lchunk, double npart_us_per_ichunk, long long max_lchunk_tiles,
+	int *best_nl, int *best_ni)
+{
+	const double t_unit = 4.0;
+	double best = 1e300;
+	*best_nl = 1;
+	*best_ni = 1;
+	const long long nl_min = std::max<long long>(1, (n_ltiles + max_lchunk_tiles - 1) / max_lchunk_tiles);
+	const long long nl_max = std::min<long long>(n_ltiles, std::max<long long>(nl_min, 4 * sms));
+	for (long long nl = nl_min; nl <= nl_max; nl++) {
+		const long long lt = (n_ltiles + nl - 1) / nl;
+		const long long ni_max = std::min<long long>(n_itiles, std::max<long long>(1, 8 * sms / nl));
+		for (long long ni = 1; ni <= ni_max; ni++) {
+			const long long it = (n_itiles + ni - 1) / ni;
+			const long long rounds = (nl * ni + sms - 1) / sms;
+			const double t = (double)rounds * ((double)(lt * it) * t_tile + t_unit)
+				+ (double)nl * apart_us_per_lchunk + (double)ni * npart_us_per_ichunk;
+			if (t < best * (1.0 - 1e-9)) {
+				best = t;
+				*best_nl = (int)nl;
+				*best_ni = (int)ni;
+			}
+		}
+	}
+}
+
+
 static int raise_smem_limit(mc_ctx *c, const void *fn, size_t smem)
 {
 	for (auto &e : c->smem_attr)
@@ -672,33 +734,12 @@ static int make_plan3(mc_ctx *c)
 	}
 	const long long sms = (long long)c->num_sms * A3_CTAS_PER_SM;
 
-	/* locus chunks x individual chunks: fill the persistent grid evenly.  More
-	 * locus chunks cost A_ik partial sums (written once, read once: 16 bytes per
-	 * individual, cluster and chunk against ~1e-11 s per allele copy of the
-	 * kernel itself), more individual chunks cost allele-sum buffers */
+	/* locus chunks x individual chunks: ~13 us per (256 individuals x 16 copies)
+	 * tile with two CTAs per SM */
 	int n_lchunks = 1, n_ichunks = 1;
-	{
-		double best_eff = -1e30;
-		const int nl_max = (int)std::min<long long>(n_ltiles, 2 * sms);
-		for (int nl = 1; nl <= nl_max; nl++) {
-			const double apart = (double)nl * K * 16.0 / ((double)L * c->P * 64.0);
-			const double lmax = (double)((n_ltiles + nl - 1) / nl) * nl / n_ltiles;
-			const long long cmax = std::min<long long>(n_itiles,
-				std::max<long long>(1, (4 * sms + nl - 1) / nl));
-			for (long long cc = 1; cc <= cmax; cc++) {
-				const long long units = cc * nl;
-				const long long rounds = (units + sms - 1) / sms;
-				const double imax = (double)((n_itiles + cc - 1) / cc) * cc / n_itiles;
-				const double eff = (double)units / (double)(rounds * sms) / (lmax * imax)
-					- apart - 0.004 * (double)cc - 0.002 * (double)rounds;
-				if (eff > best_eff + 1e-12) {
-					best_eff = eff;
-					n_lchunks = nl;
-					n_ichunks = (int)cc;
-				}
-			}
-		}
-	}
+	choose_chunks(n_ltiles, n_itiles, sms, 13.0,
+		(double)n_itiles * A3_IT * K * 16.0 / 5e6,
+		(double)K * (double)c->T * 40.0 / 5e6, n_ltiles, &n_lchunks, &n_ichunks);
 	std::vector<int> lc_first((size_t)n_lchunks + 1);
 	for (int x = 0; x <= n_lchunks; x++)
 		lc_first[x] = (int)((long long)n_ltiles * x / n_lchunks);
@@ -836,31 +877,11 @@ static int make_plan_dense(mc_ctx *c)
 	if (budget < 1)
 		return MC_OK;
 	const long long sms = (long long)c->num_sms * DN_CTAS_PER_SM;
-	const int nl_min = (int)((n_ltiles + budget - 1) / budget);
-	int best_nl = nl_min, best_ni = 1;
-	{
-		double best_eff = -1;
-		const int nl_max = (int)std::min<long long>(n_ltiles, std::max<long long>(nl_min, 2 * sms));
-		for (int nl = nl_min; nl <= nl_max; nl++) {
-			const long long cmax = std::min<long long>(n_itiles,
-				std::max<long long>(1, (4 * sms + nl - 1) / nl));
-			for (long long ni = 1; ni <= cmax; ni++) {
-				const long long units = ni * nl;
-				const long long rounds = (units + sms - 1) / sms;
-				/* ragged chunks: the longest unit sets the round's length */
-				const double lmax = (double)((n_ltiles + nl - 1) / nl) * nl / n_ltiles;
-				const double imax = (double)((n_itiles + ni - 1) / ni) * ni / n_itiles;
-				const double eff = (double)units / (double)(rounds * sms) / (lmax * imax)
-					- 0.02 * (double)nl / (double)std::max(nl_min, 1)
-					- 0.004 * (double)ni - 0.002 * (double)rounds;
-				if (eff > best_eff + 1e-12) {
-					best_eff = eff;
-					best_nl = nl;
-					best_ni = (int)ni;
-				}
-			}
-		}
-	}
+	int best_nl = 1, best_ni = 1;
+	/* ~7 us per (256 individuals x 16 loci) tile with two CTAs per SM */
+	choose_chunks(n_ltiles, n_itiles, sms, 7.0,
+		(double)n_itiles * DN_IT * c->K * 16.0 / 5e6,
+		(double)c->K * (double)c->T * 24.0 / 5e6, budget, &best_nl, &best_ni);
 	std::vector<int> lc_first((size_t)best_nl + 1);
 	int max_chunk_tiles = 1;
 	for (int x = 0; x <= best_nl; x++)
@@ -1616,24 +1637,112 @@ extern "C" int mc_init_mixture(mc_ctx *c, int slot, const int32_t *center_idx,
 	return rc;
 }
 
+/* Capture `body` (kernel launches on c->stream and c->aux only) into a graph.
+ * Returns MC_OK with *exec set, or MC_OK with *exec null when capture is not
+ * possible here (the caller then runs the body directly, and graphs are
+ * switched off for this plan). */
+template <typename F>
+static int capture_graph(mc_ctx *c, cudaGraphExec_t *exec, int64_t *n_kernels, F body)
+{
+	*exec = nullptr;
+	if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+		(void)cudaGetLastError();
+		c->graphs_ok = false;
+		return MC_OK;
+	}
+	const int64_t l0 = c->launches;
+	const int rc = body();
+	cudaGraph_t graph = nullptr;
+	const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+	*n_kernels = c->launches - l0;
+	c->launches = l0;
+	if (rc || e != cudaSuccess || !graph
+		|| cudaGraphInstantiate(exec, graph, 0) != cudaSuccess) {
+		(void)cudaGetLastError();
+		if (graph)
+			cudaGraphDestroy(graph);
+		*exec = nullptr;
+		c->graphs_ok = false;
+		c->aux_pending = false;
+		c->fused_step = false;
+		return rc;
+	}
+	cudaGraphDestroy(graph);
+	return MC_OK;
+}
+
+static int read_ll(mc_ctx *c, double *ll)
+{
+	if (ll) {
+		CK(cudaMemcpyAsync(ll, xb_ll(c), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	return MC_OK;
+}
+
 extern "C" int mc_em_step(mc_ctx *c, int from, int to, double *ll)
 {
 	if (!c)
 		return MC_ERR_ARG;
-	c->fused_step = true;	/* nobody exchanges the allele sums in between */
-	int rc = mc_em_step_local(c, from, to);
-	if (rc) {
-		c->fused_step = false;
-		return rc;
+	if (!c->have_model)
+		return fail(c, MC_ERR_STATE, "mc_em_step: no model allocated");
+	CHECK_SLOT(from);
+	CHECK_SLOT(to);
+	auto body = [&]() {
+		c->fused_step = true;	/* nobody exchanges the allele sums in between */
+		int rc = mc_em_step_local(c, from, to);
+		if (rc) {
+			c->fused_step = false;
+			return rc;
+		}
+		return mc_em_step_finish(c, to, nullptr);
+	};
+	/* the first call of a slot pair runs directly (it also raises the kernels'
+	 * shared-memory limits), the second one is captured, later ones replayed */
+	const int key = from * 3 + to;
+	if (c->opt_graph && c->graphs_ok && !c->profile) {
+		CK(cudaSetDevice(c->device));
+		if (!c->g_step[key] && c->g_step_seen[key]++ >= 1) {
+			const int rc = capture_graph(c, &c->g_step[key], &c->g_step_n[key], body);
+			if (rc)
+				return rc;
+		}
+		if (c->g_step[key]) {
+			CK(cudaGraphLaunch(c->g_step[key], c->stream));
+			c->launches += c->g_step_n[key];
+			return read_ll(c, ll);
+		}
 	}
-	return mc_em_step_finish(c, to, ll);
+	const int rc = body();
+	return rc ? rc : read_ll(c, ll);
 }
+
+static int loglik_launch(mc_ctx *c, int slot);
 
 extern "C" int mc_loglik(mc_ctx *c, int slot, double *ll)
 {
 	NVTX_FN();
 	NEED_MODEL();
 	CHECK_SLOT(slot);
+	if (c->opt_graph && c->graphs_ok && !c->profile) {
+		if (!c->g_ll[slot] && c->g_ll_seen[slot]++ >= 1) {
+			const int rc = capture_graph(c, &c->g_ll[slot], &c->g_ll_n[slot],
+				[&]() { return loglik_launch(c, slot); });
+			if (rc)
+				return rc;
+		}
+		if (c->g_ll[slot]) {
+			CK(cudaGraphLaunch(c->g_ll[slot], c->stream));
+			c->launches += c->g_ll_n[slot];
+			return read_ll(c, ll);
+		}
+	}
+	const int rc = loglik_launch(c, slot);
+	return rc ? rc : read_ll(c, ll);
+}
+
+static int loglik_launch(mc_ctx *c, int slot)
+{
 	int rc;
 	if (c->admixture) {
 		rc = c->use_dn
@@ -1655,10 +1764,6 @@ extern "C" int mc_loglik(mc_ctx *c, int slot, double *ll)
 		 * individual ll buffer is written */
 		if ((rc = mix_tail(c, c->d_eta[slot], nullptr, 1))) return rc;
 		if ((rc = reduce_vector(c, c->d_lli, c->I, xb_ll(c)))) return rc;
-	}
-	if (ll) {
-		CK(cudaMemcpyAsync(ll, xb_ll(c), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-		CK(cudaStreamSynchronize(c->stream));
 	}
 	return MC_OK;
 }
@@ -1954,6 +2059,9 @@ extern "C" int mc_set_option(mc_ctx *c, int option, int value)
 		return MC_OK;
 	case MC_OPT_TIMING:
 		c->opt_timing = value != 0;
+		return MC_OK;
+	case MC_OPT_GRAPH:
+		c->opt_graph = value != 0;
 		return MC_OK;
 	}
 	return fail(c, MC_ERR_ARG, "mc_set_option: unknown option %d", option);

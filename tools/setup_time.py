@@ -12,6 +12,7 @@ ctx.lib.mc_get_codes(ctx.h, ctypes.c_void_p(pinned.ctypes.data))
 J = ctx.get_J()
 for rep in range(2):
     c2 = Context(0)
+    c2.set_option(c2.OPT_TIMING, 1)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     c2.set_data(J, pinned)
     torch.cuda.synchronize(); t1 = time.perf_counter()
