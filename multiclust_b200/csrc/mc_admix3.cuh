@@ -51,6 +51,10 @@
 				 * A3_IT * A3_NC entries, so the per-tile costs (two barriers,
 				 * the fold, the staging) are paid once per A3_NC copies */
 #endif
+#define A3_WP (A3_IT + 8)	/* pitch of a copy's row of w in doubles: rows of copies of
+				 * different parity start 8 bank pairs apart, so the two
+				 * lanes of a half warp that share an eta bank group (i % 8)
+				 * collide on w only when their copies have the same parity */
 #define A3_PR 192		/* pitch of the k-major p tile in doubles: a compile-time
 				 * constant, so the K loads of a copy share one address
 				 * register (a tile has at most A3_PR allele rows) */
@@ -366,7 +370,7 @@ static inline size_t a3_smem_bytes(int KP, bool em, int ncolmax, int cap)
 	const size_t csw = ((size_t)ncolmax + 1 + 7) / 8 * 8;
 	size_t d = (size_t)KR * A3_PR + 16;
 	if (em)
-		d += (size_t)A3_IT * NP * 2 + (size_t)A3_NC * A3_IT + (size_t)A3_THREADS * KR;
+		d += (size_t)A3_IT * NP * 2 + (size_t)A3_NC * A3_WP + (size_t)A3_THREADS * KR;
 	return d * sizeof(double)
 		+ ((em ? (size_t)cap : 0) + 2 * (3 * csw + A3_THREADS / 2)) * sizeof(unsigned short)
 		+ 2 * 16 * sizeof(int);
@@ -428,8 +432,8 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 
 	/* eta rows first: the xor rotation needs them aligned to their size */
 	double *eta_s = smem3d;						/* [A3_IT][2 NP] */
-	double *w_s = eta_s + (EM ? (size_t)A3_IT * NP * 2 : 0);	/* [A3_NC][A3_IT] */
-	double *part_s = w_s + (EM ? (size_t)A3_NC * A3_IT : 0);	/* [A3_THREADS][KR] */
+	double *w_s = eta_s + (EM ? (size_t)A3_IT * NP * 2 : 0);	/* [A3_NC][A3_WP] */
+	double *part_s = w_s + (EM ? (size_t)A3_NC * A3_WP : 0);	/* [A3_THREADS][KR] */
 	double *p_s = part_s + (EM ? (size_t)A3_THREADS * KR : 0);	/* [KR][PR] */
 	double *red = p_s + (size_t)KR * PR;				/* [16] */
 	unsigned short *csc_s = reinterpret_cast<unsigned short *>(red + 16);	/* [cap] */
@@ -622,7 +626,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 										== codes_q[z];
 							wst = wgt * (double)n;
 						}
-						w_s[(size_t)(hh * 8 + q) * A3_IT + t] = wst;
+						w_s[(size_t)(hh * 8 + q) * A3_WP + t] = wst;
 					}
 					if (z == 0) {
 						tprev = tmp;
@@ -669,7 +673,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					const int lane0c = cst_s[csw + col], lane1c = cst_s[csw + col + 1];
 					const int S2 = (lane1c - lane0c) * 2;	/* list stride, bytes */
 					const unsigned wb = w_sa + (unsigned)(cst_s[2 * csw + col] >> 8)
-						* (PP * A3_IT * 8);
+						* (PP * A3_WP * 8);
 					const unsigned xe = csc_sa + 2u * cst_s[col + 1];
 					unsigned x = csc_sa + 2u * (cst_s[col] + (t - lane0c));
 					/* ids run two trips ahead and weights one, and nothing is
@@ -677,7 +681,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					 * issues in order, so an operation on a fresh load would hold
 					 * the accumulation of the current entry back */
 					auto w_addr = [&](unsigned en) {
-						return wb + ((en >> 9) & 7) * (A3_IT * 8) + (en & (A3_IT - 1)) * 8;
+						return wb + ((en >> 9) & 7) * (A3_WP * 8) + (en & (A3_IT - 1)) * 8;
 					};
 					unsigned e0 = x < xe ? a3_lds_u16(x) : 0u;
 					unsigned e1 = x + S2 < xe ? a3_lds_u16(x + S2) : 0u;
