@@ -13,8 +13,8 @@ tot_inst = tot_s = 0
 by = defaultdict(lambda: [0, 0, 0, 0, 0])
 lines = []
 for r in rows[2:]:
-    if len(r) < len(hdr) - 2:
-        continue
+    if len(r) < len(hdr) - 2 or r[ix["Instructions Executed"]] == "Instructions Executed":
+        continue        # short rows and the repeated header of a second kernel
     op = r[ix["Source"]].split()
     if op and op[0].startswith("@"):
         op = op[1:]
@@ -34,7 +34,7 @@ for name, b in sorted(by.items(), key=lambda kv: -kv[1][1])[:24]:
 stalls = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
 agg = defaultdict(int)
 for r in rows[2:]:
-    if len(r) < len(hdr) - 2:
+    if len(r) < len(hdr) - 2 or r[ix["Instructions Executed"]] == "Instructions Executed":
         continue
     for n in stalls:
         agg[n] += int(r[ix[n]] or 0)
