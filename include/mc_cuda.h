@@ -7,8 +7,13 @@
  * reference makes in C -- slot rotation, accept/reject of accelerated steps,
  * stop()/converged(), the exit(0) rules (em_alg.c:44-207, accel_em.c:35-114)
  * -- and calls down here only for the data-parallel work.  Plain pointers and
- * sizes, no C++ or torch types.  One host thread per context; no hidden global
- * state; every device buffer is owned by the context.
+ * sizes, no C++ or torch types.  One host thread per context; every device
+ * buffer is owned by the context.  One piece of process-wide state: device
+ * memory comes from the device's default stream-ordered pool (cudaMallocAsync),
+ * and mc_create lifts that pool's release threshold so that what one context
+ * frees is handed out again to the next (a K sweep re-plans per K, and a fresh
+ * cudaMalloc of the multi-GB layouts costs ~1 s); a host that shares the
+ * process with other pool users can lower it again with cudaMemPoolSetAttribute.
  *
  * Flat layouts (all parameters IEEE double, as in the reference):
  *   J[l]    = allele slots of locus l, INCLUDING the phantom slot the

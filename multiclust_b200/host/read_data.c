@@ -385,8 +385,11 @@ int read_file(options *opt, data *dat)
 	/* raw alleles, haplotype-major like dat->IL */
 	raw = malloc(sizeof *raw * (size_t)nhap * dat->L);
 	dat->idv = calloc((size_t)dat->I, sizeof *dat->idv);
-	if (!raw || !dat->idv)
+	if (!raw || !dat->idv) {
+		free(raw);
+		free(text);
 		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "genotype table\n");
+	}
 	data_start.p = text;
 	data_start.end = text + text_len;
 	*fp = data_start;
@@ -395,12 +398,20 @@ int read_file(options *opt, data *dat)
 		skip_line(fp);
 	for (int h = 0, idv = 0; h < nhap; h += opt->interleaved ? dat->ploidy : 1) {
 		const int rows = opt->interleaved ? dat->ploidy : 1;
-		if (!(word = next_word(fp)))
-			break;
+		if (!(word = next_word(fp))) {
+			/* fewer rows than the line count promised (a short last
+			 * record): the recoder must not see uninitialised rows */
+			free(raw);
+			free(text);
+			return mmessage(ERROR_MSG, END_OF_FILE, opt->filename);
+		}
 		if (opt->interleaved || !(h % dat->ploidy)) {
 			dat->idv[idv].name = word;
-			if (!(word = next_word(fp)))
+			if (!(word = next_word(fp))) {
+				free(raw);
+				free(text);
 				return mmessage(ERROR_MSG, END_OF_FILE, opt->filename);
+			}
 			dat->idv[idv].locale = locale_index(dat, word);
 			free(word);
 			idv++;
@@ -411,11 +422,14 @@ int read_file(options *opt, data *dat)
 		for (int l = 0; l < dat->L; l++)
 			for (int j = 0; j < rows; j++) {
 				int v;
-				if (!scan_int(fp, &v))
+				if (!scan_int(fp, &v)) {
+					free(raw);
+					free(text);
 					return mmessage(ERROR_MSG, FILE_FORMAT_ERROR,
 						"failed to read locus %d of haplotype "
 						"%d in file '%s'.  Check option -R.\n",
 						l + 1, h + j + 1, opt->filename);
+				}
 				raw[(size_t)(h + j) * dat->L + l] = v;
 			}
 	}
@@ -441,8 +455,15 @@ int read_file(options *opt, data *dat)
 	dat->allele_off = calloc((size_t)dat->L + 1, sizeof(int32_t));
 	dat->label_off = calloc((size_t)dat->L + 1, sizeof(int64_t));
 	dat->codes = malloc((size_t)dat->I * dat->L * dat->ploidy);
-	if ((err = recode_loci(dat, raw, nhap, &labels, &nlab)))
+	if (!dat->uniquealleles || !dat->nreal || !dat->allele_off || !dat->label_off
+		|| !dat->codes) {
+		free(raw);
+		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "recoded genotypes\n");
+	}
+	if ((err = recode_loci(dat, raw, nhap, &labels, &nlab))) {
+		free(raw);
 		return err;
+	}
 	LAP("labels and 8-bit codes");
 	dat->label_off[dat->L] = nlab;
 	dat->labels = labels;
