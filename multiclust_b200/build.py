@@ -39,14 +39,36 @@ def _run(cmd):
     subprocess.check_call(cmd)
 
 
+OBJ = os.path.join(CSRC, "_obj")
+
+
 def build_cuda(force=False, extra=()):
+    """libmc_cuda.so from mc_cuda.cu and the mc_inst_*.cu instantiation units,
+    compiled in parallel (one nvcc per unit) and linked"""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != "mc_comm.cu"]
-    srcs += [os.path.join(INC, f) for f in os.listdir(INC)]
-    if not force and _newer(LIB, srcs):
+    units = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu") and f != "mc_comm.cu")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+            if f.endswith((".cu", ".cuh", ".h")) and f != "mc_comm.cu"]
+    deps += [os.path.join(INC, f) for f in os.listdir(INC)]
+    if not force and _newer(LIB, deps):
         return LIB
-    _run([nvcc] + NVCC_FLAGS + list(extra)
-         + ["-o", LIB, os.path.join(CSRC, "mc_cuda.cu")])
+    os.makedirs(OBJ, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    procs = []
+    for u in units:
+        obj = os.path.join(OBJ, u[:-3] + ".o")
+        cmd = [nvcc] + flags + list(extra) + ["-c", "-o", obj, os.path.join(CSRC, u)]
+        print("+", " ".join(cmd), flush=True)
+        procs.append((u, obj, subprocess.Popen(cmd)))
+    objs = []
+    for u, obj, pr in procs:
+        if pr.wait() != 0:
+            for _, _, other in procs:
+                if other.poll() is None:
+                    other.kill()
+            raise subprocess.CalledProcessError(pr.returncode, "nvcc -c " + u)
+        objs.append(obj)
+    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
     return LIB
 
 

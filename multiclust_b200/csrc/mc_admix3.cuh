@@ -41,6 +41,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "mc_device.cuh"
+
 #ifndef A3_THREADS
 #define A3_THREADS 256		/* measured at C3: 256 x 2 CTAs/SM 26.7 ms, 512 x 1 30.3 ms */
 #endif
@@ -94,224 +96,6 @@ struct Admix3Args {
 };
 
 /* ---------------------------------------------------------------------- */
-/* one-time layout builders                                                 */
-
-/* how often each allele slot occurs (orders the columns of a locus tile) */
-__global__ void k_allele_hist(const unsigned char *nat, long long I, int L, int P,
-	const int *off, unsigned *hist)
-{
-	const long long n = I * (long long)L;
-	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
-		x += (long long)gridDim.x * blockDim.x) {
-		const int l = (int)(x % L);
-		for (int ap = 0; ap < P; ap++) {
-			const unsigned char c = nat[(size_t)x * P + ap];
-			if (c != 255)
-				atomicAdd(&hist[off[l] + c], 1u);
-		}
-	}
-}
-
-/* natural [I][L][P] codes -> A3_NC bytes per (tile, individual): LT = A3_NC / PP
- * loci x PP copies, thread-major inside a tile */
-__global__ void k3_build_codes(const unsigned char *nat, unsigned char *codes,
-	long long I, int L, int P, int PP, int n_itiles, int n_ltiles)
-{
-	const int LT = A3_NC / PP;
-	const long long n = (long long)n_itiles * n_ltiles * A3_THREADS;
-	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
-		x += (long long)gridDim.x * blockDim.x) {
-		const int t = (int)(x % A3_THREADS);
-		const long long r = x / A3_THREADS;
-		const int lt = (int)(r % n_ltiles);
-		const long long i = (r / n_ltiles) * A3_IT + t;
-		for (int h = 0; h < A3_NC / 8; h++) {
-			unsigned char b[8];
-			for (int q = 0; q < 8; q++) {
-				const int l = lt * LT + (h * 8 + q) / PP, a = q % PP;
-				b[q] = (i < I && l < L && a < P) ? nat[((size_t)i * L + l) * P + a] : 255;
-			}
-			*reinterpret_cast<uint2 *>(codes + (size_t)x * A3_NC + h * 8)
-				= *reinterpret_cast<uint2 *>(b);
-		}
-	}
-}
-
-/* entry lists of one (itile, ltile): for every real allele column in `colinfo`
- * order, one entry per (individual, allele) carrying it:
- *     i | first copy << 9 | (count - 1) << 12.
- * The column owns S consecutive pass-2 lanes, S chosen per tile from the tile's
- * own counts so that no lane gets more than q = ceil(entries / A3_THREADS) (+1)
- * entries; lane seg reads the entries at start + s * S + seg, s = 0, 1, ...  The eta rows
- * of 8 individuals with different i % 8 lie in different bank groups, so an
- * entry is dealt to a slot whose (lane + step) % 8 equals i % 8 wherever such a
- * slot is still free; the rest fill the remaining positions in ascending order
- * of i. */
-__global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
-	int ncolmax, int cap, const int *lt_ncol, const unsigned short *colinfo,
-	unsigned short *csc, unsigned short *colstart)
-{
-	extern __shared__ unsigned char sm3[];
-	unsigned char *cd = sm3;				/* [A3_IT][A3_NC] */
-	int *cnt = reinterpret_cast<int *>(sm3 + (size_t)A3_IT * A3_NC);	/* [ncolmax] */
-	int *lane_first = cnt + ncolmax;				/* [ncolmax + 1] */
-	/* carriers of every column as a bit mask over the tile's individuals: the
-	 * sweeps below then visit carriers only (a sixth of the individuals at
-	 * config 3) instead of testing every individual three times */
-	constexpr int MW = A3_IT / 32;
-	unsigned *mask = reinterpret_cast<unsigned *>(lane_first + ncolmax + 1);	/* [ncolmax][MW] */
-	const int lt = blockIdx.x % n_ltiles;
-	const int ncol = lt_ncol[lt];
-	const unsigned short *ci = colinfo + (size_t)lt * ncolmax;
-	unsigned short *out = csc + (size_t)blockIdx.x * cap;
-	const int csw = ((ncolmax + 1 + 7) / 8) * 8;
-	unsigned short *cs = colstart + (size_t)blockIdx.x * (3 * csw + A3_THREADS / 2);
-	const uint2 *src = reinterpret_cast<const uint2 *>(codes)
-		+ (size_t)blockIdx.x * A3_THREADS * (A3_NC / 8);
-
-	for (int x = threadIdx.x; x < A3_IT * (A3_NC / 8); x += blockDim.x)
-		reinterpret_cast<uint2 *>(cd)[x] = src[x];
-	__syncthreads();
-	for (int x = threadIdx.x; x < ncol * MW; x += blockDim.x) {
-		const int c = x / MW, w = x - c * MW;
-		const int ll = ci[c] >> 8, j = ci[c] & 0xff;
-		unsigned m = 0;
-		for (int b = 0; b < 32; b++) {
-			const unsigned char *pc = cd + (w * 32 + b) * A3_NC + ll * PP;
-			bool has = false;
-			for (int a = 0; a < PP; a++)
-				has |= pc[a] == j;
-			m |= (unsigned)has << b;
-		}
-		mask[x] = m;
-	}
-	__syncthreads();
-	for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
-		int n = 0;
-		for (int w = 0; w < MW; w++)
-			n += __popc(mask[c * MW + w]);
-		cnt[c] = n;
-	}
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		int acc = 0;
-		for (int c = 0; c < ncol; c++) {
-			const int n = cnt[c];
-			cs[c] = (unsigned short)acc;
-			acc += n;
-		}
-		for (int c = ncol; c < csw; c++)
-			cs[c] = (unsigned short)acc;
-		/* lanes of THIS tile: the smallest list length q with
-		 * sum_c ceil(n_c / q) <= A3_THREADS, column c gets ceil(n_c / q) lanes */
-		int q = (acc + A3_THREADS - 1) / A3_THREADS;
-		if (q < 1)
-			q = 1;
-		for (;; q++) {
-			int lanes = 0;
-			for (int c = 0; c < ncol; c++)
-				lanes += (cnt[c] + q - 1) / q;
-			if (lanes <= A3_THREADS)
-				break;
-		}
-		int l0 = 0;
-		for (int c = 0; c < ncol; c++) {
-			lane_first[c] = l0;
-			cs[csw + c] = (unsigned short)l0;
-			l0 += (cnt[c] + q - 1) / q;
-		}
-		lane_first[ncol] = l0;
-		for (int c = ncol; c < csw; c++)
-			cs[csw + c] = (unsigned short)l0;
-		for (int c = 0; c < csw; c++)	/* column -> locus_in_tile << 8 | allele */
-			cs[2 * csw + c] = c < ncol ? ci[c] : 0;
-	}
-	__syncthreads();
-	/* the column of every pass-2 lane, two lanes per 16-bit word */
-	for (int x = threadIdx.x; x < A3_THREADS / 2; x += blockDim.x) {
-		unsigned v = 0;
-		for (int h = 0; h < 2; h++) {
-			const int ln = 2 * x + h;
-			int col = 255;
-			if (ln < lane_first[ncol]) {
-				int lo = 0, hi = ncol - 1;	/* last column with lane_first <= ln */
-				while (lo < hi) {
-					const int mid = (lo + hi + 1) >> 1;
-					if (lane_first[mid] <= ln)
-						lo = mid;
-					else
-						hi = mid - 1;
-				}
-				col = lo;
-				/* columns without entries own no lane: step to the owner */
-				while (lane_first[col + 1] <= ln)
-					col++;
-			}
-			v |= (unsigned)col << (8 * h);
-		}
-		cs[3 * csw + x] = (unsigned short)v;
-	}
-	for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
-		const int ll = ci[c] >> 8, j = ci[c] & 0xff;
-		const int n = cnt[c], start = cs[c];
-		const int lane0 = lane_first[c], S = lane_first[c + 1] - lane0;
-		if (!n)
-			continue;
-		const int q = n / S, rem = n - q * S;	/* lane seg holds q + (seg < rem) entries */
-		for (int x = 0; x < n; x++)
-			out[start + x] = 0xffff;
-		/* slot (seg, s) belongs to residue class (lane0 + seg + s) % 8: in step s
-		 * the 8 lanes of a quarter warp then want 8 different residues, and every
-		 * lane meets every residue once in 8 steps, so a column finds room for
-		 * all residues however few lanes it owns.  Two sweeps over the carriers:
-		 * the first places the entries that find a slot of their class, the
-		 * second the others */
-		for (int sweep = 0; sweep < 2; sweep++) {
-			int cs_s[8], cs_seg[8];		/* next free slot of every class */
-			for (int r = 0; r < 8; r++) {
-				cs_s[r] = 0;
-				cs_seg[r] = (r - lane0) & 7;
-			}
-			int fill = 0;
-			for (int w = 0; w < MW; w++)
-			for (unsigned mm = mask[c * MW + w]; mm; mm &= mm - 1) {
-				const int ii = w * 32 + __ffs((int)mm) - 1;
-				int cn = 0, first = 0;
-				for (int a = PP - 1; a >= 0; a--)
-					if (cd[ii * A3_NC + ll * PP + a] == j) {
-						cn++;
-						first = a;
-					}
-				const int r = ii & 7;
-				/* skip over slots that do not exist (segments beyond S, the
-				 * short last step) */
-				int s_ = cs_s[r], seg = cs_seg[r];
-				while (s_ <= q && (seg >= S || (s_ == q && seg >= rem))) {
-					s_++;
-					seg = (r - lane0 - s_) & 7;
-				}
-				const bool ok = s_ < q || (s_ == q && seg < rem);
-				if (ok) {
-					if (sweep == 0)
-						out[start + s_ * S + seg] = (unsigned short)(ii | first << 9
-							| (cn - 1) << 12);
-					cs_s[r] = s_;
-					cs_seg[r] = seg + 8;
-				} else {
-					cs_s[r] = q + 1;
-					if (sweep == 1) {
-						while (out[start + fill] != 0xffff)
-							fill++;
-						out[start + fill++] = (unsigned short)(ii | first << 9
-							| (cn - 1) << 12);
-					}
-				}
-			}
-		}
-	}
-}
-
-/* ---------------------------------------------------------------------- */
 
 __device__ __forceinline__ void a3_cp_async16(void *smem_dst, const void *gsrc)
 {
@@ -354,7 +138,7 @@ __device__ __forceinline__ unsigned a3_lds_u16(unsigned addr)
 
 /* log-likelihood terms of sums that are zero, subnormal or not finite (never
  * seen in a healthy fit); out of line to keep pass 1 short */
-__device__ __noinline__ double a3_slow_ll(double t0, double t1)
+static __device__ __noinline__ double a3_slow_ll(double t0, double t1)
 {
 	return log(t0) + log(t1);
 }
@@ -363,16 +147,24 @@ __device__ __noinline__ double a3_slow_ll(double t0, double t1)
  * of 8 individuals with different i % 8 start in 8 different bank groups */
 template <int KP> struct A3Row { static constexpr int NP = KP | 1; };
 
+/* kernel modes */
+enum { A3_ADMIX_EM = 0, A3_ADMIX_LL = 1, A3_MIX_E = 2, A3_MIX_M = 3 };
+
 /* bytes of dynamic shared memory; the host planner uses the same formula */
-static inline size_t a3_smem_bytes(int KP, bool em, int ncolmax, int cap)
+static inline size_t a3_smem_bytes(int KP, int mode, int ncolmax, int cap)
 {
 	const int KR = 2 * KP, NP = KP | 1;
+	const bool p1 = mode != A3_MIX_M, p2 = mode == A3_ADMIX_EM || mode == A3_MIX_M;
 	const size_t csw = ((size_t)ncolmax + 1 + 7) / 8 * 8;
-	size_t d = (size_t)KR * A3_PR + 16;
-	if (em)
-		d += (size_t)A3_IT * NP * 2 + (size_t)A3_NC * A3_WP + (size_t)A3_THREADS * KR;
+	size_t d = 16;
+	if (p1)
+		d += (size_t)KR * A3_PR;
+	if (p2)
+		d += (size_t)A3_IT * NP * 2 + (size_t)A3_THREADS * KR;
+	if (mode == A3_ADMIX_EM)
+		d += (size_t)A3_NC * A3_WP;
 	return d * sizeof(double)
-		+ ((em ? (size_t)cap : 0) + 2 * (3 * csw + A3_THREADS / 2)) * sizeof(unsigned short)
+		+ ((p2 ? (size_t)cap : 0) + 2 * (3 * csw + A3_THREADS / 2)) * sizeof(unsigned short)
 		+ 2 * 16 * sizeof(int);
 }
 
@@ -406,25 +198,32 @@ __device__ __forceinline__ void a3_stcg2(double *p, double2 v, unsigned long lon
 	asm volatile("st.global.cg.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;"
 		:: "l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void a3_cp_async16_stream(void *smem_dst, const void *gsrc,
-	unsigned long long pol)
-{
-	const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-	asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;"
-		:: "r"(s), "l"(gsrc), "l"(pol));
-}
+/* (The entry lists are staged with plain cp.async: `cp.async ... L2::cache_hint` came
+ * out of ptxas 12.9 with a clobbered descriptor register in some instantiations --
+ * UMOV into the descriptor pair between its set-up and the LDGSTS -- and faulted as
+ * an illegal instruction on B200.) */
 
-/* MODE 0: E+M step, MODE 1: log likelihood only */
+/* MODE A3_ADMIX_EM: admixture E+M step (both passes); A3_ADMIX_LL: admixture log
+ * likelihood (pass 1 only); A3_MIX_E: mixture E pass, a_ik = sum of log p over the
+ * observed copies (pass 1 only: `p` is the log p table, no eta; em_alg.c:793-827,
+ * log_likelihood.c:189-203); A3_MIX_M: mixture M pass, N_klj = sum_i v_ik c_ilj (pass 2
+ * only: `eta` holds the v_ik rows, the weight of an entry is its copy count;
+ * em_alg.c:965-986) */
 template <int KP, int PP, int MODE>
 __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(const Admix3Args a)
 {
+	constexpr bool P1 = (MODE != A3_MIX_M);			/* pass 1 runs */
+	constexpr bool P2 = (MODE == A3_ADMIX_EM || MODE == A3_MIX_M);	/* pass 2 + fold run */
+	constexpr bool HAS_W = (MODE == A3_ADMIX_EM);
+	constexpr bool HAS_A = (MODE == A3_ADMIX_EM || MODE == A3_MIX_E);
+	constexpr bool HAS_TMP = (MODE == A3_ADMIX_EM || MODE == A3_ADMIX_LL);
+	constexpr bool HAS_E = (MODE != A3_MIX_E);
 	constexpr int KR = 2 * KP;
 	constexpr int NP = A3Row<KP>::NP;
 	constexpr int LT = A3_NC / PP;		/* loci per tile */
 	constexpr int LH = 8 / PP;		/* loci per round of 8 copies */
 	constexpr int NH = A3_NC / 8;		/* rounds of pass 1 */
 	constexpr int PR = A3_PR;
-	constexpr bool EM = (MODE == 0);
 	extern __shared__ __align__(128) double smem3d[];
 	const int t = threadIdx.x, lane = t & 31;
 	const int csw = ((a.ncolmax + 1 + 7) / 8) * 8;	/* colstart row, 16-byte multiple */
@@ -432,12 +231,12 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 
 	/* eta rows first: the xor rotation needs them aligned to their size */
 	double *eta_s = smem3d;						/* [A3_IT][2 NP] */
-	double *w_s = eta_s + (EM ? (size_t)A3_IT * NP * 2 : 0);	/* [A3_NC][A3_WP] */
-	double *part_s = w_s + (EM ? (size_t)A3_NC * A3_WP : 0);	/* [A3_THREADS][KR] */
-	double *p_s = part_s + (EM ? (size_t)A3_THREADS * KR : 0);	/* [KR][PR] */
-	double *red = p_s + (size_t)KR * PR;				/* [16] */
+	double *w_s = eta_s + (P2 ? (size_t)A3_IT * NP * 2 : 0);	/* [A3_NC][A3_WP] */
+	double *part_s = w_s + (HAS_W ? (size_t)A3_NC * A3_WP : 0);	/* [A3_THREADS][KR] */
+	double *p_s = part_s + (P2 ? (size_t)A3_THREADS * KR : 0);	/* [KR][PR] */
+	double *red = p_s + (P1 ? (size_t)KR * PR : 0);		/* [16] */
 	unsigned short *csc_s = reinterpret_cast<unsigned short *>(red + 16);	/* [cap] */
-	unsigned short *cst2_s = csc_s + (EM ? a.cap : 0);		/* [2][cstn]: first entry, first
+	unsigned short *cst2_s = csc_s + (P2 ? a.cap : 0);		/* [2][cstn]: first entry, first
 									 * lane, locus/allele per column,
 									 * column per lane; two tiles (the
 									 * fold still reads one while the
@@ -457,13 +256,13 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 		const int lend = lt1 * LT < a.L ? lt1 * LT : a.L;
 		const int row0 = a.off[l0];
 		const int chunk_rows = a.off[lend] - row0;
-		double *G_u = EM ? a.Gacc + ((size_t)r * a.T + row0) * KR : nullptr;
+		double *G_u = P2 ? a.Gacc + ((size_t)r * a.T + row0) * KR : nullptr;
 		double prod = 1.0, ll_slow = 0.0;
 		long long esum = 0;
-		double e[KR], A[EM ? KR : 1];
+		double e[KR], A[HAS_A ? KR : 1];
 
 		__syncthreads();
-		if (EM)
+		if (P2)
 			for (int x = t; x < chunk_rows * KP; x += A3_THREADS)
 				a3_stcg2(G_u + 2 * (size_t)x, make_double2(0.0, 0.0), pol_keep);
 
@@ -478,7 +277,9 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 			const size_t tix = (size_t)it * a.n_ltiles + lt;
 			const uint2 *src = reinterpret_cast<const uint2 *>(a.codes)
 				+ (tix * A3_THREADS + t) * NH;
-			if (NH == 2) {
+			if (!P1) {
+				/* no pass 1: the codes are not read */
+			} else if (NH == 2) {
 				uint4 v;
 				asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
 					: "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src), "l"(pol_stream));
@@ -506,21 +307,29 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 				rb_s[buf * 16 + t] = lf + t < a.L ? a.off[lf + t] - trow0 : 0;
 			a3_cp_async_commit();
 		};
+		auto stage_rb = [&](int lt, int buf) {	/* row bases when there is no p tile */
+			const int lf = lt * LT;
+			if (t < LT)
+				rb_s[buf * 16 + t] = lf + t < a.L ? a.off[lf + t] - a.off[lf] : 0;
+		};
 		auto stage_lists = [&](long long it, int lt, int buf) {
 			const size_t tix = (size_t)it * a.n_ltiles + lt;
 			unsigned short *cst_s = cst2_s + buf * cstn;
 			for (int x = t * 8; x < a.cap; x += A3_THREADS * 8)
-				a3_cp_async16_stream(csc_s + x, a.csc + tix * a.cap + x, pol_stream);
+				a3_cp_async16(csc_s + x, a.csc + tix * a.cap + x);
 			if (t * 8 < cstn)
-				a3_cp_async16_stream(cst_s + t * 8, a.colstart + tix * cstn + t * 8, pol_stream);
+				a3_cp_async16(cst_s + t * 8, a.colstart + tix * cstn + t * 8);
 			a3_cp_async_commit();
 		};
 
 		fetch_regs(it0, lt0);
-		stage_p(lt0, 0);
-		if (EM) {
+		if (P1)
+			stage_p(lt0, 0);
+		else
+			stage_rb(lt0, 0);
+		if (P2) {
 			stage_lists(it0, lt0, 0);
-			/* the E+M sweep keeps two barriers per tile (after pass 1, after
+			/* the two-pass sweeps keep two barriers per tile (after pass 1, after
 			 * pass 2); the first tile's p rows are waited for here */
 			a3_cp_async_wait<0>();
 			__syncthreads();
@@ -531,13 +340,17 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 			const long long i = it * A3_IT + t;
 			const long long ic = i < a.I ? i : a.I - 1;
 
+			if (HAS_E) {
 #pragma unroll
-			for (int k = 0; k < KR; k++)
-				e[k] = k < a.K ? __ldg(a.eta + (size_t)ic * a.eta_stride + k) : 0.0;
-			if (EM) {
+				for (int k = 0; k < KR; k++)
+					e[k] = k < a.K ? __ldg(a.eta + (size_t)ic * a.eta_stride + k) : 0.0;
+			}
+			if (HAS_A) {
 #pragma unroll
 				for (int k = 0; k < KR; k++)
 					A[k] = 0.0;
+			}
+			if (P2) {
 				/* every reader of the previous tile's eta rows is past the
 				 * barrier that follows pass 2 */
 				double2 *dst = reinterpret_cast<double2 *>(eta_s + (size_t)t * NP * 2);
@@ -561,7 +374,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 
 				if (more)
 					fetch_regs(itn, ltn);
-				if (!EM) {
+				if (!P2) {
 					a3_cp_async_wait<0>();
 					__syncthreads();
 				}
@@ -571,7 +384,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 
 				/* ---- pass 1: tmp, w, A, log likelihood; rounds of 8 copies ---- */
 #pragma unroll 1
-				for (int hh = 0; hh < NH; hh++) {
+				for (int hh = 0; P1 && hh < NH; hh++) {
 				const uint2 cw = (NH == 2 && hh) ? cwa[NH - 1] : cwa[0];
 				const int *rbh = rb + hh * LH;
 				double pr[2][KR];
@@ -595,6 +408,12 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					const int z = q & 1;
 					if (q + 1 < 8)
 						load_row(q + 1, z ^ 1);
+					if (MODE == A3_MIX_E) {	/* a_ik += log p_klj of an observed copy */
+#pragma unroll
+						for (int k = 0; k < KR; k++)
+							A[k] += valid[z] ? pr[z][k] : 0.0;
+						continue;
+					}
 					double s0 = 0.0, s1 = 0.0;
 #pragma unroll
 					for (int kp = 0; kp < KP; kp++) {
@@ -602,7 +421,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 						s1 = fma(e[2 * kp + 1], pr[z][2 * kp + 1], s1);
 					}
 					const double tmp = valid[z] ? s0 + s1 : 1.0;
-					if (EM) {
+					if (MODE == A3_ADMIX_EM) {
 						const double wgt = valid[z] ? mc_rcp(tmp) : 0.0;
 #pragma unroll
 						for (int k = 0; k < KR; k++)
@@ -651,15 +470,15 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					}
 				}
 				}
-				if (EM)
+				if (P2)
 					a3_cp_async_wait<0>();
 				__syncthreads();
 				/* p_s is free: the next tile's p rows travel during pass 2 */
-				if (more)
+				if (more && P1)
 					stage_p(ltn, buf ^ 1);
 				else
 					a3_cp_async_commit();	/* keeps the group count in step */
-				if (!EM)
+				if (!P2)
 					continue;
 
 				/* ---- pass 2: G_lj += eta_i w over the lane's entries ---- */
@@ -685,17 +504,23 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					};
 					unsigned e0 = x < xe ? a3_lds_u16(x) : 0u;
 					unsigned e1 = x + S2 < xe ? a3_lds_u16(x + S2) : 0u;
-					double w0 = x < xe ? a3_lds_f64(w_addr(e0)) : 0.0;
+					double w0 = (HAS_W && x < xe) ? a3_lds_f64(w_addr(e0)) : 0.0;
 					while (x < xe) {
 						const unsigned rm = eta_sa + (e0 & (A3_IT - 1)) * (NP * 16);
-						const double wc = w0;
+						/* mixture: the weight is the number of copies of the allele,
+						 * made a double as 2^52 + n - 2^52 (an I2F.F64 here came out
+						 * of ptxas 12.9 with its source inside the destination pair
+						 * for even KP and faulted as an illegal instruction on B200) */
+						const double wc = HAS_W ? w0
+							: __hiloint2double(0x43300000, (int)((e0 >> 12) + 1)) - 4503599627370496.0;
 						const unsigned e2 = x + 2 * S2 < xe ? a3_lds_u16(x + 2 * S2) : 0u;
 						double2 v[KP];
 #pragma unroll
 						for (int s = 0; s < KP; s++)
 							v[s] = a3_lds_f64x2(rm + (s << 4));
 						x += S2;
-						w0 = x < xe ? a3_lds_f64(w_addr(e1)) : 0.0;
+						if (HAS_W)
+							w0 = x < xe ? a3_lds_f64(w_addr(e1)) : 0.0;
 #pragma unroll
 						for (int s = 0; s < KP; s++) {
 							g[2 * s] = fma(v[s].x, wc, g[2 * s]);
@@ -712,10 +537,13 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 						= make_double2(g[2 * pc], g[2 * pc + 1]);
 				a3_cp_async_wait<0>();	/* the next tile's p rows */
 				__syncthreads();
-				if (more)
+				if (more) {
+					if (!P1)
+						stage_rb(ltn, buf ^ 1);
 					stage_lists(itn, ltn, buf ^ 1);
-				else
+				} else {
 					a3_cp_async_commit();
+				}
 
 				/* ---- fold: thread <-> (column, piece), lanes in order; the
 				 * column's running sum lives in L2 ---- */
@@ -754,7 +582,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					a3_stcg2(dst, v, pol_keep);
 				}
 			}
-			if (EM) {
+			if (HAS_A) {
 				double *dst = a.Apart + ((size_t)c * a.Ipad + i) * a.K;
 #pragma unroll
 				for (int k = 0; k < KR; k++)
@@ -764,17 +592,21 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 		}
 		a3_cp_async_wait<0>();
 
-		/* ---- flush the chunk's allele sums: N_klj = p_klj G_klj ---- */
-		if (EM) {
+		/* ---- flush the chunk's allele sums: N_klj = p_klj G_klj (the mixture's
+		 * sums are the counts themselves) ---- */
+		if (P2) {
 			__syncthreads();
 			double *Np = a.Npart + (size_t)r * a.K * a.T;
 			for (int x = t; x < chunk_rows * a.K; x += A3_THREADS) {
 				const int k = x / chunk_rows, row = x - k * chunk_rows;
 				const size_t gx = (size_t)k * a.T + row0 + row;
-				Np[gx] = __ldcg(G_u + (size_t)row * KR + k) * __ldg(a.p + gx);
+				const double gv = __ldcg(G_u + (size_t)row * KR + k);
+				Np[gx] = MODE == A3_ADMIX_EM ? gv * __ldg(a.p + gx) : gv;
 			}
 		}
 		/* ---- log likelihood of the unit ---- */
+		if (!HAS_TMP)
+			continue;
 		double ll = log(prod) + (double)esum * 0.693147180559945309417232121458 + ll_slow;
 #pragma unroll
 		for (int mm = 16; mm >= 1; mm >>= 1)

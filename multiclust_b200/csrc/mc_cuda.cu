@@ -19,9 +19,10 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include "mc_cuda.h"
+#include "mc_dispatch.h"
 #include "mc_kernels.cuh"
-#include "mc_admix3.cuh"
-#include "mc_dense.cuh"
+#include "mc_admix3_build.cuh"
+#include "mc_dense_build.cuh"
 
 #define KH_MAX 6
 #define SMEM_LIMIT (227 * 1024)
@@ -630,7 +631,7 @@ static int alloc_outputs(mc_ctx *c, int n_tiles, int n_chunks, int n_units, long
 static int make_plan3(mc_ctx *c)
 {
 	c->use3 = false;
-	if (!c->admixture || c->PP > 8 || c->K > 16 || c->T < 1)
+	if (c->PP > 8 || c->K > 16 || c->T < 1)
 		return MC_OK;
 	if (c->opt_kernel == MC_KERNEL_TILE || c->opt_kernel == MC_KERNEL_DENSE)
 		return MC_OK;
@@ -725,14 +726,17 @@ static int make_plan3(mc_ctx *c)
 	const int ncolmax = c->l3_ncolmax, max_tile_rows = c->l3_max_tile_rows;
 
 	/* shared memory holds the tile only; the chunk's allele sums live in L2 */
-	c->smem3 = a3_smem_bytes(KP, true, ncolmax, cap);
-	c->smem3_ll = a3_smem_bytes(KP, false, ncolmax, cap);
-	const size_t smem_cap = (size_t)(228 * 1024) / A3_CTAS_PER_SM - 1024 - 64;
-	if (c->smem3 + 64 > smem_cap || max_tile_rows > A3_PR) {
+	c->smem3 = a3_smem_bytes(KP, c->admixture ? A3_ADMIX_EM : A3_MIX_M, ncolmax, cap);
+	c->smem3_ll = a3_smem_bytes(KP, c->admixture ? A3_ADMIX_LL : A3_MIX_E, ncolmax, cap);
+	/* two CTAs per SM while the tile fits twice (K <= 10 at 16 copies per tile),
+	 * else one */
+	const size_t smem_cap2 = (size_t)(228 * 1024) / A3_CTAS_PER_SM - 1024 - 64;
+	const size_t smem_cap1 = (size_t)(227 * 1024) - 64;
+	if (c->smem3 + 64 > smem_cap1 || max_tile_rows > A3_PR) {
 		free_layout3(c);	/* the one-pass kernel takes over: drop the multi-GB lists */
 		return MC_OK;
 	}
-	const long long sms = (long long)c->num_sms * A3_CTAS_PER_SM;
+	const long long sms = (long long)c->num_sms * (c->smem3 + 64 > smem_cap2 ? 1 : A3_CTAS_PER_SM);
 
 	/* locus chunks x individual chunks: ~13 us per (256 individuals x 16 copies)
 	 * tile with two CTAs per SM */
@@ -769,43 +773,16 @@ static int make_plan3(mc_ctx *c)
 	return MC_OK;
 }
 
-typedef void (*admix3_fn)(const Admix3Args);
-
-template <int KP, int MODE> static admix3_fn pick3_pp(int PP)
-{
-	switch (PP) {
-	case 1: return admix3_kernel<KP, 1, MODE>;
-	case 2: return admix3_kernel<KP, 2, MODE>;
-	case 4: return admix3_kernel<KP, 4, MODE>;
-	case 8: return admix3_kernel<KP, 8, MODE>;
-	}
-	return nullptr;
-}
-
-template <int MODE> static admix3_fn pick3(int KP, int PP)
-{
-	switch (KP) {
-	case 1: return pick3_pp<1, MODE>(PP);
-	case 2: return pick3_pp<2, MODE>(PP);
-	case 3: return pick3_pp<3, MODE>(PP);
-	case 4: return pick3_pp<4, MODE>(PP);
-	case 5: return pick3_pp<5, MODE>(PP);
-	case 6: return pick3_pp<6, MODE>(PP);
-	case 7: return pick3_pp<7, MODE>(PP);
-	case 8: return pick3_pp<8, MODE>(PP);
-	}
-	return nullptr;
-}
-
-static int launch_admix3(mc_ctx *c, int ll_only, const double *p, const double *eta,
+/* mode: A3_ADMIX_EM / A3_ADMIX_LL / A3_MIX_E (p = the log p table) / A3_MIX_M (eta = v_ik) */
+static int launch_admix3(mc_ctx *c, int mode, const double *p, const double *eta,
 	long long eta_stride)
 {
-	admix3_fn fn = ll_only ? pick3<1>(c->KP3, c->PP) : pick3<0>(c->KP3, c->PP);
+	admix3_fn fn = mc_pick_admix3(mode, c->KP3, c->PP);
 	if (!fn)
 		return fail(c, MC_ERR_UNSUPPORTED, "no admix3 kernel for K=%d P=%d", c->K, c->P);
 	Admix3Args a = c->a3;
 	a.p = p; a.eta = eta; a.eta_stride = eta_stride;
-	const size_t smem = ll_only ? c->smem3_ll : c->smem3;
+	const size_t smem = a3_smem_bytes(c->KP3, mode, a.ncolmax, a.cap);
 	{
 		const int rca = raise_smem_limit(c, (const void *)fn, smem);
 		if (rca)
@@ -818,7 +795,9 @@ static int launch_admix3(mc_ctx *c, int ll_only, const double *p, const double *
 		CK(cudaEventRecord(e0, c->stream));
 	}
 	fn<<<c->grid3, A3_THREADS, smem, c->stream>>>(a);
-	LAUNCH_CHECK("admix3_kernel");
+	LAUNCH_CHECK(mode == A3_ADMIX_EM ? "admix3_kernel<ADMIX_EM>" : mode == A3_ADMIX_LL
+		? "admix3_kernel<ADMIX_LL>" : mode == A3_MIX_E ? "admix3_kernel<MIX_E>"
+		: "admix3_kernel<MIX_M>");
 	if (c->profile) {
 		CK(cudaEventRecord(e1, c->stream));
 		c->prof_events.push_back({ e0, e1 });
@@ -912,41 +891,12 @@ static int make_plan_dense(mc_ctx *c)
 	return MC_OK;
 }
 
-typedef void (*dense_fn)(const DenseArgs);
-
-template <int NB, int MODE> static dense_fn pick_dn_bits(int pmax)
-{
-	switch (pmax) {
-	case 1: return dense_kernel<NB, 1, MODE>;
-	case 2: return dense_kernel<NB, 2, MODE>;
-	case 4: return dense_kernel<NB, 4, MODE>;
-	case 7: return dense_kernel<NB, 7, MODE>;
-	case 15: return dense_kernel<NB, 15, MODE>;
-	}
-	return nullptr;
-}
-
-static dense_fn pick_dn(int NB, int pbits, int mode)
-{
-	switch (mode) {
-	case DN_ADMIX_EM:
-		return NB == 1 ? pick_dn_bits<1, DN_ADMIX_EM>(pbits) : pick_dn_bits<2, DN_ADMIX_EM>(pbits);
-	case DN_ADMIX_LL:
-		return NB == 1 ? pick_dn_bits<1, DN_ADMIX_LL>(pbits) : pick_dn_bits<2, DN_ADMIX_LL>(pbits);
-	case DN_MIX_E:
-		return NB == 1 ? dense_kernel<1, 1, DN_MIX_E> : dense_kernel<2, 1, DN_MIX_E>;
-	case DN_MIX_M:
-		return NB == 1 ? dense_kernel<1, 1, DN_MIX_M> : dense_kernel<2, 1, DN_MIX_M>;
-	}
-	return nullptr;
-}
-
 /* `ptab`: the [K][T] table the dense p fragments are built from (p, or log p
  * for the mixture E pass; nullptr for the mixture M pass) */
 static int launch_dense(mc_ctx *c, int mode, const double *ptab, const double *p,
 	const double *eta, long long eta_stride)
 {
-	dense_fn fn = pick_dn(c->dn_NB, c->dn_pbits, mode);
+	dense_fn fn = mc_pick_dense(c->dn_NB, c->dn_pbits, mode);
 	if (!fn)
 		return fail(c, MC_ERR_UNSUPPORTED, "no dense kernel for K=%d P=%d", c->K, c->P);
 	DenseArgs a = c->dn;
@@ -1193,48 +1143,10 @@ extern "C" int mc_copy_slot(mc_ctx *c, int dst, int src)
 
 /* --------------------------------------------------- tile kernel dispatch */
 
-typedef void (*tile_fn)(const TileArgs);
-
-template <int KH, int MODE> static tile_fn pick_pp(int PP)
-{
-	switch (PP) {
-	case 1: return tile_kernel<KH, 1, MODE>;
-	case 2: return tile_kernel<KH, 2, MODE>;
-	case 4: return tile_kernel<KH, 4, MODE>;
-	case 8: return tile_kernel<KH, 8, MODE>;
-	case 16: return tile_kernel<KH, 16, MODE>;
-	}
-	return nullptr;
-}
-
-template <int MODE> static tile_fn pick_kh(int KH, int PP)
-{
-	switch (KH) {
-	case 1: return pick_pp<1, MODE>(PP);
-	case 2: return pick_pp<2, MODE>(PP);
-	case 3: return pick_pp<3, MODE>(PP);
-	case 4: return pick_pp<4, MODE>(PP);
-	case 5: return pick_pp<5, MODE>(PP);
-	case 6: return pick_pp<6, MODE>(PP);
-	}
-	return nullptr;
-}
-
-static tile_fn pick_kernel(int mode, int KH, int PP)
-{
-	switch (mode) {
-	case MODE_ADMIX_EM: return pick_kh<MODE_ADMIX_EM>(KH, PP);
-	case MODE_ADMIX_LL: return pick_kh<MODE_ADMIX_LL>(KH, PP);
-	case MODE_MIX_E: return pick_kh<MODE_MIX_E>(KH, PP);
-	case MODE_MIX_M: return pick_kh<MODE_MIX_M>(KH, PP);
-	}
-	return nullptr;
-}
-
 static int launch_tile(mc_ctx *c, int mode, const double *p, const double *eta,
 	long long eta_stride)
 {
-	tile_fn fn = pick_kernel(mode, c->KH, c->PP);
+	tile_fn fn = mc_pick_tile(mode, c->KH, c->PP);
 	if (!fn)
 		return fail(c, MC_ERR_UNSUPPORTED, "no kernel for KH=%d PP=%d", c->KH, c->PP);
 	TileArgs ta = c->ta;
@@ -1328,7 +1240,7 @@ extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 			? launch_dense(c, DN_ADMIX_EM, c->d_p[from], c->d_p[from], c->d_eta[from],
 				c->per_indiv ? K : 0)
 			: c->use3
-			? launch_admix3(c, 0, c->d_p[from], c->d_eta[from], c->per_indiv ? K : 0)
+			? launch_admix3(c, A3_ADMIX_EM, c->d_p[from], c->d_eta[from], c->per_indiv ? K : 0)
 			: launch_tile(c, MODE_ADMIX_EM, c->d_p[from], c->d_eta[from],
 				c->per_indiv ? K : 0);
 		if (rc) return rc;
@@ -1368,10 +1280,12 @@ extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 			c->d_logp, c->np, 1);
 		LAUNCH_CHECK("k_log_table");
 		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_E, c->d_logp, nullptr, nullptr, 0)
+			: c->use3 ? launch_admix3(c, A3_MIX_E, c->d_logp, nullptr, 0)
 			: launch_tile(c, MODE_MIX_E, c->d_logp, nullptr, 0))) return rc;
 		if ((rc = mix_tail(c, c->d_eta[from], c->d_post, 0))) return rc;
 		if ((rc = reduce_vector(c, c->d_lli, c->I, xb_ll(c)))) return rc;
 		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_M, nullptr, nullptr, c->d_post, K)
+			: c->use3 ? launch_admix3(c, A3_MIX_M, nullptr, c->d_post, K)
 			: launch_tile(c, MODE_MIX_M, nullptr, c->d_post, K))) return rc;
 		if (!c->fused_step) {
 			k_sum_chunks<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_Npart,
@@ -1749,7 +1663,7 @@ static int loglik_launch(mc_ctx *c, int slot)
 			? launch_dense(c, DN_ADMIX_LL, c->d_p[slot], c->d_p[slot], c->d_eta[slot],
 				c->per_indiv ? c->K : 0)
 			: c->use3
-			? launch_admix3(c, 1, c->d_p[slot], c->d_eta[slot], c->per_indiv ? c->K : 0)
+			? launch_admix3(c, A3_ADMIX_LL, c->d_p[slot], c->d_eta[slot], c->per_indiv ? c->K : 0)
 			: launch_tile(c, MODE_ADMIX_LL, c->d_p[slot], c->d_eta[slot],
 				c->per_indiv ? c->K : 0);
 		if (rc) return rc;
@@ -1759,6 +1673,7 @@ static int loglik_launch(mc_ctx *c, int slot)
 			c->d_logp, c->np, 0);
 		LAUNCH_CHECK("k_log_table");
 		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_E, c->d_logp, nullptr, nullptr, 0)
+			: c->use3 ? launch_admix3(c, A3_MIX_E, c->d_logp, nullptr, 0)
 			: launch_tile(c, MODE_MIX_E, c->d_logp, nullptr, 0))) return rc;
 		/* the posterior of the last E-step must survive: only the per-
 		 * individual ll buffer is written */

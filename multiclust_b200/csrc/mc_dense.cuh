@@ -44,6 +44,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "mc_device.cuh"
+
 #define DN_THREADS 256
 #define DN_IT 256		/* individuals per tile */
 #define DN_TL 16		/* loci per tile */
@@ -73,75 +75,6 @@ struct DenseArgs {
 };
 
 /* ---------------------------------------------------------------------- */
-/* one-time layout builders                                                 */
-
-/* largest allele code in the data (255 = missing is skipped) */
-__global__ void k_dense_maxcode(const unsigned char *nat, long long n, unsigned *out)
-{
-	unsigned m = 0;
-	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
-		x += (long long)gridDim.x * blockDim.x) {
-		const unsigned c = nat[x];
-		if (c != 255u && c > m)
-			m = c;
-	}
-	for (int s = 16; s >= 1; s >>= 1)
-		m = max(m, __shfl_xor_sync(0xffffffffu, m, s));
-	if ((threadIdx.x & 31) == 0 && m)
-		atomicMax(out, m);
-}
-
-/* natural [I][L][P] codes -> c0 | c1 << 4 per (individual, locus), tile major */
-__global__ void k_dense_counts(const unsigned char *nat, unsigned char *cnt,
-	long long I, int L, int P, int n_itiles, int n_ltiles)
-{
-	const long long n = (long long)n_itiles * n_ltiles * DN_IT;
-	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
-		x += (long long)gridDim.x * blockDim.x) {
-		const int row = (int)(x % DN_IT);
-		const long long tix = x / DN_IT;
-		const int lt = (int)(tix % n_ltiles);
-		const long long i = (tix / n_ltiles) * DN_IT + row;
-		unsigned w[4] = { 0u, 0u, 0u, 0u };
-		if (i < I)
-			for (int s = 0; s < DN_TL; s++) {
-				const int l = lt * DN_TL + s;
-				if (l >= L)
-					break;
-				const unsigned char *c = nat + ((size_t)i * L + l) * P;
-				unsigned c0 = 0, c1 = 0;
-				for (int a = 0; a < P; a++) {
-					c0 += c[a] == 0;
-					c1 += c[a] == 1;
-				}
-				w[s >> 2] |= (c0 | c1 << 4) << ((s & 3) * 8);
-			}
-		*reinterpret_cast<uint4 *>(cnt + (size_t)x * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-	}
-}
-
-/* p (or log p) [K][T] -> dense [locus][k][allele] with the fragment pitch;
- * minus infinity (log 0, only without the projection) becomes -DBL_MAX so that
- * a zero count still contributes zero */
-__global__ void k_dense_p(const double *p, double *pd, const int *off, const int *J,
-	int K, int L, long long T, int n_loci_pad, int PL, int K8)
-{
-	const long long n = (long long)n_loci_pad * K8 * 2;
-	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
-		x += (long long)gridDim.x * blockDim.x) {
-		const int a = (int)(x & 1), k = (int)((x >> 1) % K8);
-		const int l = (int)(x / (2 * K8));
-		double v = 0.0;
-		if (l < L && k < K && a < J[l]) {
-			v = p[(size_t)k * T + off[l] + a];
-			if (v == -INFINITY)
-				v = -1.7976931348623157e308;
-		}
-		pd[(size_t)l * PL + 2 * k + a] = v;
-	}
-}
-
-/* ---------------------------------------------------------------------- */
 
 __device__ __forceinline__ void dn_mma(double &c0, double &c1, double a, double b)
 {
@@ -159,7 +92,7 @@ __device__ __forceinline__ void dn_cp_async16(void *smem_dst, const void *gsrc)
 /* log-likelihood terms the mantissa product cannot take (never seen in a
  * healthy fit); out of line: sixteen inlined copies of log() per tile would
  * push the tile loop out of the instruction cache */
-__device__ __noinline__ double dn_slow_ll(double t0, double t1, unsigned c0, unsigned c1)
+static __device__ __noinline__ double dn_slow_ll(double t0, double t1, unsigned c0, unsigned c1)
 {
 	double s = 0.0;
 	if (c0)
@@ -503,59 +436,3 @@ __global__ void __launch_bounds__(DN_THREADS, DN_CTAS_PER_SM) dense_kernel(const
 	}
 }
 
-/* ---------------------------------------------------------------------- */
-/* mixture tail: a_ik = log eta_k + sum over locus chunks, then the softmax
- * of the E-step (em_alg.c:828-882) or the guarded log-sum-exp of
- * logL_mixture (log_likelihood.c:203-228).  One thread per (individual, k)
- * adds the chunk partial sums (a warp reads contiguous runs of Apart), one
- * thread per individual finishes the row. */
-#define MT_ROWS 32
-__global__ void k_mix_tail(const double *Apart, int n_chunks, long long Ipad, long long I,
-	int K, const double *eta, double *vik, double *ll_i, int ll_only)
-{
-	extern __shared__ double mt_rows[];	/* [MT_ROWS][K] */
-	const int n = MT_ROWS * K;
-	for (long long i0 = (long long)blockIdx.x * MT_ROWS; i0 < I; i0 += (long long)gridDim.x * MT_ROWS) {
-		for (int x = threadIdx.x; x < n; x += blockDim.x) {
-			const long long i = i0 + x / K;
-			if (i >= I)
-				continue;
-			const double *src = Apart + (size_t)i0 * K + x;
-			const size_t ts = (size_t)Ipad * K;
-			double acc = 0.0;
-			for (int c = 0; c < n_chunks; c++)
-				acc += __ldg(src + (size_t)c * ts);
-			mt_rows[x] = acc + log(eta[x % K]);
-		}
-		__syncthreads();
-		if (threadIdx.x < MT_ROWS && i0 + threadIdx.x < I) {
-			const long long i = i0 + threadIdx.x;
-			const double *v = mt_rows + threadIdx.x * K;
-			double mx = -INFINITY;
-			for (int k = 0; k < K; k++)
-				mx = v[k] > mx ? v[k] : mx;
-			if (!ll_only) {
-				double s = 0.0;
-				for (int k = 0; k < K; k++)
-					s += exp(v[k] - mx);
-				for (int k = 0; k < K; k++)
-					vik[(size_t)i * K + k] = exp(v[k] - mx) / s;
-				ll_i[i] = log(s) + mx;
-			} else {
-				double te = exp(mx), scale = 0.0, s = 0.0;
-				if (te == 0.0 || te == HUGE_VAL) {
-					scale = (te == HUGE_VAL) ? mx : -mx;
-					do {
-						scale *= 0.5;
-						te = exp(scale);
-					} while (te == HUGE_VAL);
-					scale = mx - scale;
-				}
-				for (int k = 0; k < K; k++)
-					s += exp(v[k] - scale);
-				ll_i[i] = log(s) + scale;
-			}
-		}
-		__syncthreads();
-	}
-}

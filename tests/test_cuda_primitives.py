@@ -369,3 +369,33 @@ def test_locale_sums_and_mixture_init(orc, tmp_path):
         assert np.max(np.abs(got - ref)) < 1e-12
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("admixture", [1, 0])
+def test_every_gather_kernel_instantiation(orc, tmp_path, P, admixture):
+    """every (K pair count, padded ploidy) instantiation of the two-pass gather kernel
+    -- admixture E+M / log likelihood and the mixture E / M modes -- runs one EM step
+    and one log-likelihood pass against the oracle (a miscompiled instantiation shows up
+    as a launch failure or a wrong number, not as an untested path)"""
+    from multiclust_b200 import Context
+    I, L = 40, 24
+    d = gen_data(tmp_path, I, L, K=3, jmax=6, miss=300, P=P)
+    c = Context(0)
+    try:
+        c.set_option(c.OPT_KERNEL, c.KERNEL_ADMIX3)
+        c.set_data(d["J"], d["codes"])
+        for K in range(1, 17):
+            fit = orc.Fit(d["J"], d["codes"], admixture=admixture)
+            fit.alloc(K)
+            lb = fit.lower_bound
+            c.alloc_model(K, admixture=admixture, q=0, eta_lb=lb, p_lb=lb)
+            assert c.plan()["two_pass"] == 2
+            eta, p = random_params(np.random.default_rng(100 * K + P), I, K, d["J"], bool(admixture))
+            fit.set_params(0, eta, p)
+            c.set_params(0, eta, p)
+            ll_o = fit.log_likelihood(0)
+            assert abs(c.loglik(0) - ll_o) <= 1e-12 * abs(ll_o), (K, P)
+            check_step(orc, c, fit, 0, 1)
+    finally:
+        c.close()
