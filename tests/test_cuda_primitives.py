@@ -399,3 +399,51 @@ def test_every_gather_kernel_instantiation(orc, tmp_path, P, admixture):
             check_step(orc, c, fit, 0, 1)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("admixture", [1, 0])
+@pytest.mark.parametrize("kernel", [0, 1, 2])
+def test_degenerate_loci(orc, admixture, kernel):
+    """hand-made biallelic data with a monomorphic locus (J = 1), a locus where everybody is
+    missing (J = 0, read_file.c:525-526), a locus with one observed allele plus the phantom
+    slot (J = 2) and an individual without any data at several loci: every kernel family
+    against the oracle (kernel 0 picks the dense DMMA path here)"""
+    from multiclust_b200 import Context
+    rng = np.random.default_rng(42)
+    I, L, P, K = 37, 21, 2, 3
+    codes = rng.integers(0, 2, size=(I, L, P)).astype(np.uint8)
+    miss = rng.random((I, L, P)) < 0.1
+    codes[miss] = 255
+    codes[5, :10, :] = 255                  # an individual with little data
+    codes[:, 3, :] = 0                      # monomorphic, nobody missing: J = 1
+    codes[:, 7, :] = 255                    # all missing: J = 0
+    codes[:, 11, :] = 0
+    codes[::5, 11, 0] = 255                 # one allele + phantom slot: J = 2
+    J = np.zeros(L, dtype=np.int32)
+    for l in range(L):
+        obs = codes[:, l, :][codes[:, l, :] != 255]
+        nreal = int(obs.max()) + 1 if obs.size else 0
+        # the allele codes must be dense: relabel a locus that only shows allele 1
+        if nreal == 2 and not (obs == 0).any():
+            codes[:, l, :][codes[:, l, :] == 1] = 0
+            nreal = 1
+        J[l] = nreal + (1 if nreal and (codes[:, l, :] == 255).any() else 0)
+    assert J[3] == 1 and J[7] == 0 and J[11] == 2
+    fit = orc.Fit(J, codes, admixture=admixture)
+    fit.alloc(K)
+    lb = fit.lower_bound
+    c = Context(0)
+    try:
+        c.set_option(c.OPT_KERNEL, kernel)
+        c.set_data(J, codes)
+        c.alloc_model(K, admixture=admixture, q=0, eta_lb=lb, p_lb=lb)
+        assert c.plan()["two_pass"] == {0: 3, 1: 0, 2: 2}[kernel]
+        eta, p = random_params(np.random.default_rng(5), I, K, J, bool(admixture))
+        fit.set_params(0, eta, p)
+        c.set_params(0, eta, p)
+        ll_o = fit.log_likelihood(0)
+        assert abs(c.loglik(0) - ll_o) <= 1e-12 * abs(ll_o)
+        check_step(orc, c, fit, 0, 1)
+        check_step(orc, c, fit, 1, 1)
+    finally:
+        c.close()
