@@ -59,7 +59,8 @@ struct mc_ctx {
 	double *d_eta[3] = { nullptr, nullptr, nullptr };
 	std::vector<double *> d_up, d_vp, d_ue, d_ve;
 	double *d_post = nullptr;	/* D_ik or v_ik [I][K] */
-	double *d_lli = nullptr;	/* mixture: per-individual ll [I] */
+	double *d_lli = nullptr;	/* mixture: per-block partial sums of the tail */
+	long long lli_n = 0;
 	double *d_logp = nullptr;	/* mixture: log p table [K][T] */
 
 	/* plan */
@@ -891,10 +892,10 @@ static int make_plan_dense(mc_ctx *c)
 	return MC_OK;
 }
 
-/* `ptab`: the [K][T] table the dense p fragments are built from (p, or log p
- * for the mixture E pass; nullptr for the mixture M pass) */
+/* `ptab`: the [K][T] table the dense p fragments are built from (p; its log,
+ * take_log as in k_dense_p, for the mixture E pass; nullptr for the M pass) */
 static int launch_dense(mc_ctx *c, int mode, const double *ptab, const double *p,
-	const double *eta, long long eta_stride)
+	const double *eta, long long eta_stride, int take_log = 0)
 {
 	dense_fn fn = mc_pick_dense(c->dn_NB, c->dn_pbits, mode);
 	if (!fn)
@@ -904,7 +905,8 @@ static int launch_dense(mc_ctx *c, int mode, const double *ptab, const double *p
 	if (ptab) {
 		const int K8 = 8 * c->dn_NB, npad = a.n_ltiles * DN_TL;
 		k_dense_p<<<grid_for(c, (long long)npad * K8 * 2, 256), 256, 0, c->stream>>>(ptab,
-			c->d_dn_pd, c->d_off, c->d_J, c->K, c->L, c->T, npad, dn_pl(c->dn_NB), K8);
+			c->d_dn_pd, c->d_off, c->d_J, c->K, c->L, c->T, npad, dn_pl(c->dn_NB), K8,
+			take_log);
 		LAUNCH_CHECK("k_dense_p");
 	}
 	const size_t smem = dn_smem_bytes(c->dn_NB, mode, a.max_chunk_tiles);
@@ -1075,7 +1077,8 @@ extern "C" int mc_alloc_model(mc_ctx *c, int32_t K, int admixture,
 	CK(cudaMemsetAsync(c->d_post, 0, sizeof(double) * (size_t)c->I * K, c->stream));
 	CK(MC_DEV_MALLOC(&c->d_IK, sizeof(int) * (size_t)c->I));
 	if (!c->admixture) {
-		CK(MC_DEV_MALLOC(&c->d_lli, sizeof(double) * (size_t)c->I));
+		c->lli_n = std::max<long long>(c->I, (long long)c->num_sms * 4 * (K + 1));
+		CK(MC_DEV_MALLOC(&c->d_lli, sizeof(double) * (size_t)c->lli_n));
 		CK(MC_DEV_MALLOC(&c->d_logp, npb));
 	}
 	int rc = make_plan(c);
@@ -1216,14 +1219,22 @@ static int join_aux(mc_ctx *c)
 	return MC_OK;
 }
 
-/* mixture E-step tail over the chunk partial sums in Apart */
+/* mixture E-step tail over the chunk partial sums in Apart: posterior rows (or
+ * the guarded log-sum-exp of the log-likelihood pass), and -- fused in -- the
+ * log likelihood and the pooled sums S_k = sum_i v_ik into the exchange buffer */
 static int mix_tail(mc_ctx *c, const double *eta, double *vik, int ll_only)
 {
 	const long long blocks = (c->I + MT_ROWS - 1) / MT_ROWS;
-	k_mix_tail<<<(unsigned)std::min<long long>(blocks, (long long)c->num_sms * 16), 256,
-		sizeof(double) * MT_ROWS * c->K, c->stream>>>(c->d_Apart, c->act_tiles,
-		c->act_Ipad, c->I, c->K, eta, vik, c->d_lli, ll_only);
+	const int grid = (int)std::min<long long>(blocks, (long long)c->num_sms * 4);
+	/* d_lli doubles as the per-block partial sums: grid * (K + 1) <= I */
+	double *part = c->d_lli;
+	if ((long long)grid * (c->K + 1) > c->lli_n)
+		return fail(c, MC_ERR_STATE, "mix_tail: partial-sum buffer too small");
+	k_mix_tail<<<grid, 256, sizeof(double) * (MT_ROWS * c->K + MT_ROWS), c->stream>>>(c->d_Apart,
+		c->act_tiles, c->act_Ipad, c->I, c->K, eta, vik, part, ll_only);
 	LAUNCH_CHECK("k_mix_tail");
+	k_mix_final<<<1, 256, 0, c->stream>>>(part, grid, c->K, xb_ll(c), xb_S(c), ll_only);
+	LAUNCH_CHECK("k_mix_final");
 	return MC_OK;
 }
 
@@ -1276,14 +1287,15 @@ extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 			if ((rc = reduce_columns(c, c->d_post, c->I, K, xb_S(c)))) return rc;
 		}
 	} else {
-		k_log_table<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_p[from],
-			c->d_logp, c->np, 1);
-		LAUNCH_CHECK("k_log_table");
-		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_E, c->d_logp, nullptr, nullptr, 0)
+		if (!c->use_dn) {
+			k_log_table<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_p[from],
+				c->d_logp, c->np, 1);
+			LAUNCH_CHECK("k_log_table");
+		}
+		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_E, c->d_p[from], nullptr, nullptr, 0, 1)
 			: c->use3 ? launch_admix3(c, A3_MIX_E, c->d_logp, nullptr, 0)
 			: launch_tile(c, MODE_MIX_E, c->d_logp, nullptr, 0))) return rc;
 		if ((rc = mix_tail(c, c->d_eta[from], c->d_post, 0))) return rc;
-		if ((rc = reduce_vector(c, c->d_lli, c->I, xb_ll(c)))) return rc;
 		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_M, nullptr, nullptr, c->d_post, K)
 			: c->use3 ? launch_admix3(c, A3_MIX_M, nullptr, c->d_post, K)
 			: launch_tile(c, MODE_MIX_M, nullptr, c->d_post, K))) return rc;
@@ -1292,7 +1304,7 @@ extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 				c->act_chunks, c->np, 0.0, xb_N(c));
 			LAUNCH_CHECK("k_sum_chunks");
 		}
-		if ((rc = reduce_columns(c, c->d_post, c->I, K, xb_S(c)))) return rc;
+		/* S_k = sum_i v_ik is already in the exchange buffer (mix_tail) */
 	}
 	return MC_OK;
 }
@@ -1342,23 +1354,20 @@ extern "C" int mc_em_step_finish(mc_ctx *c, int to, double *ll)
 	int rcj = join_aux(c);
 	if (rcj)
 		return rcj;
-	if (!c->per_indiv) {
-		k_update_eta_pooled<<<1, 32, 0, c->stream>>>(xb_S(c), c->d_eta[to], K,
-			c->do_proj, c->eta_lb);
-		LAUNCH_CHECK("k_update_eta_pooled");
-	}
 	/* the mixture adds the pseudo-count p_lower_bound to every slot
 	 * (em_alg.c:972).  A whole step on one context (mc_em_step) reads the
-	 * chunk sums directly; a split step reads the exchanged totals */
+	 * chunk sums directly; a split step reads the exchanged totals.  The pooled
+	 * eta update rides along */
 	const double add = c->admixture ? 0.0 : c->p_lb;
+	const double *S = c->per_indiv ? nullptr : xb_S(c);
 	if (c->fused_step)
 		k_update_p<<<grid_for(c, (long long)K * c->L, 128), 128, 0, c->stream>>>(
 			c->d_Npart, c->act_chunks, c->np, add, c->d_p[to], c->d_J, c->d_off, K,
-			c->L, c->T, c->do_proj, c->p_lb);
+			c->L, c->T, c->do_proj, c->p_lb, S, c->d_eta[to]);
 	else
 		k_update_p<<<grid_for(c, (long long)K * c->L, 128), 128, 0, c->stream>>>(
 			xb_N(c), 1, 0, add, c->d_p[to], c->d_J, c->d_off, K, c->L, c->T,
-			c->do_proj, c->p_lb);
+			c->do_proj, c->p_lb, S, c->d_eta[to]);
 	LAUNCH_CHECK("k_update_p");
 	c->fused_step = false;
 	if (ll) {
@@ -1669,16 +1678,17 @@ static int loglik_launch(mc_ctx *c, int slot)
 		if (rc) return rc;
 		if ((rc = reduce_vector(c, c->d_llpart, c->act_units, xb_ll(c)))) return rc;
 	} else {
-		k_log_table<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_p[slot],
-			c->d_logp, c->np, 0);
-		LAUNCH_CHECK("k_log_table");
-		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_E, c->d_logp, nullptr, nullptr, 0)
+		if (!c->use_dn) {
+			k_log_table<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_p[slot],
+				c->d_logp, c->np, 0);
+			LAUNCH_CHECK("k_log_table");
+		}
+		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_E, c->d_p[slot], nullptr, nullptr, 0, 2)
 			: c->use3 ? launch_admix3(c, A3_MIX_E, c->d_logp, nullptr, 0)
 			: launch_tile(c, MODE_MIX_E, c->d_logp, nullptr, 0))) return rc;
 		/* the posterior of the last E-step must survive: only the per-
 		 * individual ll buffer is written */
 		if ((rc = mix_tail(c, c->d_eta[slot], nullptr, 1))) return rc;
-		if ((rc = reduce_vector(c, c->d_lli, c->I, xb_ll(c)))) return rc;
 	}
 	return MC_OK;
 }

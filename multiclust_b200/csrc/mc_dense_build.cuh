@@ -54,11 +54,13 @@ __global__ void k_dense_counts(const unsigned char *nat, unsigned char *cnt,
 	}
 }
 
-/* p (or log p) [K][T] -> dense [locus][k][allele] with the fragment pitch;
+/* p [K][T] -> dense [locus][k][allele] with the fragment pitch.  take_log: 0 =
+ * the table as it is; 1 = log p with the E-step's "p == 0 contributes nothing"
+ * rule (em_alg.c:797-804); 2 = plain log p (log_likelihood.c:190-199), where
  * minus infinity (log 0, only without the projection) becomes -DBL_MAX so that
  * a zero count still contributes zero */
 __global__ void k_dense_p(const double *p, double *pd, const int *off, const int *J,
-	int K, int L, long long T, int n_loci_pad, int PL, int K8)
+	int K, int L, long long T, int n_loci_pad, int PL, int K8, int take_log)
 {
 	const long long n = (long long)n_loci_pad * K8 * 2;
 	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
@@ -68,8 +70,11 @@ __global__ void k_dense_p(const double *p, double *pd, const int *off, const int
 		double v = 0.0;
 		if (l < L && k < K && a < J[l]) {
 			v = p[(size_t)k * T + off[l] + a];
-			if (v == -INFINITY)
-				v = -1.7976931348623157e308;
+			if (take_log) {
+				v = (take_log == 1 && v == 0.0) ? 0.0 : log(v);
+				if (v == -INFINITY)
+					v = -1.7976931348623157e308;
+			}
 		}
 		pd[(size_t)l * PL + 2 * k + a] = v;
 	}
@@ -82,11 +87,17 @@ __global__ void k_dense_p(const double *p, double *pd, const int *off, const int
  * adds the chunk partial sums (a warp reads contiguous runs of Apart), one
  * thread per individual finishes the row. */
 #define MT_ROWS 32
+/* ... and the sums the step needs over individuals, fused in: every block adds
+ * up the log likelihood and (E-step) the K posterior columns of its rows in row
+ * order and leaves them in part[block][K + 1] = {S_0..S_{K-1}, ll}; k_mix_final
+ * adds the blocks in block order.  Fixed order, no atomics. */
 __global__ void k_mix_tail(const double *Apart, int n_chunks, long long Ipad, long long I,
-	int K, const double *eta, double *vik, double *ll_i, int ll_only)
+	int K, const double *eta, double *vik, double *part, int ll_only)
 {
-	extern __shared__ double mt_rows[];	/* [MT_ROWS][K] */
+	extern __shared__ double mt_rows[];	/* [MT_ROWS][K] then [MT_ROWS] */
+	double *mt_ll = mt_rows + MT_ROWS * K;
 	const int n = MT_ROWS * K;
+	double acc_col = 0.0;			/* thread k < K: S_k; thread K: ll */
 	for (long long i0 = (long long)blockIdx.x * MT_ROWS; i0 < I; i0 += (long long)gridDim.x * MT_ROWS) {
 		for (int x = threadIdx.x; x < n; x += blockDim.x) {
 			const long long i = i0 + x / K;
@@ -102,7 +113,7 @@ __global__ void k_mix_tail(const double *Apart, int n_chunks, long long Ipad, lo
 		__syncthreads();
 		if (threadIdx.x < MT_ROWS && i0 + threadIdx.x < I) {
 			const long long i = i0 + threadIdx.x;
-			const double *v = mt_rows + threadIdx.x * K;
+			double *v = mt_rows + threadIdx.x * K;
 			double mx = -INFINITY;
 			for (int k = 0; k < K; k++)
 				mx = v[k] > mx ? v[k] : mx;
@@ -110,9 +121,12 @@ __global__ void k_mix_tail(const double *Apart, int n_chunks, long long Ipad, lo
 				double s = 0.0;
 				for (int k = 0; k < K; k++)
 					s += exp(v[k] - mx);
-				for (int k = 0; k < K; k++)
-					vik[(size_t)i * K + k] = exp(v[k] - mx) / s;
-				ll_i[i] = log(s) + mx;
+				for (int k = 0; k < K; k++) {
+					const double vv = exp(v[k] - mx) / s;
+					vik[(size_t)i * K + k] = vv;
+					v[k] = vv;
+				}
+				mt_ll[threadIdx.x] = log(s) + mx;
 			} else {
 				double te = exp(mx), scale = 0.0, s = 0.0;
 				if (te == 0.0 || te == HUGE_VAL) {
@@ -125,9 +139,36 @@ __global__ void k_mix_tail(const double *Apart, int n_chunks, long long Ipad, lo
 				}
 				for (int k = 0; k < K; k++)
 					s += exp(v[k] - scale);
-				ll_i[i] = log(s) + scale;
+				mt_ll[threadIdx.x] = log(s) + scale;
 			}
 		}
 		__syncthreads();
+		const int rows = (int)(I - i0 < MT_ROWS ? I - i0 : MT_ROWS);
+		if ((int)threadIdx.x < K && !ll_only) {
+			for (int r = 0; r < rows; r++)
+				acc_col += mt_rows[r * K + threadIdx.x];
+		} else if ((int)threadIdx.x == K) {
+			for (int r = 0; r < rows; r++)
+				acc_col += mt_ll[r];
+		}
+		__syncthreads();
 	}
+	if ((int)threadIdx.x <= K)
+		part[(size_t)blockIdx.x * (K + 1) + threadIdx.x] = acc_col;
+}
+
+/* out_ll = sum_b part[b][K]; out_S[k] = sum_b part[b][k] (E-step only) */
+__global__ void k_mix_final(const double *part, int blocks, int K, double *out_ll,
+	double *out_S, int ll_only)
+{
+	const int x = threadIdx.x;
+	if (x > K || (ll_only && x < K))
+		return;
+	double s = 0.0;
+	for (int b = 0; b < blocks; b++)
+		s += part[(size_t)b * (K + 1) + x];
+	if (x == K)
+		*out_ll = s;
+	else
+		out_S[x] = s;
 }

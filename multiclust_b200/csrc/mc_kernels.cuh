@@ -219,7 +219,7 @@ __global__ void k_sum_chunks(const double *Npart, int n_chunks, long long n,
  * pseudo-count `add` on every slot (em_alg.c:972). */
 __global__ void k_update_p(const double *N, int n_chunks, long long chunk_stride,
 	double add, double *p_t, const int *J, const int *off, int K, int L, long long T,
-	int do_proj, double lb)
+	int do_proj, double lb, const double *S, double *eta_t)
 {
 	const long long n = (long long)K * L;
 	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
@@ -242,13 +242,9 @@ __global__ void k_update_p(const double *N, int n_chunks, long long chunk_stride
 		if (do_proj)
 			project_row(row, Jl, lb);
 	}
-}
-
-/* pooled eta (em_alg.c:604-648, 916-962): eta_k = S_k / sum S, projection */
-__global__ void k_update_eta_pooled(const double *S, double *eta_t, int K,
-	int do_proj, double lb)
-{
-	if (blockIdx.x == 0 && threadIdx.x == 0) {
+	/* pooled eta (em_alg.c:604-648, 916-962): eta_k = S_k / sum S, projection;
+	 * one thread of the last block, S == nullptr with per-individual eta */
+	if (S && blockIdx.x == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) {
 		double s = 0.0;
 		for (int k = 0; k < K; k++)
 			s += S[k];
