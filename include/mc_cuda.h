@@ -73,15 +73,20 @@ void *mc_ctx_stream(const mc_ctx *ctx);
 /* Plan options, to be set before mc_alloc_model (they replace environment
  * variables: a stray variable must not switch kernels).
  *   MC_OPT_KERNEL  which genotype-streaming kernel the planner may pick:
- *                  MC_KERNEL_AUTO    dense DMMA kernels (mc_dense.cuh) when no locus
- *                                    has more than two observed alleles and K <= 16,
- *                                    else the two-pass gather kernel (mc_admix3.cuh;
- *                                    admixture, K <= 16, ploidy <= 8), else the
- *                                    one-pass tile kernel
+ *                  MC_KERNEL_AUTO    when no locus has more than two observed
+ *                                    alleles and K <= 16: the dense DMMA kernels
+ *                                    (mc_dense.cuh) for the admixture model, the
+ *                                    digit-sliced integer kernels (mc_digit.cuh)
+ *                                    for the mixture model; else the two-pass
+ *                                    gather kernel (mc_admix3.cuh; K <= 16,
+ *                                    ploidy <= 8), else the one-pass tile kernel
  *                  MC_KERNEL_TILE    the one-pass tile kernel only
  *                  MC_KERNEL_ADMIX3  never the dense kernels
- *                  MC_KERNEL_DENSE   the dense kernels where they apply, else
- *                                    the one-pass tile kernel
+ *                  MC_KERNEL_DENSE   the dense DMMA kernels where they apply (for
+ *                                    the mixture model too), else the one-pass
+ *                                    tile kernel
+ *                  MC_KERNEL_DIGIT   as AUTO on biallelic data, else the one-pass
+ *                                    tile kernel
  *                  The kernels sum in different orders, so results agree to
  *                  rounding (1e-13 relative observed), not bit for bit.
  *   MC_OPT_TIMING  non-zero: the planner prints its phases to stderr
@@ -90,7 +95,8 @@ void *mc_ctx_stream(const mc_ctx *ctx);
  *                  (pair) on: a small fit is launch-bound.  Same kernels, same
  *                  results.  Off while mc_profile_enable is on. */
 enum { MC_OPT_KERNEL = 1, MC_OPT_TIMING = 2, MC_OPT_GRAPH = 3 };
-enum { MC_KERNEL_AUTO = 0, MC_KERNEL_TILE = 1, MC_KERNEL_ADMIX3 = 2, MC_KERNEL_DENSE = 3 };
+enum { MC_KERNEL_AUTO = 0, MC_KERNEL_TILE = 1, MC_KERNEL_ADMIX3 = 2, MC_KERNEL_DENSE = 3,
+	MC_KERNEL_DIGIT = 4 };
 int mc_set_option(mc_ctx *ctx, int option, int value);
 
 /* ---- data: replaces dat->IL / ILM / uniquealleles as the path reads them

@@ -159,7 +159,7 @@ class Context:
                 what, rc, self.lib.mc_last_error(self.h).decode()))
 
     OPT_KERNEL, OPT_TIMING, OPT_GRAPH = 1, 2, 3
-    KERNEL_AUTO, KERNEL_TILE, KERNEL_ADMIX3, KERNEL_DENSE = 0, 1, 2, 3
+    KERNEL_AUTO, KERNEL_TILE, KERNEL_ADMIX3, KERNEL_DENSE, KERNEL_DIGIT = 0, 1, 2, 3, 4
 
     def set_option(self, option, value):
         self._ck(self.lib.mc_set_option(self.h, int(option), int(value)), "mc_set_option")

@@ -23,6 +23,7 @@
 #include "mc_kernels.cuh"
 #include "mc_admix3_build.cuh"
 #include "mc_dense_build.cuh"
+#include "mc_digit_build.cuh"
 
 #define KH_MAX 6
 #define SMEM_LIMIT (227 * 1024)
@@ -97,6 +98,16 @@ struct mc_ctx {
 	unsigned char *d_dn_cnt = nullptr;
 	double *d_dn_pd = nullptr;
 	int *d_dn_lc_first = nullptr;
+	/* digit-sliced integer plan of the mixture model on the same data
+	 * (mc_digit.cuh); used when `use_dg`, the dense plan is its fall-back */
+	bool use_dg = false;
+	bool layout_dg = false;		/* both count layouts are built */
+	DigitArgs dgE, dgM;
+	uint4 *d_dg_cntE = nullptr, *d_dg_cntM = nullptr;
+	uint2 *d_dg_tabE = nullptr, *d_dg_tabM = nullptr;
+	int *d_dg_flag = nullptr;	/* [0] table not representable, [1] chunks of the E pass */
+	double *d_dg_vscale = nullptr;	/* [2 K] posterior column scaling, k_mix_final */
+	int dn_nl = 0, dn_ni = 0;	/* chunk counts of the dense plan */
 	/* kernels whose dynamic shared-memory limit has been raised (set once per
 	 * kernel and size, not on every launch) */
 	std::vector<std::pair<const void *, size_t>> smem_attr;
@@ -267,8 +278,10 @@ static void free_plan(mc_ctx *c)
 	dfree(c->d_llpart); dfree(c->d_xbuf); dfree(c->d_red);
 	dfree(c->d3_lc_first); dfree(c->d3_Gacc);
 	dfree(c->d_dn_pd); dfree(c->d_dn_lc_first);
+	dfree(c->d_dg_tabE); dfree(c->d_dg_tabM); dfree(c->d_dg_flag); dfree(c->d_dg_vscale);
 	c->use3 = false;
 	c->use_dn = false;
+	c->use_dg = false;
 }
 
 /* the admixture kernel's tile codes and entry lists depend on the data only,
@@ -281,6 +294,8 @@ static void free_layout3(mc_ctx *c)
 	c->layout3 = false;
 	dfree(c->d_dn_cnt);
 	c->layout_dn = false;
+	dfree(c->d_dg_cntE); dfree(c->d_dg_cntM);
+	c->layout_dg = false;
 }
 
 static void free_model(mc_ctx *c)
@@ -634,7 +649,8 @@ static int make_plan3(mc_ctx *c)
 	c->use3 = false;
 	if (c->PP > 8 || c->K > 16 || c->T < 1)
 		return MC_OK;
-	if (c->opt_kernel == MC_KERNEL_TILE || c->opt_kernel == MC_KERNEL_DENSE)
+	if (c->opt_kernel == MC_KERNEL_TILE || c->opt_kernel == MC_KERNEL_DENSE
+		|| c->opt_kernel == MC_KERNEL_DIGIT)
 		return MC_OK;
 	const int K = c->K, KP = (K + 1) / 2, KR = 2 * KP, PP = c->PP, L = c->L;
 	const int LT = A3_NC / PP;
@@ -809,6 +825,145 @@ static int launch_admix3(mc_ctx *c, int mode, const double *p, const double *eta
 
 /* ------------------------------------------------ dense DMMA plan (mc_dense) */
 
+/* ---------------------------------------------- digit-sliced mixture plan */
+
+/* Chunks of the contraction dimension for digit_kernel: n_ctarows CTAs per
+ * chunk, `slots` CTAs resident at once, ~t_block_us per CTA and block, and
+ * partial_us for writing and re-reading one chunk's partial sums. */
+static int digit_chunks(long long n_ctarows, int n_blocks, long long slots, int min_chunks,
+	double t_block_us, double partial_us)
+{
+	int best = std::max(1, std::min(min_chunks, n_blocks));
+	double best_cost = 1e300;
+	const int hi = std::max(best, std::min(n_blocks, 256));
+	for (int nc = best; nc <= hi; nc++) {
+		const double waves = (double)((n_ctarows * nc + slots - 1) / slots);
+		const double blocks = (double)((n_blocks + nc - 1) / nc);
+		const double cost = waves * (blocks + 2.0) * t_block_us + nc * partial_us;
+		if (cost < best_cost - 1e-9) {
+			best_cost = cost;
+			best = nc;
+		}
+	}
+	return best;
+}
+
+/* called from make_plan_dense for the mixture model: the same biallelic data,
+ * K <= 16.  Sets c->use_dg and the chunk counts of the two passes. */
+static int make_plan_digit(mc_ctx *c, long long Ipad, int *ncE, int *ncM)
+{
+	c->use_dg = false;
+	*ncE = *ncM = 0;
+	if (c->admixture || c->opt_kernel == MC_KERNEL_DENSE)
+		return MC_OK;
+	const int K = c->K, R = dg_R(K);
+	digit_fn fE = mc_pick_digit(K, DG_MIX_E), fM = mc_pick_digit(K, DG_MIX_M);
+	if (!fE || !fM)
+		return MC_OK;
+	const long long mtE = (c->I + 15) / 16, blE = (c->L + 63) / 64;
+	const long long mtM = (c->L + 7) / 8, blM = (c->I + 127) / 128;
+	if (mtE * blE > 0x7fffffffLL || mtM * blM > 0x7fffffffLL || blM > 0x7fffffffLL)
+		return MC_OK;
+	if (!c->layout_dg) {
+		CK(MC_DEV_MALLOC(&c->d_dg_cntE, sizeof(uint4) * (size_t)mtE * blE * 64));
+		CK(MC_DEV_MALLOC(&c->d_dg_cntM, sizeof(uint4) * (size_t)mtM * blM * 64));
+		k_digit_counts<<<grid_for(c, mtE * blE * 64, 256), 256, 0, c->stream>>>(c->d_nat,
+			c->d_dg_cntE, c->I, c->L, c->P, (int)mtE, (int)blE, DG_MIX_E);
+		LAUNCH_CHECK("k_digit_counts");
+		k_digit_counts<<<grid_for(c, mtM * blM * 64, 256), 256, 0, c->stream>>>(c->d_nat,
+			c->d_dg_cntM, c->I, c->L, c->P, (int)mtM, (int)blM, DG_MIX_M);
+		LAUNCH_CHECK("k_digit_counts");
+		c->layout_dg = true;
+	}
+	CK(MC_DEV_MALLOC(&c->d_dg_tabE, sizeof(uint2) * (size_t)blE * 4 * K * 32));
+	CK(MC_DEV_MALLOC(&c->d_dg_tabM, sizeof(uint2) * (size_t)blM * 4 * K * 32));
+	CK(MC_DEV_MALLOC(&c->d_dg_flag, sizeof(int) * 2));
+	CK(cudaMemsetAsync(c->d_dg_flag, 0, sizeof(int) * 2, c->stream));
+	CK(MC_DEV_MALLOC(&c->d_dg_vscale, sizeof(double) * 2 * K));
+	CK(cudaMemsetAsync(c->d_dg_vscale, 0, sizeof(double) * 2 * K, c->stream));
+
+	/* 32-bit accumulators: count x digit <= 255 P per element of the
+	 * contraction dimension */
+	const long long max_len = 0x7fffffffLL / (255LL * std::max(c->P, 1));
+	int rcs;
+	if ((rcs = raise_smem_limit(c, (const void *)fE, dg_smem_bytes(K)))) return rcs;
+	if ((rcs = raise_smem_limit(c, (const void *)fM, dg_smem_bytes(K)))) return rcs;
+	auto plan = [&](DigitArgs &a, digit_fn fn, long long mt, long long bl, int per_block,
+		double partial_us) {
+		int occ = 1;
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, DG_THREADS,
+			dg_smem_bytes(K));
+		occ = std::max(occ, 1);
+		memset(&a, 0, sizeof a);
+		a.K = K; a.L = c->L;
+		a.n_mtiles = (int)mt; a.n_blocks = (int)bl;
+		const long long wunits = (mt + R - 1) / R;
+		a.n_ctarows = (int)((wunits + DG_WARPS - 1) / DG_WARPS);
+		const int min_chunks = (int)((bl * per_block + max_len - 1) / max_len);
+		/* a CTA and block: 4 warps x 4 steps x R x K IMMAs at 2 clk each on
+		 * an SM shared by `occ` CTAs, or 16 R KB of counts at the SM's share
+		 * of HBM, whichever is longer */
+		const double t_mma = DG_WARPS * 4.0 * R * K * 2.0 * occ / 1900.0;
+		const double t_hbm = DG_WARPS * R * 1024.0 * occ / 43000.0;
+		a.n_chunks = digit_chunks(a.n_ctarows, (int)bl, (long long)c->num_sms * occ,
+			min_chunks, std::max(t_mma, t_hbm), partial_us);
+		a.I = c->I; a.Ipad = Ipad; a.T = c->T;
+		a.off = c->d_off; a.J = c->d_J;
+	};
+	plan(c->dgE, fE, mtE, blE, 64, (double)c->I * K * 16.0 / 5e6);
+	plan(c->dgM, fM, mtM, blM, 128, (double)K * (double)c->T * 16.0 / 5e6);
+	c->dgE.cnt = c->d_dg_cntE; c->dgE.tab = c->d_dg_tabE;
+	c->dgM.cnt = c->d_dg_cntM; c->dgM.tab = c->d_dg_tabM;
+	if ((long long)c->dgE.n_chunks * c->dgE.n_ctarows > 0x7fffffffLL
+		|| (long long)c->dgM.n_chunks * c->dgM.n_ctarows > 0x7fffffffLL)
+		return MC_OK;
+	*ncE = c->dgE.n_chunks;
+	*ncM = c->dgM.n_chunks;
+	c->use_dg = true;
+	return MC_OK;
+}
+
+/* One pass of the digit-sliced kernels.  DG_MIX_E: src = p [K][T], take_log as
+ * in k_digit_table (2 = the log-likelihood pass, where log 0 makes the pass
+ * fall back: the caller launches the FP64 kernels behind it, gated on the
+ * flag); DG_MIX_M: src = posteriors [I][K]. */
+static int launch_digit(mc_ctx *c, int mode, const double *src, int take_log)
+{
+	digit_fn fn = mc_pick_digit(c->K, mode);
+	if (!fn)
+		return fail(c, MC_ERR_UNSUPPORTED, "no digit kernel for K=%d", c->K);
+	DigitArgs a = mode == DG_MIX_E ? c->dgE : c->dgM;
+	const long long n = (long long)a.n_blocks * 4 * c->K;
+	k_digit_table<<<grid_for(c, n * 32, 256), 256, 0, c->stream>>>(src, c->d_dg_vscale,
+		const_cast<uint2 *>(a.tab), c->d_dg_flag, mode == DG_MIX_E ? take_log : 0, c->K,
+		c->I, c->L, c->T, c->d_off, c->d_J, a.n_blocks);
+	LAUNCH_CHECK("k_digit_table");
+	a.out = mode == DG_MIX_E ? c->d_Apart : c->d_Npart;
+	a.unscale = c->d_dg_vscale + c->K;
+	if (mode == DG_MIX_E && take_log == 2) {
+		a.skip_if = c->d_dg_flag;
+		a.n_chunks_dev = c->d_dg_flag + 1;
+	}
+	{
+		const int rca = raise_smem_limit(c, (const void *)fn, dg_smem_bytes(c->K));
+		if (rca)
+			return rca;
+	}
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	if (c->profile) {
+		CK(cudaEventCreate(&e0));
+		CK(cudaEventCreate(&e1));
+		CK(cudaEventRecord(e0, c->stream));
+	}
+	fn<<<(unsigned)(a.n_chunks * a.n_ctarows), DG_THREADS, dg_smem_bytes(c->K), c->stream>>>(a);
+	LAUNCH_CHECK("digit_kernel");
+	if (c->profile) {
+		CK(cudaEventRecord(e1, c->stream));
+		c->prof_events.push_back({ e0, e1 });
+	}
+	return MC_OK;
+}
+
 /* returns MC_OK with c->use_dn set when the kernels of mc_dense.cuh apply:
  * no allele code above 1 anywhere (every locus has at most two observed
  * alleles; a third slot can only be the phantom slot of read_file.c:527-530,
@@ -816,7 +971,8 @@ static int launch_admix3(mc_ctx *c, int mode, const double *p, const double *eta
 static int make_plan_dense(mc_ctx *c)
 {
 	c->use_dn = false;
-	if (c->opt_kernel != MC_KERNEL_AUTO && c->opt_kernel != MC_KERNEL_DENSE)
+	if (c->opt_kernel != MC_KERNEL_AUTO && c->opt_kernel != MC_KERNEL_DENSE
+		&& c->opt_kernel != MC_KERNEL_DIGIT)
 		return MC_OK;
 	if (c->K > 16 || c->P > 15 || c->T < 1)
 		return MC_OK;
@@ -885,7 +1041,13 @@ static int make_plan_dense(mc_ctx *c)
 	CK(MC_DEV_MALLOC(&c->d_dn_pd, sizeof(double) * (size_t)n_ltiles * DN_TL * dn_pl(NB)));
 	a.lc_first = c->d_dn_lc_first; a.off = c->d_off; a.J = c->d_J;
 	a.cnt = c->d_dn_cnt; a.pd = c->d_dn_pd;
-	if ((rc = alloc_outputs(c, best_nl, best_ni, a.n_units, a.Ipad))) return rc;
+	int ncE = 0, ncM = 0;
+	if ((rc = make_plan_digit(c, a.Ipad, &ncE, &ncM))) return rc;
+	if ((rc = alloc_outputs(c, std::max(best_nl, ncE), std::max(best_ni, ncM), a.n_units,
+		a.Ipad))) return rc;
+	c->dn_nl = best_nl; c->dn_ni = best_ni;
+	c->act_tiles = c->use_dg ? ncE : best_nl;
+	c->act_chunks = c->use_dg ? ncM : best_ni;
 	a.Apart = c->d_Apart; a.Npart = c->d_Npart; a.llpart = c->d_llpart;
 	CK(cudaStreamSynchronize(c->stream));
 	c->use_dn = true;
@@ -895,18 +1057,22 @@ static int make_plan_dense(mc_ctx *c)
 /* `ptab`: the [K][T] table the dense p fragments are built from (p; its log,
  * take_log as in k_dense_p, for the mixture E pass; nullptr for the M pass) */
 static int launch_dense(mc_ctx *c, int mode, const double *ptab, const double *p,
-	const double *eta, long long eta_stride, int take_log = 0)
+	const double *eta, long long eta_stride, int take_log = 0, bool fallback = false)
 {
 	dense_fn fn = mc_pick_dense(c->dn_NB, c->dn_pbits, mode);
 	if (!fn)
 		return fail(c, MC_ERR_UNSUPPORTED, "no dense kernel for K=%d P=%d", c->K, c->P);
 	DenseArgs a = c->dn;
 	a.p = p; a.eta = eta; a.eta_stride = eta_stride;
+	if (fallback) {	/* behind the digit kernels: runs only when they declined */
+		a.run_if = c->d_dg_flag;
+		a.n_chunks_dev = c->d_dg_flag + 1;
+	}
 	if (ptab) {
 		const int K8 = 8 * c->dn_NB, npad = a.n_ltiles * DN_TL;
 		k_dense_p<<<grid_for(c, (long long)npad * K8 * 2, 256), 256, 0, c->stream>>>(ptab,
 			c->d_dn_pd, c->d_off, c->d_J, c->K, c->L, c->T, npad, dn_pl(c->dn_NB), K8,
-			take_log);
+			take_log, a.run_if);
 		LAUNCH_CHECK("k_dense_p");
 	}
 	const size_t smem = dn_smem_bytes(c->dn_NB, mode, a.max_chunk_tiles);
@@ -1077,7 +1243,7 @@ extern "C" int mc_alloc_model(mc_ctx *c, int32_t K, int admixture,
 	CK(cudaMemsetAsync(c->d_post, 0, sizeof(double) * (size_t)c->I * K, c->stream));
 	CK(MC_DEV_MALLOC(&c->d_IK, sizeof(int) * (size_t)c->I));
 	if (!c->admixture) {
-		c->lli_n = std::max<long long>(c->I, (long long)c->num_sms * 4 * (K + 1));
+		c->lli_n = (long long)c->num_sms * 4 * (2 * K + 1);
 		CK(MC_DEV_MALLOC(&c->d_lli, sizeof(double) * (size_t)c->lli_n));
 		CK(MC_DEV_MALLOC(&c->d_logp, npb));
 	}
@@ -1224,16 +1390,23 @@ static int join_aux(mc_ctx *c)
  * log likelihood and the pooled sums S_k = sum_i v_ik into the exchange buffer */
 static int mix_tail(mc_ctx *c, const double *eta, double *vik, int ll_only)
 {
+	/* digit-sliced plan: the log-likelihood pass may have fallen back to the
+	 * dense kernels, which cut the loci differently -- the kernel that ran left
+	 * its chunk count on the device.  A table that cannot be represented in
+	 * the E-step (a NaN in p) poisons the log likelihood instead. */
+	const int *n_chunks_dev = c->use_dg && ll_only ? c->d_dg_flag + 1 : nullptr;
+	int *flag = c->use_dg ? c->d_dg_flag : nullptr;
 	const long long blocks = (c->I + MT_ROWS - 1) / MT_ROWS;
 	const int grid = (int)std::min<long long>(blocks, (long long)c->num_sms * 4);
-	/* d_lli doubles as the per-block partial sums: grid * (K + 1) <= I */
+	/* per-block partial sums: grid * (2 K + 1) doubles */
 	double *part = c->d_lli;
-	if ((long long)grid * (c->K + 1) > c->lli_n)
+	if ((long long)grid * (2 * c->K + 1) > c->lli_n)
 		return fail(c, MC_ERR_STATE, "mix_tail: partial-sum buffer too small");
 	k_mix_tail<<<grid, 256, sizeof(double) * (MT_ROWS * c->K + MT_ROWS), c->stream>>>(c->d_Apart,
-		c->act_tiles, c->act_Ipad, c->I, c->K, eta, vik, part, ll_only);
+		c->act_tiles, n_chunks_dev, c->act_Ipad, c->I, c->K, eta, vik, part, ll_only);
 	LAUNCH_CHECK("k_mix_tail");
-	k_mix_final<<<1, 256, 0, c->stream>>>(part, grid, c->K, xb_ll(c), xb_S(c), ll_only);
+	k_mix_final<<<1, 256, 0, c->stream>>>(part, grid, c->K, xb_ll(c), xb_S(c), ll_only, flag,
+		c->use_dg && !ll_only ? c->d_dg_vscale : nullptr);
 	LAUNCH_CHECK("k_mix_final");
 	return MC_OK;
 }
@@ -1292,11 +1465,13 @@ extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 				c->d_logp, c->np, 1);
 			LAUNCH_CHECK("k_log_table");
 		}
-		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_E, c->d_p[from], nullptr, nullptr, 0, 1)
+		if ((rc = c->use_dg ? launch_digit(c, DG_MIX_E, c->d_p[from], 1)
+			: c->use_dn ? launch_dense(c, DN_MIX_E, c->d_p[from], nullptr, nullptr, 0, 1)
 			: c->use3 ? launch_admix3(c, A3_MIX_E, c->d_logp, nullptr, 0)
 			: launch_tile(c, MODE_MIX_E, c->d_logp, nullptr, 0))) return rc;
 		if ((rc = mix_tail(c, c->d_eta[from], c->d_post, 0))) return rc;
-		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_M, nullptr, nullptr, c->d_post, K)
+		if ((rc = c->use_dg ? launch_digit(c, DG_MIX_M, c->d_post, 0)
+			: c->use_dn ? launch_dense(c, DN_MIX_M, nullptr, nullptr, c->d_post, K)
 			: c->use3 ? launch_admix3(c, A3_MIX_M, nullptr, c->d_post, K)
 			: launch_tile(c, MODE_MIX_M, nullptr, c->d_post, K))) return rc;
 		if (!c->fused_step) {
@@ -1683,7 +1858,11 @@ static int loglik_launch(mc_ctx *c, int slot)
 				c->d_logp, c->np, 0);
 			LAUNCH_CHECK("k_log_table");
 		}
-		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_E, c->d_p[slot], nullptr, nullptr, 0, 2)
+		if (c->use_dg) {
+			if ((rc = launch_digit(c, DG_MIX_E, c->d_p[slot], 2))) return rc;
+			if ((rc = launch_dense(c, DN_MIX_E, c->d_p[slot], nullptr, nullptr, 0, 2,
+				true))) return rc;
+		} else if ((rc = c->use_dn ? launch_dense(c, DN_MIX_E, c->d_p[slot], nullptr, nullptr, 0, 2)
 			: c->use3 ? launch_admix3(c, A3_MIX_E, c->d_logp, nullptr, 0)
 			: launch_tile(c, MODE_MIX_E, c->d_logp, nullptr, 0))) return rc;
 		/* the posterior of the last E-step must survive: only the per-
@@ -1934,6 +2113,16 @@ extern "C" int mc_get_plan(const mc_ctx *c, mc_plan_info *o)
 		o->smem_bytes = (int64_t)dn_smem_bytes(c->dn_NB,
 			c->admixture ? DN_ADMIX_EM : DN_MIX_M, c->dn.max_chunk_tiles);
 	}
+	if (c->use_dg) {	/* digit-sliced mixture kernels: chunks of the two passes */
+		o->two_pass = 4;
+		o->k_per_lane = c->K;
+		o->loci_per_warp = 64; o->warps = DG_WARPS;
+		o->n_tiles = c->dgE.n_chunks; o->n_chunks = c->dgM.n_chunks;
+		o->n_units = c->dgE.n_chunks * c->dgE.n_ctarows;
+		o->grid = o->n_units; o->block = DG_THREADS;
+		o->indiv_per_block = 16 * dg_R(c->K) * DG_WARPS;
+		o->smem_bytes = (int64_t)dg_smem_bytes(c->K);
+	}
 	const int64_t g = c->I * (int64_t)c->L * c->P;
 	o->algorithmic_bytes_em = g + 16 * c->I * (int64_t)c->K + 16 * (int64_t)c->K * c->T;
 	o->algorithmic_bytes_ll = g + 8 * c->I * (int64_t)c->K + 8 * (int64_t)c->K * c->T;
@@ -1978,7 +2167,7 @@ extern "C" int mc_set_option(mc_ctx *c, int option, int value)
 		return MC_ERR_ARG;
 	switch (option) {
 	case MC_OPT_KERNEL:
-		if (value < MC_KERNEL_AUTO || value > MC_KERNEL_DENSE)
+		if (value < MC_KERNEL_AUTO || value > MC_KERNEL_DIGIT)
 			return fail(c, MC_ERR_ARG, "mc_set_option: kernel %d out of range", value);
 		c->opt_kernel = value;
 		return MC_OK;

@@ -72,6 +72,10 @@ struct DenseArgs {
 	double *Apart;			/* [n_lchunks][Ipad][K] */
 	double *Npart;			/* [n_ichunks][K * T] */
 	double *llpart;			/* [n_units] */
+	/* fall-back of the digit-sliced mixture pass (mc_digit.cuh): run only when
+	 * *run_if is set, and leave the chunk count for k_mix_tail */
+	const int *run_if;
+	int *n_chunks_dev;
 };
 
 /* ---------------------------------------------------------------------- */
@@ -160,6 +164,12 @@ __global__ void __launch_bounds__(DN_THREADS, DN_CTAS_PER_SM) dense_kernel(const
 	extern __shared__ __align__(128) double dsm[];
 	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
 	const int r = lane >> 2, q = lane & 3;
+	if (MODE == DN_MIX_E) {
+		if (a.run_if && !*a.run_if)
+			return;
+		if (a.n_chunks_dev && blockIdx.x == 0 && t == 0)
+			*a.n_chunks_dev = a.n_lchunks;
+	}
 
 	double *B_s = dsm;								/* [chunk tiles][NB][256] */
 	double *scr = B_s + (HAS_G ? (size_t)a.max_chunk_tiles * NB * 256 : 0);	/* [8][NB][4][32][2] */

@@ -60,8 +60,11 @@ __global__ void k_dense_counts(const unsigned char *nat, unsigned char *cnt,
  * minus infinity (log 0, only without the projection) becomes -DBL_MAX so that
  * a zero count still contributes zero */
 __global__ void k_dense_p(const double *p, double *pd, const int *off, const int *J,
-	int K, int L, long long T, int n_loci_pad, int PL, int K8, int take_log)
+	int K, int L, long long T, int n_loci_pad, int PL, int K8, int take_log,
+	const int *run_if)
 {
+	if (run_if && !*run_if)
+		return;
 	const long long n = (long long)n_loci_pad * K8 * 2;
 	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
 		x += (long long)gridDim.x * blockDim.x) {
@@ -89,15 +92,19 @@ __global__ void k_dense_p(const double *p, double *pd, const int *off, const int
 #define MT_ROWS 32
 /* ... and the sums the step needs over individuals, fused in: every block adds
  * up the log likelihood and (E-step) the K posterior columns of its rows in row
- * order and leaves them in part[block][K + 1] = {S_0..S_{K-1}, ll}; k_mix_final
- * adds the blocks in block order.  Fixed order, no atomics. */
-__global__ void k_mix_tail(const double *Apart, int n_chunks, long long Ipad, long long I,
-	int K, const double *eta, double *vik, double *part, int ll_only)
+ * order and leaves them in part[block][2 K + 1] = {S_0..S_{K-1}, ll, max_i v_i0..};
+ * k_mix_final adds the blocks in block order.  Fixed order, no atomics. */
+__global__ void k_mix_tail(const double *Apart, int n_chunks, const int *n_chunks_dev,
+	long long Ipad, long long I, int K, const double *eta, double *vik, double *part,
+	int ll_only)
 {
+	if (n_chunks_dev)	/* left by whichever kernel ran (mc_digit.cuh) */
+		n_chunks = *n_chunks_dev;
 	extern __shared__ double mt_rows[];	/* [MT_ROWS][K] then [MT_ROWS] */
 	double *mt_ll = mt_rows + MT_ROWS * K;
 	const int n = MT_ROWS * K;
 	double acc_col = 0.0;			/* thread k < K: S_k; thread K: ll */
+	double max_col = 0.0;			/* thread k < K: max_i v_ik */
 	for (long long i0 = (long long)blockIdx.x * MT_ROWS; i0 < I; i0 += (long long)gridDim.x * MT_ROWS) {
 		for (int x = threadIdx.x; x < n; x += blockDim.x) {
 			const long long i = i0 + x / K;
@@ -145,8 +152,11 @@ __global__ void k_mix_tail(const double *Apart, int n_chunks, long long Ipad, lo
 		__syncthreads();
 		const int rows = (int)(I - i0 < MT_ROWS ? I - i0 : MT_ROWS);
 		if ((int)threadIdx.x < K && !ll_only) {
-			for (int r = 0; r < rows; r++)
-				acc_col += mt_rows[r * K + threadIdx.x];
+			for (int r = 0; r < rows; r++) {
+				const double vv = mt_rows[r * K + threadIdx.x];
+				acc_col += vv;
+				max_col = fmax(max_col, vv);
+			}
 		} else if ((int)threadIdx.x == K) {
 			for (int r = 0; r < rows; r++)
 				acc_col += mt_ll[r];
@@ -154,21 +164,56 @@ __global__ void k_mix_tail(const double *Apart, int n_chunks, long long Ipad, lo
 		__syncthreads();
 	}
 	if ((int)threadIdx.x <= K)
-		part[(size_t)blockIdx.x * (K + 1) + threadIdx.x] = acc_col;
+		part[(size_t)blockIdx.x * (2 * K + 1) + threadIdx.x] = acc_col;
+	if ((int)threadIdx.x < K)
+		part[(size_t)blockIdx.x * (2 * K + 1) + K + 1 + threadIdx.x] = max_col;
 }
 
-/* out_ll = sum_b part[b][K]; out_S[k] = sum_b part[b][k] (E-step only) */
+/* out_ll = sum_b part[b][K]; out_S[k] = sum_b part[b][k] (E-step only).  vscale
+ * (nullable, E-step only): the power-of-two scaling of the posterior column k
+ * for the digit-sliced M pass, {2^(64 - e_k)} then {2^(e_k - 64)} with
+ * max_i v_ik < 2^e_k (mc_digit.cuh). */
 __global__ void k_mix_final(const double *part, int blocks, int K, double *out_ll,
-	double *out_S, int ll_only)
+	double *out_S, int ll_only, int *flag, double *vscale)
 {
-	const int x = threadIdx.x;
-	if (x > K || (ll_only && x < K))
-		return;
-	double s = 0.0;
-	for (int b = 0; b < blocks; b++)
-		s += part[(size_t)b * (K + 1) + x];
-	if (x == K)
-		*out_ll = s;
-	else
-		out_S[x] = s;
+	/* one warp per column: lanes stride over the blocks, then a fixed tree */
+	const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+	for (int x = threadIdx.x >> 5; x <= K; x += nw) {
+		if (ll_only && x < K)
+			continue;
+		double s = 0.0, m = 0.0;
+		for (int b = lane; b < blocks; b += 32) {
+			s += part[(size_t)b * (2 * K + 1) + x];
+			if (x < K && vscale)
+				m = fmax(m, part[(size_t)b * (2 * K + 1) + K + 1 + x]);
+		}
+		for (int o = 16; o >= 1; o >>= 1) {
+			s += shfl_xor_f64(s, o);
+			m = fmax(m, shfl_xor_f64(m, o));
+		}
+		if (lane)
+			continue;
+		if (x < K && vscale) {
+			int e = 0;
+			if (m > 0.0 && m <= 1.0)
+				frexp(m, &e);		/* m = f 2^e, 0.5 <= f < 1 */
+			e = e < -900 ? -900 : e;
+			vscale[x] = scalbn(1.0, 64 - e);
+			vscale[K + x] = scalbn(1.0, e - 64);
+		}
+		if (x == K) {
+			/* the digit table's flag ends with the pass.  The log-likelihood
+			 * pass fell back to the FP64 kernels on it; the E-step has no
+			 * fall-back -- only a NaN or a negative p raises it there -- and
+			 * reports NaN */
+			if (flag) {
+				if (flag[0] && !ll_only)
+					s = __longlong_as_double(0x7ff8000000000000LL);
+				flag[0] = 0;
+			}
+			*out_ll = s;
+		} else {
+			out_S[x] = s;
+		}
+	}
 }

@@ -274,6 +274,105 @@ def test_dense_kernels(orc, tmp_path, shape, admixture):
         c.close()
 
 
+# ---- the digit-sliced integer kernels of the mixture model (mc_digit.cuh) ----
+
+DIGIT_SHAPES = DENSE_SHAPES + [
+    (530, 300, 5, 2, 300, 2),      # several blocks of loci (64) and of individuals (128)
+    (129, 65, 1, 2, 0, 2),         # K = 1, one element past a block in both directions
+    (200, 150, 16, 2, 200, 2),     # K = 16 (one m-tile per warp)
+    (90, 130, 7, 2, 100, 15),      # the largest ploidy of the packed counts
+    (150, 100, 10, 2, 0, 2),       # BASELINE K
+]
+
+
+@pytest.mark.parametrize("shape", DIGIT_SHAPES)
+def test_digit_kernels(orc, tmp_path, shape):
+    """mixture model on biallelic data: the planner picks the digit-sliced kernels; E-step,
+    M-step and log likelihood against the oracle, the posterior survives mc_loglik"""
+    from multiclust_b200 import Context
+    c = Context(0)
+    try:
+        d, fit, eta, p = setup_pair(orc, c, tmp_path, shape, admixture=0)
+        assert c.plan()["two_pass"] == 4
+        ll_o = fit.log_likelihood(0)
+        assert abs(c.loglik(0) - ll_o) <= 1e-12 * abs(ll_o)
+        check_step(orc, c, fit, 0, 1)
+        check_step(orc, c, fit, 1, 1)
+        check_step(orc, c, fit, 1, 2)
+        post = c.posterior()
+        assert abs(c.loglik(2) - fit.log_likelihood(2)) <= 1e-12 * abs(ll_o)
+        assert np.array_equal(post, c.posterior())
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("K", [2, 3, 4, 6, 9, 11, 12, 13, 14, 15])
+def test_digit_kernels_every_k(orc, tmp_path, K):
+    from multiclust_b200 import Context
+    c = Context(0)
+    try:
+        d, fit, eta, p = setup_pair(orc, c, tmp_path, (70, 90, K, 2, 300, 2), admixture=0)
+        assert c.plan()["two_pass"] == 4
+        ll_o = fit.log_likelihood(0)
+        assert abs(c.loglik(0) - ll_o) <= 1e-12 * abs(ll_o)
+        check_step(orc, c, fit, 0, 1)
+    finally:
+        c.close()
+
+
+def test_digit_kernels_agree_with_dmma(orc, tmp_path):
+    """the integer path against the FP64 tensor path on the same start: the sums are exact
+    on one side and rounded on the other, so they agree to a few ulp of the sums"""
+    from multiclust_b200 import Context
+    out = []
+    for kernel in (3, 4):
+        c = Context(0)
+        try:
+            c.set_option(c.OPT_KERNEL, kernel)
+            d, fit, eta, p = setup_pair(orc, c, tmp_path, DIGIT_SHAPES[5], admixture=0)
+            assert c.plan()["two_pass"] == kernel
+            lls = [c.em_step(0, 0) for _ in range(5)]
+            out.append((lls, c.get_params(0), c.posterior(), c.loglik(0)))
+        finally:
+            c.close()
+    (l3, (e3, p3), v3, f3), (l4, (e4, p4), v4, f4) = out
+    assert np.max(np.abs(np.array(l3) - np.array(l4)) / np.abs(l3)) < 1e-13
+    assert abs(f3 - f4) <= 1e-13 * abs(f3)
+    assert np.max(np.abs(e3 - e4)) < 1e-12 and np.max(np.abs(p3 - p4)) < 1e-12
+    assert np.max(np.abs(v3 - v4)) < 1e-10
+
+
+def test_digit_log_zero_falls_back(orc, tmp_path):
+    """log 0 has no fixed-point form: without the projection p reaches 0, the log-likelihood
+    pass falls back to the FP64 kernels on the device (no host round trip) and the next pass
+    is back on the integer kernels"""
+    from multiclust_b200 import Context
+    c = Context(0)
+    try:
+        shape = (300, 200, 4, 2, 300, 2)
+        d, fit, eta, p = setup_pair(orc, c, tmp_path, shape, admixture=0, proj=0)
+        assert c.plan()["two_pass"] == 4
+        J = d["J"]
+        off = np.concatenate([[0], np.cumsum(J)])
+        T = int(J.sum())
+        p = p.reshape(4, T).copy()
+        for l in (0, 7, 150):               # class 2 cannot carry allele 0 of these loci
+            if J[l] >= 2:
+                p[2, off[l]] = 0.0
+                p[2, off[l] + 1] = 1.0 if J[l] == 2 else p[2, off[l] + 1]
+        p = p.ravel()
+        fit.set_params(0, eta, p)
+        c.set_params(0, eta, p)
+        ll_o = fit.log_likelihood(0)
+        assert np.isfinite(ll_o)
+        assert abs(c.loglik(0) - ll_o) <= 1e-12 * abs(ll_o)
+        check_step(orc, c, fit, 0, 1)       # E-step: p == 0 contributes nothing
+        ll_1 = fit.log_likelihood(1)
+        assert abs(c.loglik(1) - ll_1) <= 1e-12 * abs(ll_1)
+    finally:
+        c.close()
+
+
 def test_dense_pooled_eta(orc, tmp_path):
     from multiclust_b200 import Context
     c = Context(0)
@@ -437,7 +536,8 @@ def test_degenerate_loci(orc, admixture, kernel):
         c.set_option(c.OPT_KERNEL, kernel)
         c.set_data(J, codes)
         c.alloc_model(K, admixture=admixture, q=0, eta_lb=lb, p_lb=lb)
-        assert c.plan()["two_pass"] == {0: 3, 1: 0, 2: 2}[kernel]
+        # kernel 0: dense DMMA (admixture) / digit-sliced integer kernels (mixture)
+        assert c.plan()["two_pass"] == {0: 3 if admixture else 4, 1: 0, 2: 2}[kernel]
         eta, p = random_params(np.random.default_rng(5), I, K, J, bool(admixture))
         fit.set_params(0, eta, p)
         c.set_params(0, eta, p)

@@ -150,7 +150,7 @@ def test_config2_full_size_properties():
         ctx.set_data_synth(I2, L2, SynthParams(seed=20261018, K=K2, jmax=2, miss_bp=0, ploidy=2))
         lb = min(1e-8, 0.5 / I2 / 2)
         ctx.alloc_model(K2, admixture=0, q=0, eta_lb=lb, p_lb=lb)
-        assert ctx.plan()["two_pass"] == 3
+        assert ctx.plan()["two_pass"] == 4      # digit-sliced integer kernels
         eta0, p0, J, seg = _start(ctx, K2, False, 5)
         runs = []
         for rep in range(2):

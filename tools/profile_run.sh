@@ -2,7 +2,7 @@
 # One evidence run on the GPU box (under gpurun): the default bench line, the ncu launch list of
 # the short bench command, and full ncu captures of the dominant kernels, reduced ON THE BOX to the
 # raw-metric and per-instruction CSV pages (the .ncu-rep files are too large to travel back).
-#   bash tools/profile_run.sh [bench|admix3|dense|mix ...]
+#   bash tools/profile_run.sh [bench|launches|admix3|dense|mix|digit ...]
 set -u
 O=gpurun_out
 mkdir -p $O
@@ -37,6 +37,12 @@ mix)
     ncu --set full --clock-control none --import-source on -k regex:dense_kernel -s 6 -c 2 \
         -o $O/prof_r2m $CMD > $O/ncu_m.log 2>&1
     pages prof_r2m ;;
+digit)
+    CMD="python tools/dense_time.py c2 --steps 2"
+    $CMD > $O/plain_g.log 2>&1 &&
+    ncu --set full --clock-control none --import-source on -k regex:digit_kernel -s 6 -c 2 \
+        -o $O/prof_r2g $CMD > $O/ncu_g.log 2>&1
+    pages prof_r2g ;;
 esac
 done
 ls -la $O | head -30
