@@ -17,8 +17,9 @@ the reference's stop() needs it (em_alg.c:195-207).
   e2e        iterations/s of a whole fit driven through the C ABI from HOST
              buffers (a fresh context; the resident-data context is closed
              first): mc_set_data from pinned host memory (H2D of the genotype
-             codes) + mc_alloc_model + mc_set_params + `steps` x mc_em_step
-             (8-byte D2H each) + mc_get_params + mc_get_posterior
+             codes) + mc_alloc_model + mc_set_params + `--e2e-iters` (200, the
+             configuration's fixed -C 200) x mc_em_step (8-byte D2H each) +
+             mc_get_params + mc_get_posterior
   roofline   algorithmic bytes (I*L*P + 16*I*K + 16*K*T) of the
              genotype-streaming kernel / its CUDA-event duration, against the
              measured HBM copy bandwidth in MEASURED_PEAKS.json.  Because the
@@ -34,9 +35,11 @@ the reference's stop() needs it (em_alg.c:195-207).
              workload, extrapolated linearly in I (cost is linear in I,
              em_alg.c:325,650,717; the reference cannot allocate its
              I*K*T-double scratch at full size, SURVEY.md finding 5)
-  parity_check  OUTSIDE the timed region, for every N: four golden cases
+  parity_check  OUTSIDE the timed region, for every N: six golden cases
              generated from the unmodified reference (tests/golden: admix_k10,
-             admix_s5 = QN q=2, admix_tetra, mix_s1 = SQUAREM) are re-fitted with
+             admix_s5 = QN q=2, admix_tetra, mix_s1 = SQUAREM on the gather
+             kernels; admix_biallelic on the DMMA kernels, mix_biallelic_k5 on
+             the digit-sliced integer kernels) are re-fitted with
              their individuals sharded over the N ranks through the same
              sharded step / acceleration calls, and the log-likelihood
              trajectory (<= 1e-9 relative) and final parameters (<= 1e-7
@@ -93,6 +96,8 @@ def parse_args():
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-iters", type=int, default=200,
+                    help="iterations of the end-to-end fit (BASELINE configs[2]: fixed -C 200)")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the other_configs block")
     return ap.parse_args()
@@ -383,7 +388,8 @@ def start_params(env, ctx, a, lb, seed):
 
 # ------------------------------------------------------------ parity check
 
-PARITY_CASES = ["admix_k10", "admix_s5", "admix_tetra", "mix_s1"]
+PARITY_CASES = ["admix_k10", "admix_s5", "admix_tetra", "mix_s1", "admix_biallelic",
+                "mix_biallelic_k5"]
 
 
 def parity_check(env):
@@ -452,7 +458,8 @@ def other_configs(env, a):
     res = {}
 
     def fit_ms(ctx, n, fn):
-        fn()
+        for _ in range(3):      # the launch graph is captured on the second call
+            fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -591,7 +598,8 @@ def main():
         ctx2.set_params(0, eta_h, p_h)
         ctx2.set_stream(env.stream.cuda_stream)
         t2 = time.perf_counter()
-        for _ in range(a.steps):
+        n_it = max(a.e2e_iters, 1)
+        for _ in range(n_it):
             sharded_em_step(ctx2, env.dist, world, 0, 0, scratch)
         t3 = time.perf_counter()
         ctx2.lib.mc_get_params(ctx2.h, 0, ctypes.c_void_p(eta_o.ctypes.data),
@@ -604,13 +612,14 @@ def main():
                   "em_steps_s": t3 - t2, "get_results_s": t4 - t3}
         ctx2.close()
         h2d = codes.nbytes + J.nbytes + eta0.nbytes + p0.nbytes
-        d2h = 8 * a.steps + eta0.nbytes + p0.nbytes + post_o.nbytes
-        e2e = {"value": world * a.steps / sec, "unit": UNIT,
-               "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps,
+        d2h = 8 * n_it + eta0.nbytes + p0.nbytes + post_o.nbytes
+        e2e = {"value": world * n_it / sec, "unit": UNIT, "iterations": n_it,
+               "h2d_bytes_per_step": h2d // n_it, "d2h_bytes_per_step": d2h // n_it,
                "phases_rank0": phases,
-               "what": "whole fit of %d iterations from pinned host buffers: mc_set_data + "
-                       "mc_alloc_model + mc_set_params + mc_em_step x%d + mc_get_params + "
-                       "mc_get_posterior; bytes amortised per iteration" % (a.steps, a.steps)}
+               "what": "whole fit of %d iterations (the configuration's fixed -C %d) from pinned "
+                       "host buffers: mc_set_data + mc_alloc_model + mc_set_params + mc_em_step "
+                       "x%d + mc_get_params + mc_get_posterior; bytes amortised per iteration"
+                       % (n_it, n_it, n_it)}
         del codes, pinned, codes_p
     else:
         ctx.close()

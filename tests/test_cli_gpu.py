@@ -133,7 +133,8 @@ def _n_gpus():
 
 
 @pytest.mark.parametrize("name", ["admix_em", "admix_s3", "admix_s5", "admix_c_em", "mix_em",
-                                  "mix_s1", "admix_k10", "admix_tetra"])
+                                  "mix_s1", "admix_k10", "admix_tetra", "admix_biallelic",
+                                  "mix_biallelic_k5"])
 def test_cli_two_gpus_matches_reference(tmp_path, name):
     """--gpus 2: individuals sharded over two devices, NCCL exchange of the
     sufficient statistics (libmc_comm.so); same parity bars as one device"""

@@ -1,6 +1,6 @@
 """Time the dense (biallelic) configurations: BASELINE config 2 (mixture, I=10k, L=5k, K=5,
 diploid) and one GPU's share of config 5 (admixture, I=125k, L=50k, K=8, tetraploid).
-  python tools/dense_time.py [c2] [c5] [--kernel N]"""
+  python tools/dense_time.py [c2] [c5] [c5mix] [--kernel N] [--steps N]"""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -70,7 +70,10 @@ if __name__ == "__main__":
     if "--kernel" in args:
         kernel = int(args[args.index("--kernel") + 1])
     steps = int(args[args.index("--steps") + 1]) if "--steps" in args else 0
-    if "c2" in args or not [x for x in args if x in ("c2", "c5")]:
+    named = [x for x in args if x in ("c2", "c5", "c5mix")]
+    if "c2" in args or not named:
         run("C2 mixture", 10000, 5000, 5, 2, 0, kernel, steps=steps or 20)
-    if "c5" in args or not [x for x in args if x in ("c2", "c5")]:
+    if "c5" in args or not named:
         run("C5 share admixture", 125000, 50000, 8, 4, 1, kernel, steps=steps or 5)
+    if "c5mix" in args:     # the mixture kernels at a size that fills the machine
+        run("C5-sized mixture", 125000, 50000, 8, 4, 0, kernel, steps=steps or 5)
