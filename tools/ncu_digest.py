@@ -17,6 +17,8 @@ WANT = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "dram__bytes_read.su
         "TPC.TriageCompute.sm__pipe_fp64_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
         "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
         "SM_C.TriageCompute.smsp__pipe_tensor_subpipe_dmma_cycles_active.avg",
+        "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__block_size", "launch__grid_size", "launch__shared_mem_per_block_dynamic",

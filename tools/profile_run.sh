@@ -2,7 +2,7 @@
 # One evidence run on the GPU box (under gpurun): the default bench line, the ncu launch list of
 # the short bench command, and full ncu captures of the dominant kernels, reduced ON THE BOX to the
 # raw-metric and per-instruction CSV pages (the .ncu-rep files are too large to travel back).
-#   bash tools/profile_run.sh [bench|launches|admix3|dense|mix|digit ...]
+#   bash tools/profile_run.sh [bench|launches|admix3|dense|mix|digit|digit5 ...]
 set -u
 O=gpurun_out
 mkdir -p $O
@@ -43,6 +43,12 @@ digit)
     ncu --set full --clock-control none --import-source on -k regex:digit_kernel -s 6 -c 2 \
         -o $O/prof_r2g $CMD > $O/ncu_g.log 2>&1
     pages prof_r2g ;;
+digit5)
+    CMD="python tools/dense_time.py c5mix --steps 1"
+    $CMD > $O/plain_h.log 2>&1 &&
+    ncu --set full --clock-control none --import-source on -k regex:digit_kernel -s 6 -c 2 \
+        -o $O/prof_r2h $CMD > $O/ncu_h.log 2>&1
+    pages prof_r2h ;;
 esac
 done
 ls -la $O | head -30
