@@ -73,20 +73,21 @@ void *mc_ctx_stream(const mc_ctx *ctx);
 /* Plan options, to be set before mc_alloc_model (they replace environment
  * variables: a stray variable must not switch kernels).
  *   MC_OPT_KERNEL  which genotype-streaming kernel the planner may pick:
- *                  MC_KERNEL_AUTO    when no locus has more than two observed
- *                                    alleles and K <= 16: the dense DMMA kernels
- *                                    (mc_dense.cuh) for the admixture model, the
- *                                    digit-sliced integer kernels (mc_digit.cuh)
- *                                    for the mixture model; else the two-pass
- *                                    gather kernel (mc_admix3.cuh; K <= 16,
- *                                    ploidy <= 8), else the one-pass tile kernel
+ *                  MC_KERNEL_AUTO    mixture model, K <= 16, ploidy <= 15: the
+ *                                    digit-sliced integer kernels (mc_digit.cuh;
+ *                                    the count layouts must fit the device).
+ *                                    Admixture model with no locus of more than
+ *                                    two observed alleles and K <= 16: the dense
+ *                                    DMMA kernels (mc_dense.cuh).  Else the
+ *                                    two-pass gather kernel (mc_admix3.cuh;
+ *                                    K <= 16, ploidy <= 8), else the one-pass
+ *                                    tile kernel
  *                  MC_KERNEL_TILE    the one-pass tile kernel only
- *                  MC_KERNEL_ADMIX3  never the dense kernels
+ *                  MC_KERNEL_ADMIX3  never the dense or the digit-sliced kernels
  *                  MC_KERNEL_DENSE   the dense DMMA kernels where they apply (for
  *                                    the mixture model too), else the one-pass
  *                                    tile kernel
- *                  MC_KERNEL_DIGIT   as AUTO on biallelic data, else the one-pass
- *                                    tile kernel
+ *                  MC_KERNEL_DIGIT   same plans as AUTO (named for tests)
  *                  The kernels sum in different orders, so results agree to
  *                  rounding (1e-13 relative observed), not bit for bit.
  *   MC_OPT_TIMING  non-zero: the planner prints its phases to stderr

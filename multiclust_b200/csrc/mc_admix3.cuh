@@ -93,6 +93,10 @@ struct Admix3Args {
 					 * read-modified-written in L2 by the fold (each row belongs
 					 * to one CTA) */
 	double *llpart;			/* [n_units] */
+	/* MIX_E as the fall-back of the digit-sliced pass (mc_digit.cuh): run only
+	 * when *run_if is set, and leave the chunk count for k_mix_tail */
+	const int *run_if;
+	int *n_chunks_dev;
 };
 
 /* ---------------------------------------------------------------------- */
@@ -212,6 +216,12 @@ __device__ __forceinline__ void a3_stcg2(double *p, double2 v, unsigned long lon
 template <int KP, int PP, int MODE>
 __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(const Admix3Args a)
 {
+	if (MODE == A3_MIX_E) {
+		if (a.run_if && !*a.run_if)
+			return;
+		if (a.n_chunks_dev && blockIdx.x == 0 && threadIdx.x == 0)
+			*a.n_chunks_dev = a.n_lchunks;
+	}
 	constexpr bool P1 = (MODE != A3_MIX_M);			/* pass 1 runs */
 	constexpr bool P2 = (MODE == A3_ADMIX_EM || MODE == A3_MIX_M);	/* pass 2 + fold run */
 	constexpr bool HAS_W = (MODE == A3_ADMIX_EM);

@@ -108,6 +108,9 @@ struct mc_ctx {
 	int *d_dg_flag = nullptr;	/* [0] table not representable, [1] chunks of the E pass */
 	double *d_dg_vscale = nullptr;	/* [2 K] posterior column scaling, k_mix_final */
 	int dn_nl = 0, dn_ni = 0;	/* chunk counts of the dense plan */
+	int dg_kind = 0;		/* layout built: 1 biallelic (locus pairs), 2 column pairs */
+	int dg_min_tiles = 0, dg_min_chunks = 0;	/* partial-sum slots the digit plan needs */
+	int *d_col_locus = nullptr;	/* [T] locus of every allele column (column-pair form) */
 	/* kernels whose dynamic shared-memory limit has been raised (set once per
 	 * kernel and size, not on every launch) */
 	std::vector<std::pair<const void *, size_t>> smem_attr;
@@ -282,6 +285,7 @@ static void free_plan(mc_ctx *c)
 	c->use3 = false;
 	c->use_dn = false;
 	c->use_dg = false;
+	c->dg_min_tiles = c->dg_min_chunks = 0;
 }
 
 /* the admixture kernel's tile codes and entry lists depend on the data only,
@@ -294,8 +298,14 @@ static void free_layout3(mc_ctx *c)
 	c->layout3 = false;
 	dfree(c->d_dn_cnt);
 	c->layout_dn = false;
-	dfree(c->d_dg_cntE); dfree(c->d_dg_cntM);
+}
+
+/* the count layouts of the digit-sliced mixture kernels: data only, too */
+static void free_layout_dg(mc_ctx *c)
+{
+	dfree(c->d_dg_cntE); dfree(c->d_dg_cntM); dfree(c->d_col_locus);
 	c->layout_dg = false;
+	c->dg_kind = 0;
 }
 
 static void free_model(mc_ctx *c)
@@ -318,6 +328,7 @@ static void free_data(mc_ctx *c)
 {
 	free_model(c);
 	free_layout3(c);
+	free_layout_dg(c);
 	dfree(c->d_init_z); dfree(c->d_init_N); dfree(c->d_init_h);
 	c->init_z_n = c->init_N_n = c->init_h_n = 0;
 	dfree(c->d_nat); dfree(c->d_J); dfree(c->d_off);
@@ -628,6 +639,9 @@ static int alloc_outputs(mc_ctx *c, int n_tiles, int n_chunks, int n_units, long
 	const int K = c->K;
 	c->act_tiles = n_tiles; c->act_chunks = n_chunks; c->act_units = n_units;
 	c->act_Ipad = Ipad;
+	/* room for the chunk counts of a digit-sliced plan on the same buffers */
+	n_tiles = std::max(n_tiles, c->dg_min_tiles);
+	n_chunks = std::max(n_chunks, c->dg_min_chunks);
 	const size_t nN = (size_t)n_chunks * K * std::max<int64_t>(c->T, 1);
 	CK(MC_DEV_MALLOC(&c->d_Apart, sizeof(double) * (size_t)n_tiles * Ipad * K));
 	CK(MC_DEV_MALLOC(&c->d_Npart, sizeof(double) * nN));
@@ -649,8 +663,7 @@ static int make_plan3(mc_ctx *c)
 	c->use3 = false;
 	if (c->PP > 8 || c->K > 16 || c->T < 1)
 		return MC_OK;
-	if (c->opt_kernel == MC_KERNEL_TILE || c->opt_kernel == MC_KERNEL_DENSE
-		|| c->opt_kernel == MC_KERNEL_DIGIT)
+	if (c->opt_kernel == MC_KERNEL_TILE || c->opt_kernel == MC_KERNEL_DENSE)
 		return MC_OK;
 	const int K = c->K, KP = (K + 1) / 2, KR = 2 * KP, PP = c->PP, L = c->L;
 	const int LT = A3_NC / PP;
@@ -792,13 +805,17 @@ static int make_plan3(mc_ctx *c)
 
 /* mode: A3_ADMIX_EM / A3_ADMIX_LL / A3_MIX_E (p = the log p table) / A3_MIX_M (eta = v_ik) */
 static int launch_admix3(mc_ctx *c, int mode, const double *p, const double *eta,
-	long long eta_stride)
+	long long eta_stride, bool fallback = false)
 {
 	admix3_fn fn = mc_pick_admix3(mode, c->KP3, c->PP);
 	if (!fn)
 		return fail(c, MC_ERR_UNSUPPORTED, "no admix3 kernel for K=%d P=%d", c->K, c->P);
 	Admix3Args a = c->a3;
 	a.p = p; a.eta = eta; a.eta_stride = eta_stride;
+	if (fallback) {	/* behind the digit kernels: runs only when they declined */
+		a.run_if = c->d_dg_flag;
+		a.n_chunks_dev = c->d_dg_flag + 1;
+	}
 	const size_t smem = a3_smem_bytes(c->KP3, mode, a.ncolmax, a.cap);
 	{
 		const int rca = raise_smem_limit(c, (const void *)fn, smem);
@@ -850,30 +867,52 @@ static int digit_chunks(long long n_ctarows, int n_blocks, long long slots, int 
 
 /* called from make_plan_dense for the mixture model: the same biallelic data,
  * K <= 16.  Sets c->use_dg and the chunk counts of the two passes. */
-static int make_plan_digit(mc_ctx *c, long long Ipad, int *ncE, int *ncM)
+static int make_plan_digit(mc_ctx *c, int general, long long Ipad, int *ncE, int *ncM)
 {
 	c->use_dg = false;
 	*ncE = *ncM = 0;
-	if (c->admixture || c->opt_kernel == MC_KERNEL_DENSE)
+	if (c->admixture || c->opt_kernel == MC_KERNEL_DENSE || c->K > 16 || c->P > 15 || c->T < 1)
 		return MC_OK;
 	const int K = c->K, R = dg_R(K);
 	digit_fn fE = mc_pick_digit(K, DG_MIX_E), fM = mc_pick_digit(K, DG_MIX_M);
 	if (!fE || !fM)
 		return MC_OK;
-	const long long mtE = (c->I + 15) / 16, blE = (c->L + 63) / 64;
-	const long long mtM = (c->L + 7) / 8, blM = (c->I + 127) / 128;
+	/* bytes per row of the count matrix: one per locus, or one per column pair */
+	const long long nb = general ? (c->T + 1) / 2 : c->L;
+	const long long mtE = (c->I + 15) / 16, blE = (nb + 63) / 64;
+	const long long mtM = (nb + 7) / 8, blM = (c->I + 127) / 128;
 	if (mtE * blE > 0x7fffffffLL || mtM * blM > 0x7fffffffLL || blM > 0x7fffffffLL)
 		return MC_OK;
+	if (c->layout_dg && c->dg_kind != (general ? 2 : 1))
+		return MC_OK;
 	if (!c->layout_dg) {
+		const size_t need = sizeof(uint4) * ((size_t)mtE * blE + (size_t)mtM * blM) * 64;
+		size_t mfree = 0, mtotal = 0;
+		CK(cudaMemGetInfo(&mfree, &mtotal));
+		/* the two count layouts must leave room for the model: else the
+		 * gather kernels run the mixture passes */
+		if (general && need + (need >> 2) + ((size_t)1 << 30) > mfree)
+			return MC_OK;
+		if (general) {
+			std::vector<int> cl((size_t)c->T);
+			for (int l = 0; l < c->L; l++)
+				for (int j = 0; j < c->J[l]; j++)
+					cl[(size_t)c->off[l] + j] = l;
+			int rcu;
+			if ((rcu = upload(c, c->d_col_locus, cl))) return rcu;
+		}
 		CK(MC_DEV_MALLOC(&c->d_dg_cntE, sizeof(uint4) * (size_t)mtE * blE * 64));
 		CK(MC_DEV_MALLOC(&c->d_dg_cntM, sizeof(uint4) * (size_t)mtM * blM * 64));
 		k_digit_counts<<<grid_for(c, mtE * blE * 64, 256), 256, 0, c->stream>>>(c->d_nat,
-			c->d_dg_cntE, c->I, c->L, c->P, (int)mtE, (int)blE, DG_MIX_E);
+			c->d_dg_cntE, c->I, c->L, c->P, (int)mtE, (int)blE, DG_MIX_E, general, c->T,
+			c->d_col_locus, c->d_off);
 		LAUNCH_CHECK("k_digit_counts");
 		k_digit_counts<<<grid_for(c, mtM * blM * 64, 256), 256, 0, c->stream>>>(c->d_nat,
-			c->d_dg_cntM, c->I, c->L, c->P, (int)mtM, (int)blM, DG_MIX_M);
+			c->d_dg_cntM, c->I, c->L, c->P, (int)mtM, (int)blM, DG_MIX_M, general, c->T,
+			c->d_col_locus, c->d_off);
 		LAUNCH_CHECK("k_digit_counts");
 		c->layout_dg = true;
+		c->dg_kind = general ? 2 : 1;
 	}
 	CK(MC_DEV_MALLOC(&c->d_dg_tabE, sizeof(uint2) * (size_t)blE * 4 * K * 32));
 	CK(MC_DEV_MALLOC(&c->d_dg_tabM, sizeof(uint2) * (size_t)blM * 4 * K * 32));
@@ -895,7 +934,7 @@ static int make_plan_digit(mc_ctx *c, long long Ipad, int *ncE, int *ncM)
 			dg_smem_bytes(K));
 		occ = std::max(occ, 1);
 		memset(&a, 0, sizeof a);
-		a.K = K; a.L = c->L;
+		a.K = K; a.L = c->L; a.general = general;
 		a.n_mtiles = (int)mt; a.n_blocks = (int)bl;
 		const long long wunits = (mt + R - 1) / R;
 		a.n_ctarows = (int)((wunits + DG_WARPS - 1) / DG_WARPS);
@@ -910,7 +949,9 @@ static int make_plan_digit(mc_ctx *c, long long Ipad, int *ncE, int *ncM)
 		a.I = c->I; a.Ipad = Ipad; a.T = c->T;
 		a.off = c->d_off; a.J = c->d_J;
 	};
-	plan(c->dgE, fE, mtE, blE, 64, (double)c->I * K * 16.0 / 5e6);
+	/* elements of the contraction dimension per block that can carry counts:
+	 * 64 loci, or 128 columns that may be 128 loci, or 128 individuals */
+	plan(c->dgE, fE, mtE, blE, general ? 128 : 64, (double)c->I * K * 16.0 / 5e6);
 	plan(c->dgM, fM, mtM, blM, 128, (double)K * (double)c->T * 16.0 / 5e6);
 	c->dgE.cnt = c->d_dg_cntE; c->dgE.tab = c->d_dg_tabE;
 	c->dgM.cnt = c->d_dg_cntM; c->dgM.tab = c->d_dg_tabM;
@@ -919,6 +960,8 @@ static int make_plan_digit(mc_ctx *c, long long Ipad, int *ncE, int *ncM)
 		return MC_OK;
 	*ncE = c->dgE.n_chunks;
 	*ncM = c->dgM.n_chunks;
+	c->dg_min_tiles = *ncE;
+	c->dg_min_chunks = *ncM;
 	c->use_dg = true;
 	return MC_OK;
 }
@@ -936,9 +979,10 @@ static int launch_digit(mc_ctx *c, int mode, const double *src, int take_log)
 	const long long n = (long long)a.n_blocks * 4 * c->K;
 	k_digit_table<<<grid_for(c, n * 32, 256), 256, 0, c->stream>>>(src, c->d_dg_vscale,
 		const_cast<uint2 *>(a.tab), c->d_dg_flag, mode == DG_MIX_E ? take_log : 0, c->K,
-		c->I, c->L, c->T, c->d_off, c->d_J, a.n_blocks);
+		c->I, c->L, c->T, c->d_off, c->d_J, a.n_blocks, a.general);
 	LAUNCH_CHECK("k_digit_table");
 	a.out = mode == DG_MIX_E ? c->d_Apart : c->d_Npart;
+	a.Ipad = c->act_Ipad;
 	a.unscale = c->d_dg_vscale + c->K;
 	if (mode == DG_MIX_E && take_log == 2) {
 		a.skip_if = c->d_dg_flag;
@@ -1042,7 +1086,7 @@ static int make_plan_dense(mc_ctx *c)
 	a.lc_first = c->d_dn_lc_first; a.off = c->d_off; a.J = c->d_J;
 	a.cnt = c->d_dn_cnt; a.pd = c->d_dn_pd;
 	int ncE = 0, ncM = 0;
-	if ((rc = make_plan_digit(c, a.Ipad, &ncE, &ncM))) return rc;
+	if ((rc = make_plan_digit(c, 0, a.Ipad, &ncE, &ncM))) return rc;
 	if ((rc = alloc_outputs(c, std::max(best_nl, ncE), std::max(best_ni, ncM), a.n_units,
 		a.Ipad))) return rc;
 	c->dn_nl = best_nl; c->dn_ni = best_ni;
@@ -1096,14 +1140,40 @@ static int launch_dense(mc_ctx *c, int mode, const double *ptab, const double *p
 	return MC_OK;
 }
 
+static int make_plan_base(mc_ctx *c);
+
+/* The planner: dense / digit-sliced plans for biallelic data; else, for the
+ * mixture model, the digit-sliced plan on column pairs (mc_digit.cuh) on top
+ * of the gather plan that stays as its fall-back; else the gather plans. */
 static int make_plan(mc_ctx *c)
 {
-	const int K = c->K;
 	{
 		const int rcd = make_plan_dense(c);
 		if (rcd || c->use_dn)
 			return rcd;
 	}
+	int ncE = 0, ncM = 0;
+	if (!c->admixture && (c->opt_kernel == MC_KERNEL_AUTO || c->opt_kernel == MC_KERNEL_DIGIT)
+		&& c->dg_kind != 1) {
+		const int rcg = make_plan_digit(c, 1, 0, &ncE, &ncM);
+		if (rcg)
+			return rcg;
+	}
+	const bool dg = c->use_dg;
+	const int rc = make_plan_base(c);	/* free of use_dg; sizes the partial sums */
+	if (rc)
+		return rc;
+	if (dg) {
+		c->use_dg = true;
+		c->act_tiles = ncE;
+		c->act_chunks = ncM;
+	}
+	return MC_OK;
+}
+
+static int make_plan_base(mc_ctx *c)
+{
+	const int K = c->K;
 	{
 		const int rc3 = make_plan3(c);
 		if (rc3 || c->use3)
@@ -1313,13 +1383,17 @@ extern "C" int mc_copy_slot(mc_ctx *c, int dst, int src)
 /* --------------------------------------------------- tile kernel dispatch */
 
 static int launch_tile(mc_ctx *c, int mode, const double *p, const double *eta,
-	long long eta_stride)
+	long long eta_stride, bool fallback = false)
 {
 	tile_fn fn = mc_pick_tile(mode, c->KH, c->PP);
 	if (!fn)
 		return fail(c, MC_ERR_UNSUPPORTED, "no kernel for KH=%d PP=%d", c->KH, c->PP);
 	TileArgs ta = c->ta;
 	ta.p = p; ta.eta = eta; ta.eta_stride = eta_stride;
+	if (fallback) {
+		ta.run_if = c->d_dg_flag;
+		ta.n_chunks_dev = c->d_dg_flag + 1;
+	}
 	{
 		const int rca = raise_smem_limit(c, (const void *)fn, c->smem_em);
 		if (rca)
@@ -1460,9 +1534,9 @@ extern "C" int mc_em_step_local(mc_ctx *c, int from, int to)
 			if ((rc = reduce_columns(c, c->d_post, c->I, K, xb_S(c)))) return rc;
 		}
 	} else {
-		if (!c->use_dn) {
+		if (!c->use_dn && !c->use_dg) {
 			k_log_table<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_p[from],
-				c->d_logp, c->np, 1);
+				c->d_logp, c->np, 1, nullptr);
 			LAUNCH_CHECK("k_log_table");
 		}
 		if ((rc = c->use_dg ? launch_digit(c, DG_MIX_E, c->d_p[from], 1)
@@ -1853,18 +1927,18 @@ static int loglik_launch(mc_ctx *c, int slot)
 		if (rc) return rc;
 		if ((rc = reduce_vector(c, c->d_llpart, c->act_units, xb_ll(c)))) return rc;
 	} else {
+		/* the digit-sliced pass first (it raises the flag), then the FP64 pass:
+		 * the pass proper, or the fall-back gated on the flag */
+		const bool fb = c->use_dg;
+		if (fb && (rc = launch_digit(c, DG_MIX_E, c->d_p[slot], 2))) return rc;
 		if (!c->use_dn) {
 			k_log_table<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_p[slot],
-				c->d_logp, c->np, 0);
+				c->d_logp, c->np, 0, fb ? c->d_dg_flag : nullptr);
 			LAUNCH_CHECK("k_log_table");
 		}
-		if (c->use_dg) {
-			if ((rc = launch_digit(c, DG_MIX_E, c->d_p[slot], 2))) return rc;
-			if ((rc = launch_dense(c, DN_MIX_E, c->d_p[slot], nullptr, nullptr, 0, 2,
-				true))) return rc;
-		} else if ((rc = c->use_dn ? launch_dense(c, DN_MIX_E, c->d_p[slot], nullptr, nullptr, 0, 2)
-			: c->use3 ? launch_admix3(c, A3_MIX_E, c->d_logp, nullptr, 0)
-			: launch_tile(c, MODE_MIX_E, c->d_logp, nullptr, 0))) return rc;
+		if ((rc = c->use_dn ? launch_dense(c, DN_MIX_E, c->d_p[slot], nullptr, nullptr, 0, 2, fb)
+			: c->use3 ? launch_admix3(c, A3_MIX_E, c->d_logp, nullptr, 0, fb)
+			: launch_tile(c, MODE_MIX_E, c->d_logp, nullptr, 0, fb))) return rc;
 		/* the posterior of the last E-step must survive: only the per-
 		 * individual ll buffer is written */
 		if ((rc = mix_tail(c, c->d_eta[slot], nullptr, 1))) return rc;

@@ -23,6 +23,12 @@
  * the integer tensor path runs 32 MACs for each FP64 FMA of the DMMA path
  * (tools/imma_probe.cu, profiles/r02_imma_probe.txt).
  *
+ * Data with more than two alleles at a locus use the same kernel on COLUMN
+ * pairs instead of (locus, allele) pairs (`general`): the count matrix is
+ * [I][T] over the allele columns off_l + j, two adjacent columns per byte, and
+ * "locus l, allele h" below reads "column 2 B + h of byte B".  Biallelic data keep
+ * the locus form: a phantom slot (J_l = 3) costs no column there.
+ *
  * Layout (built once per data set by mc_digit_build.cuh):
  *	cnt [m-tile][block][2][32] uint4 -- 16 rows x 64 count bytes (c0 | c1 << 4)
  *	    in fragment order: a warp's two 512-byte loads are contiguous.
@@ -59,6 +65,7 @@ __host__ __device__ constexpr int dg_R(int K)
 
 struct DigitArgs {
 	int K, L;
+	int general;			/* 0: biallelic (locus, allele) pairs; 1: column pairs */
 	int n_mtiles, n_blocks, n_chunks, n_ctarows;
 	long long I, Ipad, T;
 	const int *off, *J;		/* [L + 1], [L] */
@@ -237,10 +244,15 @@ __global__ void __launch_bounds__(DG_THREADS, 2) digit_kernel(const DigitArgs a)
 		int Jl = 0;
 		long long ol = 0;
 		if (MODE == DG_MIX_M) {
-			const int l = mt * 8 + g;
-			if (l < a.L) {
-				Jl = a.J[l];
-				ol = a.off[l];
+			if (a.general) {	/* row g + 8 h = allele column 2 (8 mt + g) + h */
+				ol = 2LL * (mt * 8 + g);
+				Jl = ol + 1 < a.T ? 2 : ol < a.T ? 1 : 0;
+			} else {
+				const int l = mt * 8 + g;
+				if (l < a.L) {
+					Jl = a.J[l];
+					ol = a.off[l];
+				}
 			}
 		}
 #pragma unroll

@@ -21,11 +21,35 @@ __device__ __forceinline__ unsigned dg_count_byte(const unsigned char *nat, long
 	return c0 | c1 << 4;
 }
 
+/* counts of the allele columns 2 B and 2 B + 1 of individual i (general form):
+ * column t belongs to locus col_locus[t] and stands for allele code t - off_l */
+__device__ __forceinline__ unsigned dg_count_cols(const unsigned char *nat, long long i,
+	long long B, long long I, int L, int P, long long T, const int *col_locus, const int *off)
+{
+	unsigned byte = 0u;
+	if (i >= I)
+		return 0u;
+	for (int h = 0; h < 2; h++) {
+		const long long col = 2 * B + h;
+		if (col >= T)
+			break;
+		const int l = col_locus[col];
+		const unsigned code = (unsigned)(col - off[l]);
+		const unsigned char *c = nat + ((size_t)i * L + l) * P;
+		unsigned n = 0;
+		for (int a = 0; a < P; a++)
+			n += c[a] == code;
+		byte |= n << (4 * h);
+	}
+	return byte;
+}
+
 /* one thread per uint4 of the fragment-ordered count array (mc_digit.cuh).
  * mode DG_MIX_E: m-tile = 16 individuals, block = 64 loci;
  * mode DG_MIX_M: m-tile = 8 loci, block = 128 individuals. */
 __global__ void k_digit_counts(const unsigned char *nat, uint4 *cnt, long long I, int L,
-	int P, int n_mtiles, int n_blocks, int mode)
+	int P, int n_mtiles, int n_blocks, int mode, int general, long long T,
+	const int *col_locus, const int *off)
 {
 	const long long n = (long long)n_mtiles * n_blocks * 64;
 	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
@@ -48,7 +72,10 @@ __global__ void k_digit_counts(const unsigned char *nat, uint4 *cnt, long long I
 					l = mt * 8 + g;
 					i = (long long)b * 128 + 32 * t + 16 * h + 4 * s + jj;
 				}
-				if (l < L)
+				/* general form: `l` is the byte (column pair) index */
+				if (general)
+					w[s] |= dg_count_cols(nat, i, l, I, L, P, T, col_locus, off) << (8 * jj);
+				else if (l < L)
 					w[s] |= dg_count_byte(nat, i, (int)l, I, L, P) << (8 * jj);
 			}
 		}
@@ -72,7 +99,7 @@ __global__ void k_digit_counts(const unsigned char *nat, uint4 *cnt, long long I
  * empty class keeps its relative precision. */
 __global__ void k_digit_table(const double *src, const double *vscale, uint2 *tab, int *flag,
 	int take_log, int K, long long I, int L, long long T, const int *off, const int *J,
-	int n_blocks)
+	int n_blocks, int general)
 {
 	const int lane = threadIdx.x & 31;
 	const int g = lane >> 2, t = lane & 3;
@@ -88,8 +115,10 @@ __global__ void k_digit_table(const double *src, const double *vscale, uint2 *ta
 		unsigned long long X = 0ull;
 		if (take_log) {
 			const long long l = b * 64 + 16 * t + 4 * s + jj;
-			if (l < L && half < J[l]) {
-				const double p = src[(size_t)k * T + off[l] + half];
+			/* general form: column 2 l + half of the [K][T] table */
+			const bool valid = general ? 2 * l + half < T : l < L && half < J[l];
+			if (valid) {
+				const double p = src[(size_t)k * T + (general ? 2 * l : off[l]) + half];
 				if (!(take_log == 1 && p == 0.0)) {
 					const double lp = -log(p);
 					if (lp >= 0.0 && lp < 1024.0)

@@ -258,8 +258,10 @@ __global__ void k_update_p(const double *N, int n_chunks, long long chunk_stride
 /* log p table for the mixture passes; zero_skip reproduces the E-step's
  * "p == 0 contributes nothing" rule (em_alg.c:797-804) */
 __global__ void k_log_table(const double *p, double *lp, long long n,
-	int zero_skip)
+	int zero_skip, const int *run_if)
 {
+	if (run_if && !*run_if)		/* fall-back pass that is not needed */
+		return;
 	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
 		x += (long long)gridDim.x * blockDim.x) {
 		const double v = p[x];

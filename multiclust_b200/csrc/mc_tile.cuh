@@ -64,6 +64,9 @@ struct TileArgs {
 	double *Apart;			/* [n_tiles][Ipad][K] */
 	double *Npart;			/* [n_chunks][K*T] */
 	double *llpart;			/* [n_units] */
+	/* MODE_MIX_E as the fall-back of the digit-sliced pass (mc_digit.cuh) */
+	const int *run_if;
+	int *n_chunks_dev;
 };
 
 /* one recursive-halving step over N live values: lanes whose `mask` bit is
@@ -139,6 +142,12 @@ __device__ __forceinline__ void prefetch_l1(const void *ptr)
 template <int KH, int PP, int MODE>
 __global__ void __launch_bounds__(256, 1) tile_kernel(const TileArgs a)
 {
+	if (MODE == MODE_MIX_E) {
+		if (a.run_if && !*a.run_if)
+			return;
+		if (a.n_chunks_dev && blockIdx.x == 0 && threadIdx.x == 0)
+			*a.n_chunks_dev = a.n_tiles;
+	}
 	constexpr int IB = (PP >= 2) ? 16 / PP : 8;	/* individuals per unit */
 	constexpr int UB = IB * PP;			/* bytes per unit: 8 or 16 */
 	constexpr int NH = UB / 8;			/* groups of 8 copies per unit */

@@ -342,6 +342,70 @@ def test_digit_kernels_agree_with_dmma(orc, tmp_path):
     assert np.max(np.abs(v3 - v4)) < 1e-10
 
 
+DIGIT_GENERAL_SHAPES = [
+    # I, L, K, jmax, miss_bp, P: more than two alleles -> the column-pair form
+    (300, 37, 5, 6, 300, 2),
+    (70, 130, 3, 20, 100, 1),      # haploid, up to 20 alleles
+    (129, 65, 16, 5, 0, 2),        # K = 16
+    (90, 50, 7, 4, 100, 4),        # tetraploid
+    (530, 300, 5, 12, 300, 2),     # several blocks of column pairs and of individuals
+    (40, 30, 1, 3, 500, 3),        # K = 1, odd ploidy
+]
+
+
+@pytest.mark.parametrize("shape", DIGIT_GENERAL_SHAPES)
+def test_digit_kernels_multiallelic(orc, tmp_path, shape):
+    """mixture model on multi-allelic data: the digit-sliced kernels on column pairs"""
+    from multiclust_b200 import Context
+    c = Context(0)
+    try:
+        d, fit, eta, p = setup_pair(orc, c, tmp_path, shape, admixture=0)
+        assert int(d["J"].max()) > 2 and c.plan()["two_pass"] == 4
+        ll_o = fit.log_likelihood(0)
+        assert abs(c.loglik(0) - ll_o) <= 1e-12 * abs(ll_o)
+        check_step(orc, c, fit, 0, 1)
+        check_step(orc, c, fit, 1, 1)
+        check_step(orc, c, fit, 1, 2)
+        post = c.posterior()
+        assert abs(c.loglik(2) - fit.log_likelihood(2)) <= 1e-12 * abs(ll_o)
+        assert np.array_equal(post, c.posterior())
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("shape", [(300, 120, 4, 7, 300, 2), (60, 40, 3, 5, 300, 12)])
+def test_digit_multiallelic_log_zero_falls_back(orc, tmp_path, shape):
+    """the log-likelihood pass with p == 0 on multi-allelic data: the FP64 kernel of the plan
+    underneath -- the two-pass gather kernel, or the one-pass kernel at ploidy 12 -- runs
+    behind the declined digit pass, on the device"""
+    from multiclust_b200 import Context
+    I, L, K = shape[:3]
+    c = Context(0)
+    try:
+        d, fit, eta, p = setup_pair(orc, c, tmp_path, shape, admixture=0, proj=0)
+        assert c.plan()["two_pass"] == 4
+        J = d["J"]
+        off = np.concatenate([[0], np.cumsum(J)])
+        p = p.reshape(K, -1).copy()
+        for l in (0, 7, L - 1):
+            if J[l] >= 2:               # class 2 cannot carry allele 0 of these loci
+                s_ = p[2, off[l]] + p[2, off[l] + 1]
+                p[2, off[l]] = 0.0
+                p[2, off[l] + 1] = s_
+        p = p.ravel()
+        fit.set_params(0, eta, p)
+        c.set_params(0, eta, p)
+        ll_o = fit.log_likelihood(0)
+        assert np.isfinite(ll_o)
+        for rep in range(3):            # eager, captured and replayed launch sequence
+            assert abs(c.loglik(0) - ll_o) <= 1e-12 * abs(ll_o)
+        check_step(orc, c, fit, 0, 1)   # E-step: p == 0 contributes nothing
+        ll_1 = fit.log_likelihood(1)
+        assert abs(c.loglik(1) - ll_1) <= 1e-12 * abs(ll_1)
+    finally:
+        c.close()
+
+
 def test_digit_log_zero_falls_back(orc, tmp_path):
     """log 0 has no fixed-point form: without the projection p reaches 0, the log-likelihood
     pass falls back to the FP64 kernels on the device (no host round trip) and the next pass

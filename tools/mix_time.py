@@ -1,13 +1,15 @@
 """Mixture EM step on multi-allelic data of BASELINE config 2's size (I=10k, L=5k, K=5,
-diploid, <=20 alleles per locus, 5 % missing): the two-pass gather kernel's mixture modes
-(admix3 A3_MIX_E / A3_MIX_M) against the round-1 one-pass tile kernel."""
+diploid, <=20 alleles per locus, 5 % missing): the digit-sliced integer kernels on column
+pairs (mc_digit.cuh) against the two-pass gather kernel's mixture modes (admix3 A3_MIX_E /
+A3_MIX_M) and the round-1 one-pass tile kernel."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from multiclust_b200 import Context, SynthParams
 
 I, L, K = 10000, 5000, 5
-for kernel, name in ((0, "auto (admix3 mixture modes)"), (1, "one-pass tile kernel")):
+for kernel, name in ((0, "auto (digit-sliced IMMA kernels on column pairs)"),
+                     (2, "two-pass gather kernel, mixture modes"), (1, "one-pass tile kernel")):
     ctx = Context(0)
     ctx.set_option(ctx.OPT_KERNEL, kernel)
     ctx.set_data_synth(I, L, SynthParams(seed=20261018, K=K, jmax=20, miss_bp=500, ploidy=2))
