@@ -1,7 +1,6 @@
 /*
- * mc_digit.cuh -- the mixture model's two contractions on biallelic data as
- * exact integer GEMMs on the integer tensor path (IMMA, mma.sync m16n8k32
- * u8 x u8 -> s32).
+ * mc_digit.cuh -- the mixture model's two contractions as exact integer GEMMs
+ * on the integer tensor path (IMMA, mma.sync m16n8k32 u8 x u8 -> s32).
  *
  * Reference: em_alg.c:782-826 (E-step, a_ik = sum_l sum_a c_ila log p_kla),
  * log_likelihood.c:186-201 (the same sum for logL_mixture) and em_alg.c:964-990
@@ -18,7 +17,7 @@
  *	        max_i v_ik < 2^e_k
  * with n-tile j of the MMA = class k and column d of the tile = digit d, so a
  * thread quad holds the eight digits of one (row, k) and recombines them with
- * two shuffles.  Sums are exact up to the final rounding to FP64, i.e. at
+ * three shuffles per four values.  Sums are exact up to the final rounding to FP64, i.e. at
  * least as accurate as any FP64 summation order (DESIGN.md has the bound), and
  * the integer tensor path runs 32 MACs for each FP64 FMA of the DMMA path
  * (tools/imma_probe.cu, profiles/r02_imma_probe.txt).

@@ -46,7 +46,8 @@ __device__ __forceinline__ unsigned dg_count_cols(const unsigned char *nat, long
 
 /* one thread per uint4 of the fragment-ordered count array (mc_digit.cuh).
  * mode DG_MIX_E: m-tile = 16 individuals, block = 64 loci;
- * mode DG_MIX_M: m-tile = 8 loci, block = 128 individuals. */
+ * mode DG_MIX_M: m-tile = 8 loci, block = 128 individuals.
+ * general: "locus" reads "byte of two adjacent allele columns". */
 __global__ void k_digit_counts(const unsigned char *nat, uint4 *cnt, long long I, int L,
 	int P, int n_mtiles, int n_blocks, int mode, int general, long long T,
 	const int *col_locus, const int *off)
@@ -83,14 +84,16 @@ __global__ void k_digit_counts(const unsigned char *nat, uint4 *cnt, long long I
 	}
 }
 
-/* The B fragments of the digit table.  One warp per (block, step, class): lane
- * (g, t) computes the fixed-point value of k slot 4 (g & 3) + ... of its own
- * quarter -- slot (half = g / 4, jj = g % 4) of thread column t -- and the
- * lanes exchange them, every lane keeping byte g (digit g) of the eight values
- * of its column.
+/* The B fragments of the digit table.  One warp per (block, step, class): the
+ * fragment of lane (g, t) holds digit g of the eight k slots 4 t + jj and
+ * 16 + 4 t + jj (jj = 0..3) of the step.  Lane (g, t) computes the fixed-point
+ * value of one of the eight slots of thread column t -- (half = g / 4,
+ * jj = g % 4) -- then the eight lanes of a column exchange their values and
+ * every lane keeps byte g of each.
  *
  * E table (take_log 1 or 2, k_dense_p's rule): slot = (locus 64 b + 16 t + 4 s +
- * jj, allele half), X = |log p_kla| 2^54; p == 0 with take_log 1 contributes
+ * jj, allele half) -- column 2 (64 b + 16 t + 4 s + jj) + half in the general
+ * form -- X = |log p_kla| 2^54; p == 0 with take_log 1 contributes
  * nothing; any value outside [0, 1024) -- log 0 of the log-likelihood pass, a
  * NaN -- raises *flag and the pass falls back to the FP64 kernels.
  * M table (take_log 0): slot = individual 128 b + 32 t + 16 half + 4 s + jj,
