@@ -406,6 +406,27 @@ def test_digit_multiallelic_log_zero_falls_back(orc, tmp_path, shape):
         c.close()
 
 
+def test_digit_nan_parameter_is_reported(orc, tmp_path):
+    """a NaN in p has no fixed-point image: the E-step on the digit-sliced kernels must not
+    hide it (the FP64 kernels propagate it by arithmetic) -- the step's log likelihood is NaN,
+    and the flag is gone for the next call"""
+    from multiclust_b200 import Context
+    c = Context(0)
+    try:
+        d, fit, eta, p = setup_pair(orc, c, tmp_path, DIGIT_SHAPES[1], admixture=0)
+        assert c.plan()["two_pass"] == 4
+        bad = p.copy()
+        bad[3] = np.nan
+        c.set_params(1, eta, bad)
+        assert np.isnan(c.em_step(1, 2))
+        assert np.isnan(c.loglik(1))            # falls back: the FP64 kernels propagate it
+        ll_o = fit.log_likelihood(0)
+        assert abs(c.loglik(0) - ll_o) <= 1e-12 * abs(ll_o)
+        check_step(orc, c, fit, 0, 1)
+    finally:
+        c.close()
+
+
 def test_digit_log_zero_falls_back(orc, tmp_path):
     """log 0 has no fixed-point form: without the projection p reaches 0, the log-likelihood
     pass falls back to the FP64 kernels on the device (no host round trip) and the next pass
