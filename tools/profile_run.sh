@@ -31,8 +31,8 @@ dense)
     ncu --set full --clock-control none --import-source on -k regex:dense_kernel -s 3 -c 1 \
         -o $O/prof_r2d $CMD > $O/ncu_d.log 2>&1
     pages prof_r2d ;;
-mix)
-    CMD="python tools/dense_time.py c2 --steps 2"
+mix)        # the DMMA mixture kernels (the planner's own choice is `digit`)
+    CMD="python tools/dense_time.py c2 --steps 2 --kernel 3"
     $CMD > $O/plain_m.log 2>&1 &&
     ncu --set full --clock-control none --import-source on -k regex:dense_kernel -s 6 -c 2 \
         -o $O/prof_r2m $CMD > $O/ncu_m.log 2>&1
