@@ -174,6 +174,35 @@ int mc_init_mixture(mc_ctx *ctx, int slot, const int32_t *center_idx,
 int mc_init_mixture_local(mc_ctx *ctx, const int32_t *center_idx, const uint8_t *center_codes);
 int mc_init_mixture_finish(mc_ctx *ctx, int slot, int64_t I_total);
 
+/* ---- parametric bootstrap (bootstrap.c:31-175, multiclust.c:562-581, 675-708;
+ *      SURVEY.md 8f rank 4) ------------------------------------------------- */
+
+/* Keep the parameters of `slot` as the estimates under H0 that the bootstrap
+ * samples are drawn from (mod->mle_pKLM and mle_etak / mle_etaik,
+ * multiclust.c:562-581).  They survive mc_alloc_model. */
+int mc_save_mle(mc_ctx *ctx, int slot);
+/* Replace this context's genotype data by one parametric bootstrap sample
+ * drawn from the saved estimates, with the reference's draws: glibc TYPE_3
+ * rand() as in mc_init_admixture_rand -- hist[n_blocks][31] are the generator
+ * words in front of every block of block_draws draws (a multiple of 16) --
+ * r = rand() / RAND_MAX, and the inverse-CDF walks of bootstrap.c:92-117 /
+ * 136-169 in the same left-to-right FP64 sums.  Draws, in stream order:
+ *   admixture: for every individual, locus and allele copy one draw for the
+ *              source cluster (eta_i., or the pooled eta with -c) and one for
+ *              the allele (p_kl.): 2 I L P draws;
+ *   mixture:   one draw per individual for its cluster, then one per locus and
+ *              copy for the allele: I (1 + L P) draws.
+ * As in the reference's default parse mode every copy is drawn (missing data
+ * are filled in) and an allele slot is chosen among all J_l, phantom slot
+ * included; a locus without any allele (J_l = 0) stays missing.  The original
+ * data are kept: the admixture initialisers go on reading them, exactly like
+ * the reference's random_allele_partition reads dat->IL, which bootstrap.c never
+ * rewrites (rnd_init.c:460-481).  Frees the model; layouts are rebuilt by the
+ * next mc_alloc_model. */
+int mc_bootstrap_data(mc_ctx *ctx, const uint32_t *hist, int64_t n_blocks, int64_t block_draws);
+/* back to the original data (cleanup_parametric_bootstrap, bootstrap.c:60-66) */
+int mc_restore_data(mc_ctx *ctx);
+
 /* ---- the hot path ------------------------------------------------------ */
 
 /* E-step on slot `from`, M-step (+ simplex projection) into slot `to`;

@@ -15,7 +15,7 @@ SYMBOLS = [
     "mc_last_error", "mc_abi_version", "mc_create", "mc_destroy",
     "mc_set_stream", "mc_sync", "mc_ctx_device", "mc_ctx_stream", "mc_set_data", "mc_set_data_synth",
     "mc_get_dims", "mc_get_J", "mc_get_codes", "mc_alloc_model", "mc_eta_len",
-    "mc_set_params", "mc_get_params", "mc_init_admixture", "mc_init_admixture_local", "mc_init_admixture_rand", "mc_init_admixture_rand_local", "mc_init_mixture", "mc_init_mixture_local", "mc_init_mixture_finish", "mc_em_step", "mc_loglik", "mc_read_ll",
+    "mc_set_params", "mc_get_params", "mc_init_admixture", "mc_init_admixture_local", "mc_init_admixture_rand", "mc_init_admixture_rand_local", "mc_init_mixture", "mc_init_mixture_local", "mc_init_mixture_finish", "mc_save_mle", "mc_bootstrap_data", "mc_restore_data", "mc_em_step", "mc_loglik", "mc_read_ll",
     "mc_get_posterior", "mc_partition", "mc_locale_sums", "mc_delta", "mc_step_dots",
     "mc_qn_dots", "mc_accel_update", "mc_qn_update", "mc_project",
     "mc_copy_slot", "mc_em_step_local", "mc_exchange_buffer",
@@ -234,6 +234,21 @@ class Context:
         assert hist.ndim == 2 and hist.shape[1] == 31
         self._ck(self.lib.mc_init_admixture_rand(self.h, slot, _ptr(hist), hist.shape[0],
                                                  int(block_draws)), "mc_init_admixture_rand")
+
+    # -- parametric bootstrap
+    def save_mle(self, slot):
+        """keep the parameters of `slot` as the H0 estimates the samples are drawn from"""
+        self._ck(self.lib.mc_save_mle(self.h, slot), "mc_save_mle")
+
+    def bootstrap_data(self, hist, block_draws):
+        """replace the data by one parametric bootstrap sample (frees the model)"""
+        hist = np.ascontiguousarray(hist, dtype=np.uint32)
+        assert hist.ndim == 2 and hist.shape[1] == 31
+        self._ck(self.lib.mc_bootstrap_data(self.h, _ptr(hist), hist.shape[0],
+                                            int(block_draws)), "mc_bootstrap_data")
+
+    def restore_data(self):
+        self._ck(self.lib.mc_restore_data(self.h), "mc_restore_data")
 
     def init_mixture(self, slot, center_idx, center_codes):
         """mixture initialiser with the distance work on the device; the host

@@ -48,6 +48,11 @@ struct mc_ctx {
 	int L = 0, P = 0, PP = 0, IB = 0;
 	std::vector<int32_t> J, off;
 	unsigned char *d_nat = nullptr;		/* [I][L][P] */
+	/* parametric bootstrap: the original data while d_nat holds a bootstrap
+	 * sample, and the estimates under H0 the samples are drawn from */
+	unsigned char *d_nat_orig = nullptr;
+	double *d_mle_eta = nullptr, *d_mle_p = nullptr;
+	int mle_K = 0, mle_admixture = 0, mle_per_indiv = 0;
 	int *d_J = nullptr, *d_off = nullptr;
 
 	/* model */
@@ -332,6 +337,8 @@ static void free_data(mc_ctx *c)
 	dfree(c->d_init_z); dfree(c->d_init_N); dfree(c->d_init_h);
 	c->init_z_n = c->init_N_n = c->init_h_n = 0;
 	dfree(c->d_nat); dfree(c->d_J); dfree(c->d_off);
+	dfree(c->d_nat_orig); dfree(c->d_mle_eta); dfree(c->d_mle_p);
+	c->mle_K = 0;
 	c->I = 0;
 	c->dn_maxcode = -1;
 }
@@ -1659,7 +1666,9 @@ static int init_from_assignment(mc_ctx *c, int slot)
 		return rc;
 	CK(cudaMemsetAsync(c->d_init_N, 0, sizeof(unsigned) * np, c->stream));
 	k_init_counts<<<(unsigned)std::min<long long>(std::max<long long>(c->I, 1),
-		(long long)c->num_sms * 32), 128, 0, c->stream>>>(c->d_nat, c->d_init_z,
+		(long long)c->num_sms * 32), 128, 0, c->stream>>>(
+		/* rnd_init.c:460-481 reads dat->IL, which a bootstrap never rewrites */
+		c->d_nat_orig ? c->d_nat_orig : c->d_nat, c->d_init_z,
 		c->I, c->L, c->P, c->K, c->d_off, c->T, c->d_post, c->d_init_N);
 	LAUNCH_CHECK("k_init_counts");
 	k_u32_to_f64<<<grid_for(c, c->np, 256), 256, 0, c->stream>>>(c->d_init_N, xb_N(c), c->np);
@@ -1737,6 +1746,106 @@ extern "C" int mc_init_admixture_rand(mc_ctx *c, int slot, const uint32_t *hist,
 	rc = mc_em_step_finish(c, slot, nullptr);
 	CK(cudaStreamSynchronize(c->stream));
 	return rc;
+}
+
+/* ------------------------------------------------- parametric bootstrap */
+
+extern "C" int mc_save_mle(mc_ctx *c, int slot)
+{
+	NVTX_FN();
+	NEED_MODEL();
+	CHECK_SLOT(slot);
+	const size_t ne = (size_t)(c->per_indiv ? c->I * (long long)c->K : c->K);
+	const size_t np = (size_t)std::max<int64_t>(c->np, 1);
+	if (c->mle_K != c->K || c->mle_per_indiv != c->per_indiv) {
+		dfree(c->d_mle_eta); dfree(c->d_mle_p);
+		CK(MC_DEV_MALLOC(&c->d_mle_eta, sizeof(double) * std::max<size_t>(ne, 1)));
+		CK(MC_DEV_MALLOC(&c->d_mle_p, sizeof(double) * np));
+		c->mle_K = c->K;
+		c->mle_per_indiv = c->per_indiv;
+	}
+	c->mle_admixture = c->admixture;
+	CK(cudaMemcpyAsync(c->d_mle_eta, c->d_eta[slot], sizeof(double) * ne,
+		cudaMemcpyDeviceToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->d_mle_p, c->d_p[slot], sizeof(double) * (size_t)c->np,
+		cudaMemcpyDeviceToDevice, c->stream));
+	return MC_OK;
+}
+
+/* every data-derived layout goes; the model with them (its plan points there) */
+static void drop_layouts(mc_ctx *c)
+{
+	free_model(c);
+	free_layout3(c);
+	free_layout_dg(c);
+	c->dn_maxcode = -1;
+}
+
+extern "C" int mc_bootstrap_data(mc_ctx *c, const uint32_t *hist, int64_t n_blocks,
+	int64_t block_draws)
+{
+	NVTX_FN();
+	if (!c || !hist)
+		return MC_ERR_ARG;
+	if (!c->I || !c->d_mle_p)
+		return fail(c, MC_ERR_STATE, "mc_bootstrap_data: no data or no saved estimates "
+			"(mc_save_mle)");
+	CK(cudaSetDevice(c->device));
+	const long long per = (long long)c->L * c->P;
+	const long long per_i = c->mle_admixture ? 2 * per : 1 + per;
+	const long long n = c->I * per_i;
+	if (block_draws < 1 || block_draws % 16 || n_blocks * block_draws < n
+		|| (n_blocks - 1) * block_draws >= std::max<long long>(n, 1))
+		return fail(c, MC_ERR_ARG, "mc_bootstrap_data: %lld blocks of %lld draws do not "
+			"tile the %lld draws of the sample (blocks must be multiples of 16)",
+			(long long)n_blocks, (long long)block_draws, n);
+	drop_layouts(c);
+	const size_t bytes = (size_t)c->I * c->L * c->P;
+	if (!c->d_nat_orig) {
+		c->d_nat_orig = c->d_nat;
+		c->d_nat = nullptr;
+		CK(MC_DEV_MALLOC(&c->d_nat, std::max<size_t>(bytes, 1)));
+	}
+	unsigned *d_hist = nullptr, *d_draws = nullptr;
+	CK(MC_DEV_MALLOC(&d_hist, sizeof(unsigned) * 31 * (size_t)n_blocks));
+	CK(cudaMemcpyAsync(d_hist, hist, sizeof(unsigned) * 31 * (size_t)n_blocks,
+		cudaMemcpyHostToDevice, c->stream));
+	/* slabs of whole individuals, at most 2^28 draws (1 GiB of raw draws) each */
+	const long long slab_i = std::max<long long>(1, (1LL << 28) / per_i);
+	const long long cap_blocks = (slab_i * per_i + block_draws - 1) / block_draws + 2;
+	CK(MC_DEV_MALLOC(&d_draws, sizeof(unsigned) * (size_t)std::min<long long>(cap_blocks,
+		n_blocks) * block_draws));
+	for (long long i0 = 0; i0 < c->I; i0 += slab_i) {
+		const long long i1 = std::min<long long>(c->I, i0 + slab_i);
+		const long long b0 = i0 * per_i / block_draws;
+		const long long b1 = (i1 * per_i - 1) / block_draws + 1;
+		const long long d0 = b0 * block_draws;
+		k_rand_raw<<<(unsigned)((b1 - b0 + 63) / 64), 64, 0, c->stream>>>(d_hist + 31 * b0,
+			b1 - b0, block_draws, n - d0, d_draws);
+		LAUNCH_CHECK("k_rand_raw");
+		k_bootstrap_codes<<<grid_for(c, (i1 - i0) * c->L, 128), 128, 0, c->stream>>>(d_draws,
+			d0, i0, i1, c->L, c->P, c->mle_K, c->T, c->d_off, c->d_J, c->d_mle_eta,
+			c->mle_per_indiv ? c->mle_K : 0, c->d_mle_p, c->mle_admixture, c->d_nat);
+		LAUNCH_CHECK("k_bootstrap_codes");
+	}
+	CK(cudaStreamSynchronize(c->stream));	/* hist is the caller's again */
+	cudaFree(d_hist);
+	cudaFree(d_draws);
+	return MC_OK;
+}
+
+extern "C" int mc_restore_data(mc_ctx *c)
+{
+	if (!c)
+		return MC_ERR_ARG;
+	if (!c->d_nat_orig)
+		return MC_OK;
+	CK(cudaSetDevice(c->device));
+	drop_layouts(c);
+	dfree(c->d_nat);
+	c->d_nat = c->d_nat_orig;
+	c->d_nat_orig = nullptr;
+	return MC_OK;
 }
 
 /* mixture initialiser (rnd_init.c:192-339): nearest-centre assignment of this

@@ -498,6 +498,103 @@ __global__ void k_rand_assign(const unsigned *hist, long long n_blocks, long lon
 }
 
 /* ------------------------------------------------------------------ */
+/* parametric bootstrap (bootstrap.c:77-175)                              */
+
+/* the raw draws of k_rand_assign's stream: out[d] = rand() of draw d */
+__global__ void k_rand_raw(const unsigned *hist, long long n_blocks, long long block_draws,
+	long long n, unsigned *out_all)
+{
+	const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	if (b >= n_blocks)
+		return;
+	unsigned h[31];
+#pragma unroll
+	for (int j = 0; j < 31; j++)
+		h[j] = hist[(size_t)b * 31 + j];
+	const long long first = b * block_draws;
+	const long long cnt = n - first < block_draws ? n - first : block_draws;
+	unsigned *out = out_all + first;
+	long long done = 0;
+	for (; done + MC_RAND_ROUND <= cnt; done += MC_RAND_ROUND) {
+#pragma unroll
+		for (int g = 0; g < 124; g++) {
+			unsigned w[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const int i = (g * 4 + q) % 31;
+				h[i] += h[(i + 28) % 31];
+				w[q] = h[i] >> 1;
+			}
+			*reinterpret_cast<uint4 *>(out + done + g * 4) = make_uint4(w[0], w[1], w[2], w[3]);
+		}
+	}
+	if (done < cnt) {
+		unsigned t[31];
+#pragma unroll
+		for (int j = 0; j < 31; j++)
+			t[j] = h[j];
+		int f = 0;
+		for (; done < cnt; done++) {
+			t[f] += t[f >= 3 ? f - 3 : f + 28];
+			out[done] = t[f] >> 1;
+			if (++f == 31)
+				f = 0;
+		}
+	}
+}
+
+/* inverse-CDF walk of bootstrap.c:96-105, 109-114: the first index whose
+ * running sum reaches r, the last one if none does */
+__device__ __forceinline__ int boot_pick(const double *w, int n, double r)
+{
+	int j = 0;
+	double sum = 0.0;
+	while (j < n && r > sum)
+		sum = __dadd_rn(sum, w[j++]);
+	return j ? j - 1 : 0;
+}
+
+/* one thread per (individual, locus) of rows [i0, i1): the P allele copies of
+ * the bootstrap sample.  draws[] holds the stream from draw `d0` on. */
+__global__ void k_bootstrap_codes(const unsigned *draws, long long d0, long long i0,
+	long long i1, int L, int P, int K, long long T, const int *off, const int *J,
+	const double *eta, long long eta_stride, const double *p, int admixture,
+	unsigned char *nat)
+{
+	const long long n = (i1 - i0) * L;
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		const long long i = i0 + x / L;
+		const int l = (int)(x % L);
+		const int Jl = J[l];
+		unsigned char *out = nat + ((size_t)i * L + l) * P;
+		const long long per = (long long)L * P;
+		int k = 0;
+		long long base;
+		if (admixture) {
+			base = 2 * (i * per + (long long)l * P);
+		} else {
+			const long long bi = i * (1 + per);
+			k = boot_pick(eta, K, __ddiv_rn((double)draws[bi - d0], 2147483647.0));
+			base = bi + 1 + (long long)l * P;
+		}
+		for (int a = 0; a < P; a++) {
+			double r;
+			if (admixture) {
+				r = __ddiv_rn((double)draws[base + 2 * a - d0], 2147483647.0);
+				k = boot_pick(eta + (size_t)i * eta_stride, K, r);
+				r = __ddiv_rn((double)draws[base + 2 * a + 1 - d0], 2147483647.0);
+			} else {
+				r = __ddiv_rn((double)draws[base + a - d0], 2147483647.0);
+			}
+			out[a] = Jl > 0 ? (unsigned char)boot_pick(p + (size_t)k * T + off[l], Jl, r)
+				: (unsigned char)MC_MISSING;
+		}
+	}
+}
+
+
+/* ------------------------------------------------------------------ */
 /* mixture initialiser (rnd_init.c:192-339) on the device                 */
 
 /* L1 distance between the allele-count vectors of two genotypes at one locus

@@ -3,13 +3,13 @@
  * (reference multiclust.c:67-160, 365-660, 715-978, 1181-1279, 1396-1735).
  *
  * Same command line as the reference for the EM path: -a -c -k -1 -2 -m -n -s
- * -p --missing -f -d -o -e -E -g -i -r -t -T -v -w -M -R --projection --bound,
- * plus -C (the iteration cap the reference documents but only implements as
- * -T, README.md:42 vs multiclust.c:1634) and three additions: --device,
- * --gpus and --trace.  Options of the reference that belong to parts outside
- * the EM path (-b bootstrap, -x block relaxation, --simulate, -I index input,
- * --impute, -P/-Q warm start, -A, -u) are recognised and refused with a clear
- * message instead of being half-implemented.
+ * -p --missing -f -d -o -e -E -g -i -r -t -T -v -w -M -R --projection --bound
+ * -b (parametric bootstrap), plus -C (the iteration cap the reference documents
+ * but only implements as -T, README.md:42 vs multiclust.c:1634) and three
+ * additions: --device, --gpus and --trace.  Options of the reference that
+ * belong to parts outside the EM path (-x block relaxation, --simulate, -I
+ * index input, --impute, -P/-Q warm start, -A, -u) are recognised and refused
+ * with a clear message instead of being half-implemented.
  *
  * The K loop, the initialisation loop with its best-so-far bookkeeping and the
  * per-initialisation / summary output lines keep the reference's order and
@@ -162,7 +162,7 @@ void free_data(data *dat)
 		free(dat->pops[n]);
 	free(dat->pops); free(dat->idv); free(dat->i_p); free(dat->I_K);
 	free(dat->uniquealleles); free(dat->nreal); free(dat->allele_off);
-	free(dat->labels); free(dat->label_off); free(dat->codes);
+	free(dat->labels); free(dat->label_off); free(dat->codes); free(dat->codes_orig);
 	free(dat);
 }
 
@@ -216,6 +216,7 @@ void fprint_usage(FILE *fp, const char *cmd)
 "  -i <n>        plain EM iterations before accelerating\n"
 "  -g <n>        step-size halvings tried when an accelerated step fails\n"
 "  -t <min>      time limit; -r <seed>  seed rand(); --bound <x>  parameter floor\n"
+"  -b <n>        parametric bootstrap: n samples under H0: K-1, tested against Ha: K\n"
 "  --projection  do not project onto the simplex\n"
 "output\n"
 "  -d <dir>      directory of the result files; -o <prefix> their name prefix\n"
@@ -300,7 +301,10 @@ int parse_options(options *opt, data *dat, int argc, const char **argv)
 					goto bad_arg;
 				break;
 			}
-			return unsupported(argv[i], "parametric bootstrap");
+			/* -b n: parametric bootstrap (reference multiclust.c:1427-1434) */
+			if (read_int_arg(argc, argv, ++i, 0, &opt->n_bootstrap))
+				goto bad_arg;
+			break;
 		case 'c':
 			opt->eta_constrained = 1;
 			break;
@@ -527,6 +531,21 @@ int synchronize(options *opt, data *dat, model *mod)
 		return mmessage(ERROR_MSG, INVALID_USER_SETUP, "Maximum number of "
 			"clusters (%d) (set with command-line argument -k) cannot exceed "
 			"the number of individuals (%d)\n", opt->max_K, dat->I);
+	/* reference multiclust.c:869-877 */
+	if (opt->n_bootstrap && opt->max_K <= 1)
+		return mmessage(ERROR_MSG, INVALID_USER_SETUP, "When bootstrapping, maximum "
+			"K (%d) (set with command-line argument -k) must exceed 1.", opt->max_K);
+	if (opt->n_bootstrap) {
+		mod->null_K = opt->max_K - 1;
+		mod->alt_K = opt->max_K;
+		if (opt->n_gpus > 1 || opt->shard_fits || opt->fits_per_gpu > 1)
+			return mmessage(ERROR_MSG, INVALID_USER_SETUP, "The parametric "
+				"bootstrap (-b) runs on one device: drop --gpus / --shard-fits "
+				"/ --fits-per-gpu.\n");
+		if (opt->n_repeat != 1)
+			return mmessage(ERROR_MSG, INVALID_USER_SETUP, "The parametric "
+				"bootstrap (-b) cannot be timed (-w).\n");
+	}
 	if (!opt->n_seconds && !opt->n_init)
 		opt->n_init = 1;
 	if (opt->min_K > opt->max_K)
@@ -628,6 +647,10 @@ static int record_fit(options *opt, data *dat, model *mod, int i, int bootstrap,
 		mod->max_logL = mod->logL;
 		mod->aic = aic(mod);
 		mod->bic = bic(dat, mod);
+		/* save the estimates if this is H0 fitted to the observed data
+		 * (reference multiclust.c:562-581) */
+		if (!bootstrap && opt->n_bootstrap && mod->K == mod->null_K)
+			gpu_check(mod, mc_save_mle(mod->gpus[0], mod->pindex), "mc_save_mle");
 		if (!bootstrap && opt->write_files && (err = write_best(opt, dat, mod, ctx)))
 			return err;
 	}
@@ -792,7 +815,9 @@ int estimate_model(options *opt, data *dat, model *mod, int bootstrap)
 	int err;
 
 	mod->max_logL = -INFINITY;
-	mod->K = opt->min_K;
+	mod->max_logL_H0 = -INFINITY;
+	/* bootstrapping compares H0: K = null_K with Ha: K = alt_K */
+	mod->K = opt->n_bootstrap ? mod->null_K : opt->min_K;
 	dat->max_M = dat->M;
 	for (;;) {
 		if (dat->max_M < mod->K)
@@ -806,6 +831,8 @@ int estimate_model(options *opt, data *dat, model *mod, int bootstrap)
 		if (opt->n_repeat == 1 && opt->verbosity)
 			print_model_state(opt, dat, mod,
 				(int)(((double)clock() - start) / CLOCKS_PER_SEC), 1);
+		if (opt->n_bootstrap && mod->K == mod->null_K)
+			mod->max_logL_H0 = mod->max_logL;
 		if (min_aic > mod->aic) {
 			min_aic = mod->aic;
 			mod->aic_K = mod->K;
@@ -817,11 +844,49 @@ int estimate_model(options *opt, data *dat, model *mod, int bootstrap)
 		t0 = wall_now();
 		free_model_data(mod, opt);
 		g_t_plan += wall_now() - t0;
-		if (mod->K >= opt->max_K)
+		if (opt->n_bootstrap && mod->K == mod->null_K)
+			mod->K = mod->alt_K;
+		else if (!opt->n_bootstrap && mod->K < opt->max_K)
+			mod->K++;
+		else
 			break;
-		mod->K++;
+	}
+	/* the test statistic (reference multiclust.c:434-449) */
+	if (opt->n_bootstrap) {
+		const double diff = mod->max_logL - mod->max_logL_H0;
+
+		if (diff <= 0)
+			return mmessage(ERROR_MSG, INTERNAL_ERROR, "Null hypothesis likelihood "
+				"exceeds alternative hypothesis likelihood.  Try increasing "
+				"number of initializations (command-line option -n)\n");
+		if (!bootstrap)
+			mod->ts_obs = diff;
+		else
+			mod->ts_bs = diff;
 	}
 	return NO_ERROR;
+}
+
+/* reference multiclust.c:675-708 */
+static int run_bootstrap(options *opt, data *dat, model *mod)
+{
+	int ntime = 0, err = NO_ERROR;
+
+	for (int i = 0; i < opt->n_bootstrap; i++) {
+		fprintf(stdout, "Bootstrap dataset %d (of %d):", i + 1, opt->n_bootstrap);
+		if ((err = parametric_bootstrap(opt, dat, mod)))
+			break;
+		if ((err = estimate_model(opt, dat, mod, 1)))
+			break;
+		if (mod->ts_bs >= mod->ts_obs)
+			ntime++;
+		fprintf(stdout, " test statistics bs=%f obs=%f (%f)\n", mod->ts_bs, mod->ts_obs,
+			(double)ntime / (i + 1));
+	}
+	/* integer division, as in the reference (multiclust.c:703) */
+	mod->pvalue = ntime / opt->n_bootstrap;
+	const int err2 = cleanup_parametric_bootstrap(dat, mod);
+	return err ? err : err2;
 }
 
 /* reference multiclust.c:201-347, reduced to its effect: repeat the whole
@@ -900,6 +965,9 @@ int main(int argc, const char **argv)
 		err = estimate_model(opt, dat, mod, 0);
 	if (!err && opt->parallel)
 		printf("%f\n", mod->max_logL);
+	/* optionally run a bootstrap (reference multiclust.c:147-155) */
+	if (!err && opt->n_bootstrap && !(err = run_bootstrap(opt, dat, mod)))
+		fprintf(stdout, "p-value to reject H0: K=%d is %f\n", mod->null_K, mod->pvalue);
 	if (g_timing)
 		fprintf(stderr, "timing (s): read %.3f, upload %.3f, plan per K %.3f, other %.3f, "
 			"initialise %.3f, em %.3f (%d iterations), fetch+write %.3f, total %.3f\n",

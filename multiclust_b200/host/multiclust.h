@@ -85,6 +85,7 @@ struct _options {
 	int verbosity;			/* -v */
 	int compact;
 	double eta_lower_bound, p_lower_bound;
+	int n_bootstrap;		/* -b n: parametric bootstrap of H0: K-1 against Ha: K */
 	int n_repeat;			/* -w n */
 	int write_files;
 	int parallel;			/* -M */
@@ -118,6 +119,7 @@ struct _data {
 	int32_t *labels;	/* ascending allele labels, locus after locus */
 	int64_t *label_off;	/* [L+1] prefix sums of nreal */
 	uint8_t *codes;		/* [I][L][ploidy]: 0..nreal-1, 255 = missing */
+	uint8_t *codes_orig;	/* the observed data while `codes` is a bootstrap sample */
 	indiv *idv;
 	int *I_K;		/* partition of the individuals */
 	int numpops;
@@ -146,6 +148,9 @@ struct _model {
 	clock_t start;
 	double seconds_run;
 	int aic_K, bic_K;
+	/* parametric bootstrap (reference multiclust.h:340-352) */
+	int null_K, alt_K;
+	double max_logL_H0, ts_obs, ts_bs, pvalue;
 	/* device side */
 	mc_ctx *gpu;			/* = gpus[0] */
 	mc_ctx **gpus;			/* --gpus: one context per device, individuals
@@ -196,6 +201,9 @@ void start_device_contexts(options *opt);	/* CUDA start-up overlapped with the p
 
 /* ---- EM hot path (reference multiclust.h:371-388) ---- */
 int initialize_model(options *opt, data *dat, model *mod);
+/* bootstrap.c:31-66: one bootstrap sample in place of the data / the data back */
+int parametric_bootstrap(options *opt, data *dat, model *mod);
+int cleanup_parametric_bootstrap(data *dat, model *mod);
 void em(options *opt, data *dat, model *mod);
 int em_step(options *opt, data *dat, model *mod);
 int em_2_steps(model *mod, data *dat, options *opt);

@@ -197,3 +197,51 @@ def test_cli_shard_fits_matches_reference(tmp_path, name):
     assert sorted(os.listdir(out)) == sorted(os.listdir(out1))
     for fn in os.listdir(out):
         assert open(out / fn).read() == open(out1 / fn).read(), fn
+
+
+# ---- parametric bootstrap (-b) against the stock reference's stdout ----
+
+def _bootstrap_cases():
+    import glob
+    return sorted(os.path.basename(f)[len("bootstrap_"):-len(".json")]
+                  for f in glob.glob(os.path.join(ROOT, "tests", "golden", "bootstrap_*.json")))
+
+
+def _same_text(got, want):
+    """line by line; tokens that are numbers agree to 2e-6 (the reference prints %f), the
+    hh:mm:ss fields are not compared"""
+    import re
+    g, w = got.strip().splitlines(), want.strip().splitlines()
+    assert len(g) == len(w), (len(g), len(w), got[-600:])
+    for a, b in zip(g, w):
+        ta = re.sub(r"\d\d:\d\d:\d\d", "T", a).replace(",", " ").replace(";", " ")
+        tb = re.sub(r"\d\d:\d\d:\d\d", "T", b).replace(",", " ").replace(";", " ")
+        ta = ta.replace("(", " ").replace(")", " ").replace("=", " ").split()
+        tb = tb.replace("(", " ").replace(")", " ").replace("=", " ").split()
+        assert len(ta) == len(tb), (a, b)
+        for x, y in zip(ta, tb):
+            try:
+                fx, fy = float(x), float(y)
+            except ValueError:
+                assert x == y, (a, b)
+                continue
+            assert abs(fx - fy) <= 2e-6 + 1e-9 * abs(fy), (a, b)
+
+
+@pytest.mark.parametrize("name", _bootstrap_cases())
+def test_cli_bootstrap_matches_reference(tmp_path, name):
+    """-b n: the observed fits under H0 and Ha, every bootstrap sample drawn from the H0
+    estimates with the reference's rand() stream and loops, its two fits, the test statistics
+    and the p-value line -- the product binary's stdout against the stock reference's"""
+    import json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "bootstrap_%s.json" % name)))
+    gen = g["gen"]
+    subprocess.check_call([ensure_mc_gen(), "--I", str(gen["I"]), "--L", str(gen["L"]),
+                           "--K", str(gen["K"]), "--jmax", str(gen["jmax"]),
+                           "--miss", str(gen["miss"]), "--P", str(gen["P"]),
+                           "--stru", str(tmp_path / "d.stru")], stdout=subprocess.DEVNULL)
+    (tmp_path / "out").mkdir()
+    r = subprocess.run([CLI, "-f", "d.stru"] + g["cmd"].split() + ["-d", "out/"],
+                       cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    _same_text(r.stdout, g["stdout"])
