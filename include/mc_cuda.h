@@ -51,7 +51,7 @@ enum {
 	MC_ERR_UNSUPPORTED = 5	/* e.g. ploidy > 16 or > 254 alleles at a locus */
 };
 
-#define MC_ABI_VERSION 2
+#define MC_ABI_VERSION 3
 
 /* message of the last error raised through `ctx` (or creation, if ctx NULL) */
 const char *mc_last_error(const mc_ctx *ctx);

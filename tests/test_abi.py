@@ -25,7 +25,7 @@ def test_header_and_binding_agree():
 def test_library_exports_every_symbol(mclib):
     for name in declared_symbols():
         assert hasattr(mclib, name), name
-    assert mclib.mc_abi_version() == 2
+    assert mclib.mc_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_device(mclib):

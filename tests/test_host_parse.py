@@ -123,7 +123,7 @@ def test_distance_line_quirk_same_error(tmp_path):
 
 def test_unsupported_options_are_refused(tmp_path):
     stru = write(tmp_path / "e.stru", EDGE["r_format"][0])
-    for flag in (["-b", "10"], ["-x"], ["--simulate", "q", "p"], ["-I"]):
+    for flag in (["-x"], ["--simulate", "q", "p"], ["-I"], ["-u", "1"]):
         r = subprocess.run([CLI, "-f", stru] + flag, capture_output=True, text=True)
         assert r.returncode != 0
         assert "outside the EM path" in r.stderr
