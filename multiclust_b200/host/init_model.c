@@ -141,29 +141,35 @@ static int random_initialize_mixture(options *opt, data *dat, model *mod)
  * estimates.  As for the admixture initialiser the draws are made on the device
  * from the stream positions computed here (mc_bootstrap_data); the host
  * advances its generator by the 2 I L P (admixture) or I (1 + L P) (mixture)
- * draws of the sample.  The mixture initialiser reads the centres' genotype
+ * draws of the sample (split by rows of individuals over the devices).  The mixture initialiser reads the centres' genotype
  * rows on the host (dat->codes): they are fetched back from the device. */
 int parametric_bootstrap(options *opt, data *dat, model *mod)
 {
 	const long long per = (long long)dat->L * dat->ploidy;
-	const long long n = (long long)dat->I * (opt->admixture ? 2 * per : 1 + per);
-	const long long nb = n ? (n + RAND_BLOCK - 1) / RAND_BLOCK : 1;
+	const long long per_i = opt->admixture ? 2 * per : 1 + per;
 	uint32_t h[MCR_LAG];
-	uint32_t *hist = malloc(sizeof *hist * MCR_LAG * (size_t)nb);
 
-	if (!hist)
-		return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "generator states\n");
 	pthread_once(&g_jump_once, make_jump);
 	mcr_history(mod->rng, h);
-	for (long long b = 0; b < nb; b++) {
-		memcpy(hist + b * MCR_LAG, h, sizeof h);
-		if (b + 1 < nb)
-			mcr_apply(g_jump, h);
-		else
-			mcr_step_history(h, n - b * RAND_BLOCK);
+	/* with --gpus N device r draws the sample of its rows of individuals, i.e.
+	 * from draw row_first[r] * per_i of the sample on */
+	for (int r = 0; r < mod->n_gpus; r++) {
+		const long long n = (long long)(mod->row_first[r + 1] - mod->row_first[r]) * per_i;
+		const long long nb = n ? (n + RAND_BLOCK - 1) / RAND_BLOCK : 1;
+		uint32_t *hist = malloc(sizeof *hist * MCR_LAG * (size_t)nb);
+
+		if (!hist)
+			return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "generator states\n");
+		for (long long b = 0; b < nb; b++) {
+			memcpy(hist + b * MCR_LAG, h, sizeof h);
+			if (b + 1 < nb)
+				mcr_apply(g_jump, h);
+			else
+				mcr_step_history(h, n - b * RAND_BLOCK);
+		}
+		GPU(mc_bootstrap_data(mod->gpus[r], hist, nb, RAND_BLOCK));
+		free(hist);
 	}
-	GPU(mc_bootstrap_data(mod->gpus[0], hist, nb, RAND_BLOCK));
-	free(hist);
 	mcr_from_history(mod->rng, h);
 	if (!dat->codes_orig) {
 		dat->codes_orig = dat->codes;
@@ -174,7 +180,8 @@ int parametric_bootstrap(options *opt, data *dat, model *mod)
 			return mmessage(ERROR_MSG, MEMORY_ALLOCATION, "bootstrap data\n");
 		}
 	}
-	GPU(mc_get_codes(mod->gpus[0], dat->codes));
+	for (int r = 0; r < mod->n_gpus; r++)
+		GPU(mc_get_codes(mod->gpus[r], dat->codes + (size_t)mod->row_first[r] * (size_t)per));
 	return NO_ERROR;
 }
 
@@ -186,7 +193,8 @@ int cleanup_parametric_bootstrap(data *dat, model *mod)
 		dat->codes = dat->codes_orig;
 		dat->codes_orig = NULL;
 	}
-	GPU(mc_restore_data(mod->gpus[0]));
+	for (int r = 0; r < mod->n_gpus; r++)
+		GPU(mc_restore_data(mod->gpus[r]));
 	return NO_ERROR;
 }
 

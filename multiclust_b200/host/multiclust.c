@@ -538,10 +538,10 @@ int synchronize(options *opt, data *dat, model *mod)
 	if (opt->n_bootstrap) {
 		mod->null_K = opt->max_K - 1;
 		mod->alt_K = opt->max_K;
-		if (opt->n_gpus > 1 || opt->shard_fits || opt->fits_per_gpu > 1)
+		if (opt->shard_fits || opt->fits_per_gpu > 1)
 			return mmessage(ERROR_MSG, INVALID_USER_SETUP, "The parametric "
-				"bootstrap (-b) runs on one device: drop --gpus / --shard-fits "
-				"/ --fits-per-gpu.\n");
+				"bootstrap (-b) fits one model at a time: drop --shard-fits / "
+				"--fits-per-gpu (--gpus N shards the individuals).\n");
 		if (opt->n_repeat != 1)
 			return mmessage(ERROR_MSG, INVALID_USER_SETUP, "The parametric "
 				"bootstrap (-b) cannot be timed (-w).\n");
@@ -650,7 +650,8 @@ static int record_fit(options *opt, data *dat, model *mod, int i, int bootstrap,
 		/* save the estimates if this is H0 fitted to the observed data
 		 * (reference multiclust.c:562-581) */
 		if (!bootstrap && opt->n_bootstrap && mod->K == mod->null_K)
-			gpu_check(mod, mc_save_mle(mod->gpus[0], mod->pindex), "mc_save_mle");
+			for (int r = 0; r < mod->n_gpus; r++)
+				gpu_check(mod, mc_save_mle(mod->gpus[r], mod->pindex), "mc_save_mle");
 		if (!bootstrap && opt->write_files && (err = write_best(opt, dat, mod, ctx)))
 			return err;
 	}

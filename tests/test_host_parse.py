@@ -130,13 +130,13 @@ def test_unsupported_options_are_refused(tmp_path):
 
 
 def test_bootstrap_option_checks(tmp_path):
-    """-b n (reference multiclust.c:869-877, 1427-1434): K must exceed 1; one device only"""
+    """-b n (reference multiclust.c:869-877, 1427-1434): K must exceed 1; not with --shard-fits"""
     stru = write(tmp_path / "e.stru", EDGE["r_format"][0])
     r = subprocess.run([CLI, "-f", stru, "-R", "-k", "1", "-b", "2"], capture_output=True, text=True)
     assert r.returncode == 11 and "must exceed 1" in r.stderr     # INVALID_USER_SETUP
-    r = subprocess.run([CLI, "-f", stru, "-R", "-k", "2", "-b", "2", "--gpus", "2"],
-                       capture_output=True, text=True)
-    assert r.returncode == 11 and "runs on one device" in r.stderr
+    r = subprocess.run([CLI, "-f", stru, "-R", "-k", "2", "-b", "2", "--gpus", "2",
+                        "--shard-fits"], capture_output=True, text=True)
+    assert r.returncode == 11 and "one model at a time" in r.stderr
     r = subprocess.run([CLI, "-f", stru, "-R", "-k", "2", "-b", "-1"], capture_output=True, text=True)
     assert r.returncode == 10                                      # INVALID_CMD_ARGUMENT
 
