@@ -211,3 +211,38 @@ def test_config5_share_properties():
         assert np.array_equal(runs[1][2][1], runs[0][2][1])
     finally:
         ctx.close()
+
+
+def test_mixture_multiallelic_digit_against_gather_at_scale():
+    """the mixture model on 20k individuals x 10k loci with up to 20 alleles (T ~ 1.2e5 allele
+    columns, 5 % missing): the digit-sliced integer kernels on column pairs against the
+    two-pass gather kernel's mixture modes over three EM steps and a log-likelihood pass --
+    several chunks and blocks per CTA, 32-bit accumulators far from their bound -- plus the
+    usual size-independent properties"""
+    from multiclust_b200 import Context, SynthParams
+    I3, L3, K3 = 20000, 10000, 10
+    out = []
+    for kernel, family in ((0, 4), (2, 2)):
+        ctx = Context(0)
+        try:
+            ctx.set_option(ctx.OPT_KERNEL, kernel)
+            ctx.set_data_synth(I3, L3, SynthParams(seed=20261018, K=K3, jmax=20, miss_bp=500,
+                                                   ploidy=2))
+            lb = min(1e-8, 0.5 / I3 / 2)
+            ctx.alloc_model(K3, admixture=0, q=0, eta_lb=lb, p_lb=lb)
+            assert ctx.plan()["two_pass"] == family
+            eta0, p0, J, seg = _start(ctx, K3, False, 21)
+            ctx.set_params(0, eta0, p0)
+            pre = ctx.loglik(0)
+            lls = [ctx.em_step(0, 0) for _ in range(3)]
+            out.append((pre, lls, ctx.get_params(0), ctx.posterior(), ctx.loglik(0)))
+        finally:
+            ctx.close()
+    (pre, lls, (eta, p), v, post_ll), (pre2, lls2, (eta2, p2), v2, post_ll2) = out
+    assert np.all(np.isfinite(lls)) and abs(pre - lls[0]) <= 1e-12 * abs(pre)
+    assert all(b > a for a, b in zip(lls, lls[1:])) and post_ll > lls[-1]
+    assert abs(eta.sum() - 1.0) < 1e-12 and np.max(np.abs(v.sum(axis=1) - 1.0)) < 1e-12
+    assert abs(pre - pre2) <= 1e-12 * abs(pre) and abs(post_ll - post_ll2) <= 1e-12 * abs(pre)
+    assert np.max(np.abs(np.array(lls) - np.array(lls2)) / np.abs(lls)) < 1e-12
+    assert np.max(np.abs(eta - eta2)) < 1e-11 and np.max(np.abs(p - p2)) < 1e-11
+    assert np.max(np.abs(v - v2)) < 1e-9
