@@ -1807,31 +1807,37 @@ extern "C" int mc_bootstrap_data(mc_ctx *c, const uint32_t *hist, int64_t n_bloc
 		CK(MC_DEV_MALLOC(&c->d_nat, std::max<size_t>(bytes, 1)));
 	}
 	unsigned *d_hist = nullptr, *d_draws = nullptr;
-	CK(MC_DEV_MALLOC(&d_hist, sizeof(unsigned) * 31 * (size_t)n_blocks));
-	CK(cudaMemcpyAsync(d_hist, hist, sizeof(unsigned) * 31 * (size_t)n_blocks,
-		cudaMemcpyHostToDevice, c->stream));
-	/* slabs of whole individuals, at most 2^28 draws (1 GiB of raw draws) each */
-	const long long slab_i = std::max<long long>(1, (1LL << 28) / per_i);
-	const long long cap_blocks = (slab_i * per_i + block_draws - 1) / block_draws + 2;
-	CK(MC_DEV_MALLOC(&d_draws, sizeof(unsigned) * (size_t)std::min<long long>(cap_blocks,
-		n_blocks) * block_draws));
-	for (long long i0 = 0; i0 < c->I; i0 += slab_i) {
-		const long long i1 = std::min<long long>(c->I, i0 + slab_i);
-		const long long b0 = i0 * per_i / block_draws;
-		const long long b1 = (i1 * per_i - 1) / block_draws + 1;
-		const long long d0 = b0 * block_draws;
-		k_rand_raw<<<(unsigned)((b1 - b0 + 63) / 64), 64, 0, c->stream>>>(d_hist + 31 * b0,
-			b1 - b0, block_draws, n - d0, d_draws);
-		LAUNCH_CHECK("k_rand_raw");
-		k_bootstrap_codes<<<grid_for(c, (i1 - i0) * c->L, 128), 128, 0, c->stream>>>(d_draws,
-			d0, i0, i1, c->L, c->P, c->mle_K, c->T, c->d_off, c->d_J, c->d_mle_eta,
-			c->mle_per_indiv ? c->mle_K : 0, c->d_mle_p, c->mle_admixture, c->d_nat);
-		LAUNCH_CHECK("k_bootstrap_codes");
-	}
-	CK(cudaStreamSynchronize(c->stream));	/* hist is the caller's again */
+	/* the scratch is released on every path */
+	auto draw = [&]() -> int {
+		CK(MC_DEV_MALLOC(&d_hist, sizeof(unsigned) * 31 * (size_t)n_blocks));
+		CK(cudaMemcpyAsync(d_hist, hist, sizeof(unsigned) * 31 * (size_t)n_blocks,
+			cudaMemcpyHostToDevice, c->stream));
+		/* slabs of whole individuals, at most 2^28 draws (1 GiB of raw draws) each */
+		const long long slab_i = std::max<long long>(1, (1LL << 28) / per_i);
+		const long long cap_blocks = (slab_i * per_i + block_draws - 1) / block_draws + 2;
+		CK(MC_DEV_MALLOC(&d_draws, sizeof(unsigned) * (size_t)std::min<long long>(cap_blocks,
+			n_blocks) * block_draws));
+		for (long long i0 = 0; i0 < c->I; i0 += slab_i) {
+			const long long i1 = std::min<long long>(c->I, i0 + slab_i);
+			const long long b0 = i0 * per_i / block_draws;
+			const long long b1 = (i1 * per_i - 1) / block_draws + 1;
+			const long long d0 = b0 * block_draws;
+			k_rand_raw<<<(unsigned)((b1 - b0 + 63) / 64), 64, 0, c->stream>>>(
+				d_hist + 31 * b0, b1 - b0, block_draws, n - d0, d_draws);
+			LAUNCH_CHECK("k_rand_raw");
+			k_bootstrap_codes<<<grid_for(c, (i1 - i0) * c->L, 128), 128, 0, c->stream>>>(
+				d_draws, d0, i0, i1, c->L, c->P, c->mle_K, c->T, c->d_off, c->d_J,
+				c->d_mle_eta, c->mle_per_indiv ? c->mle_K : 0, c->d_mle_p,
+				c->mle_admixture, c->d_nat);
+			LAUNCH_CHECK("k_bootstrap_codes");
+		}
+		CK(cudaStreamSynchronize(c->stream));	/* hist is the caller's again */
+		return MC_OK;
+	};
+	const int rc = draw();
 	cudaFree(d_hist);
 	cudaFree(d_draws);
-	return MC_OK;
+	return rc;
 }
 
 extern "C" int mc_restore_data(mc_ctx *c)
