@@ -297,7 +297,7 @@ def have_ref():
 
 
 def run_ref(args, dump=None, mcb=None, steps=False, time_steps=0,
-            parse_only=False, timeout=600):
+            parse_only=False, timeout=600, bootstrap_seed=None):
     """Run the reference harness; `args` is the multiclust command line."""
     cmd = [REF_HARNESS]
     if dump:
@@ -310,5 +310,7 @@ def run_ref(args, dump=None, mcb=None, steps=False, time_steps=0,
         cmd += ["--time", str(time_steps)]
     if parse_only:
         cmd += ["--parse-only"]
+    if bootstrap_seed is not None:
+        cmd += ["--bootstrap-sample", str(bootstrap_seed)]
     cmd += ["--"] + [str(a) for a in args]
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)

@@ -238,6 +238,50 @@ static int load_mcb(const char *path, options *opt, data *dat)
 	return 0;
 }
 
+/* --bootstrap-sample seed (needs -b n on the multiclust command line so that the
+ * reference allocates mle_*): the fit's final parameters become the H0 estimates
+ * exactly as maximize_likelihood() copies them (multiclust.c:562-581), the
+ * generator is re-seeded so that the draws are a known stream, the reference's
+ * own parametric_bootstrap() (bootstrap.c:31-52) makes one sample, and the
+ * sample's allele counts are written as int32 [I][sum of uniquealleles] */
+static void dump_bootstrap_sample(const char *prefix, int seed, options *opt,
+	data *dat, model *mod)
+{
+	char name[4096];
+	FILE *fp;
+	int i, l, m, k;
+
+	if (!opt->n_bootstrap || !mod->mle_pKLM) {
+		fprintf(stderr, "ref_harness: --bootstrap-sample needs -b n\n");
+		exit(2);
+	}
+	for (k = 0; k < mod->K; k++)
+		for (l = 0; l < dat->L; l++)
+			for (m = 0; m < dat->uniquealleles[l]; m++)
+				mod->mle_pKLM[k][l][m] = mod->vpklm[mod->pindex][k][l][m];
+	if (!opt->admixture || opt->eta_constrained)
+		for (k = 0; k < mod->K; k++)
+			mod->mle_etak[k] = mod->vetak[mod->pindex][k];
+	else
+		for (i = 0; i < dat->I; i++)
+			for (k = 0; k < mod->K; k++)
+				mod->mle_etaik[i][k] = mod->vetaik[mod->pindex][i][k];
+	srand((unsigned)seed);
+	if (parametric_bootstrap(opt, dat, mod))
+		exit(3);
+	snprintf(name, sizeof name, "%s.bootstrap.bin", prefix);
+	if (!(fp = fopen(name, "wb")))
+		exit(4);
+	for (i = 0; i < dat->I; i++)
+		for (l = 0; l < dat->L; l++)
+			for (m = 0; m < dat->uniquealleles[l]; m++) {
+				const int32_t c = dat->ILM[i][l][m];
+				fwrite(&c, sizeof c, 1, fp);
+			}
+	fclose(fp);
+	cleanup_parametric_bootstrap(dat);
+}
+
 static double now_sec(void)
 {
 	struct timespec ts;
@@ -282,6 +326,7 @@ int main(int argc, const char **argv)
 {
 	const char *prefix = NULL, *mcb = NULL;
 	int steps = 0, ntime = 0, parse_only = 0, a = 1, err, i;
+	int boot_seed = -1;
 	options *opt = NULL;
 	data *dat = NULL;
 	model *mod = NULL;
@@ -298,6 +343,8 @@ int main(int argc, const char **argv)
 			steps = 1;
 		else if (!strcmp(argv[a], "--parse-only"))
 			parse_only = 1;
+		else if (!strcmp(argv[a], "--bootstrap-sample") && a + 1 < argc)
+			boot_seed = atoi(argv[++a]);
 		else {
 			fprintf(stderr, "ref_harness: bad option %s\n", argv[a]);
 			return 2;
@@ -388,6 +435,8 @@ int main(int argc, const char **argv)
 				snprintf(tag, sizeof tag, "K%d.init%d.final", g_K, i);
 				dump_state(prefix, tag, opt, dat, mod, mod->pindex);
 			}
+			if (boot_seed >= 0 && prefix)
+				dump_bootstrap_sample(prefix, boot_seed, opt, dat, mod);
 			if (mod->K == 1)
 				break;
 		}

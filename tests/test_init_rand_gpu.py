@@ -7,25 +7,9 @@ initialiser, which calls the C library's rand() like the reference
 import numpy as np
 import pytest
 
-from common import gen_data
+from common import gen_data, glibc_stream, bootstrap_numpy, codes_to_counts, ROOT
 
 pytestmark = pytest.mark.gpu
-
-
-def glibc_stream(seed, n):
-    """the 31 words in front of the first draw, then the n words of n draws"""
-    r = [0] * 31
-    r[0] = seed if seed else 1
-    for i in range(1, 31):
-        hi, lo = divmod(r[i - 1], 127773)
-        w = 16807 * lo - 2836 * hi
-        r[i] = w + 2147483647 if w < 0 else w
-    # srand() leaves front = 3, rear = 0: the first update is r[3] += r[0], so in
-    # linear terms the oldest word is r[3] -- the history is r rotated by 3
-    x = r[3:] + r[:3]
-    for _ in range(310 + n):
-        x.append((x[-31] + x[-3]) & 0xffffffff)
-    return np.array(x[310:], dtype=np.uint64)   # history (31) + n draws
 
 
 @pytest.mark.parametrize("shape,K,block", [
@@ -67,37 +51,6 @@ def test_device_draws_match_host_draws(tmp_path, shape, K, block):
 
 # ---- parametric bootstrap samples (mc_bootstrap_data, bootstrap.c:77-175) ----
 
-def _pick(w, r):
-    """bootstrap.c:96-105: first index whose running sum reaches r, else the last"""
-    j, acc = 0, 0.0
-    while j < len(w) and r > acc:
-        acc += w[j]
-        j += 1
-    return j - 1 if j else 0
-
-
-def _bootstrap_numpy(draws, I, L, P, K, J, off, eta, p, admixture, per_indiv):
-    """the reference's loops in the default parse mode: every copy is drawn"""
-    out = np.full((I, L, P), 255, dtype=np.uint8)
-    T = int(off[-1])
-    p = p.reshape(K, T)
-    d = 0
-    for i in range(I):
-        k = 0
-        if not admixture:
-            k = _pick(eta, draws[d] / 2147483647.0); d += 1
-        for l in range(L):
-            for a in range(P):
-                if admixture:
-                    row = eta.reshape(I, K)[i] if per_indiv else eta
-                    k = _pick(row, draws[d] / 2147483647.0); d += 1
-                r = draws[d] / 2147483647.0; d += 1
-                if J[l] > 0:
-                    out[i, l, a] = _pick(p[k, off[l]:off[l] + J[l]], r)
-    assert d == draws.size
-    return out
-
-
 @pytest.mark.parametrize("model", ["admixture", "pooled", "mixture"])
 @pytest.mark.parametrize("shape,K,block", [((23, 17, 2), 3, 496), ((9, 40, 4), 5, 31744),
                                            ((40, 7, 1), 2, 992)])
@@ -125,7 +78,7 @@ def test_bootstrap_sample_matches_reference_loops(tmp_path, model, shape, K, blo
     draws = (x[31:] >> np.uint64(1)).astype(np.float64)
     nb = max(1, -(-n // block))
     hist = np.stack([x[b * block: b * block + 31] for b in range(nb)]).astype(np.uint32)
-    want = _bootstrap_numpy(draws, I, L, P, K, J, off, eta.ravel(), p.ravel(), admixture,
+    want = bootstrap_numpy(draws, I, L, P, K, J, off, eta.ravel(), p.ravel(), admixture,
                             per_indiv)
 
     ctx = Context(0)
@@ -152,5 +105,42 @@ def test_bootstrap_sample_matches_reference_loops(tmp_path, model, shape, K, blo
             assert np.array_equal(ctx.get_codes(), want)
         ctx.restore_data()
         assert np.array_equal(ctx.get_codes(), d["codes"])
+    finally:
+        ctx.close()
+
+
+def _bootsamples():
+    import glob
+    import os
+    return sorted(os.path.basename(f)[len("bootsample_"):-len(".npz")]
+                  for f in glob.glob(os.path.join(ROOT, "tests", "golden", "bootsample_*.npz")))
+
+
+@pytest.mark.parametrize("name", _bootsamples())
+@pytest.mark.parametrize("block", [496, 31744])
+def test_bootstrap_sample_matches_reference_function(name, block):
+    """mc_bootstrap_data against a sample made by the reference's own parametric_bootstrap()
+    (bootstrap.c:31-175) from the same parameters and the same rand() stream: equal allele
+    counts for every individual and allele slot"""
+    import os
+    from multiclust_b200 import Context
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bootsample_%s.npz" % name))
+    J, codes, K = g["J"], g["codes"], int(g["K"])
+    I, L, P = codes.shape
+    admixture, per_indiv = int(g["admixture"]), int(g["per_indiv"])
+    n = I * (2 * L * P if admixture else 1 + L * P)
+    x = glibc_stream(int(g["seed"]), n)
+    nb = max(1, -(-n // block))
+    hist = np.stack([x[b * block: b * block + 31] for b in range(nb)]).astype(np.uint32)
+    ctx = Context(0)
+    try:
+        ctx.set_data(J, codes)
+        ctx.alloc_model(K, admixture=admixture, eta_constrained=int(admixture and not per_indiv),
+                        q=0)
+        ctx.set_params(0, g["eta"], g["p"])
+        ctx.save_mle(0)
+        ctx.bootstrap_data(hist, block)
+        got = codes_to_counts(ctx.get_codes(), J)
+        assert np.array_equal(got, g["counts"].astype(np.int64))
     finally:
         ctx.close()
