@@ -12,7 +12,9 @@ MC_GEN = os.path.join(ROOT, "multiclust_b200", "host", "mc_gen")
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    # (bootsample_*.npz are single bootstrap samples: tests/test_bootstrap_golden.py)
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+                  if not os.path.basename(p).startswith("bootsample_"))
 
 
 def load_golden(name):
