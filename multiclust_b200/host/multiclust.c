@@ -220,7 +220,7 @@ void fprint_usage(FILE *fp, const char *cmd)
 "  --projection  do not project onto the simplex\n"
 "output\n"
 "  -d <dir>      directory of the result files; -o <prefix> their name prefix\n"
-"  -v <level>    verbosity (4: one line per iteration); -w n <r>  timing repeats\n"
+"  -v <level>    verbosity (4: one line per iteration); -w n <r> [t <min>] [m <min>]  timed repeats\n"
 "  -M            print only the maximum log likelihood\n"
 "device\n"
 "  --device <d>  first CUDA device ordinal (default 0)\n"
@@ -474,6 +474,10 @@ int parse_options(options *opt, data *dat, int argc, const char **argv)
 				} else if (argv[i][0] == 't' || argv[i][0] == 'm') {
 					if (read_int_arg(argc, argv, ++i, 0, &tmp))
 						goto bad_arg;
+					if (argv[i - 1][0] == 't')
+						opt->repeat_seconds = 60 * tmp;
+					else
+						opt->max_repeat_seconds = 60 * tmp;
 				} else {
 					goto bad_arg;
 				}
@@ -890,23 +894,124 @@ static int run_bootstrap(options *opt, data *dat, model *mod)
 	return err ? err : err2;
 }
 
-/* reference multiclust.c:201-347, reduced to its effect: repeat the whole
- * estimation n times without writing files and report the mean time */
+/* reference multiclust.c:201-347: `-w n <r> [t <min>] [m <min>]` repeats the
+ * whole estimation (no result files) at least r times and until t minutes have
+ * passed, at most m minutes, prints one compact line per repetition and the
+ * statistics over the repetitions.  Features outside this program's flag set
+ * keep their neutral values in the output: no target log likelihood (-u: "NA",
+ * "u=(0.000000,0)", 0 "reach target") and no adjusted Rand index (-A: 0). */
 static int timed_model_estimation(options *opt, data *dat, model *mod)
 {
 	const clock_t start = clock();
-	int err, total = 0;
+	int enough_time = opt->repeat_seconds ? 0 : 1;
+	double esec = 0;
+	int max_iter = 0, max_init = 0, err;
+	double sum_init = 0, sum_init2 = 0, sum_iter = 0, sum_iter2 = 0;
+	double sum_aic_K = 0, sum_aic_K2 = 0, sum_bic_K = 0, sum_bic_K2 = 0;
+	double sum_ll = 0, sum_ll2 = 0;
+	const double sum_ar = 0, sum_ar2 = 0, arand = 0;
+	double max_ll = -INFINITY, min_aic = 0, min_bic = 0, max_ar = -1;
+	double first_ll = -INFINITY, max_ll_rand = 0;
+	int first_hit_index = 0, converged_repeats = 0, n_repeats = 0;
+	const int target_reached = 0;
 
-	for (int r = 0; r < opt->n_repeat; r++) {
+	while (n_repeats < opt->n_repeat || !enough_time) {
 		if ((err = estimate_model(opt, dat, mod, 0)))
 			return err;
-		total += mod->n_total_iter;
+		if (mod->n_init > max_init)
+			max_init = mod->n_init;
+		if (mod->n_max_iter > max_iter)
+			max_iter = mod->n_max_iter;
+		if (mod->max_logL > max_ll) {
+			max_ll = mod->max_logL;
+			min_aic = mod->aic;
+			min_bic = mod->bic;
+			max_ll_rand = arand;
+			if (!converged(opt, mod, first_ll)) {
+				first_ll = mod->max_logL;
+				first_hit_index = n_repeats;
+			}
+		}
+		if (arand > max_ar)
+			max_ar = arand;
+		sum_init += mod->n_init;
+		sum_init2 += mod->n_init * mod->n_init;
+		sum_iter += mod->n_total_iter;
+		sum_iter2 += mod->n_total_iter * mod->n_total_iter;
+		sum_aic_K += mod->aic_K;
+		sum_aic_K2 += mod->aic_K * mod->aic_K;
+		sum_bic_K += mod->bic_K;
+		sum_bic_K2 += mod->bic_K * mod->bic_K;
+		sum_ll += mod->max_logL;
+		sum_ll2 += mod->max_logL * mod->max_logL;
+		n_repeats++;
+		if (mod->ever_converged)
+			converged_repeats++;
+
+		esec = ((double)clock() - start) / CLOCKS_PER_SEC;
+		if (opt->verbosity > SILENT) {
+			print_model_state(opt, dat, mod,
+				(int)(((double)clock() - start) / CLOCKS_PER_SEC), 0);
+			fprintf(stdout, " %f %f %d %d", esec, esec / n_repeats,
+				target_reached, converged_repeats);
+			fprintf(stdout, " %f", max_ll);
+			fprintf(stdout, " NA");
+			fprintf(stdout, " %d %d %d %d", 0, n_repeats, opt->n_repeat,
+				opt->repeat_seconds);
+			fprintf(stdout, "\n");
+		}
+		if (!enough_time || opt->max_repeat_seconds) {
+			if (!enough_time && esec > opt->repeat_seconds)
+				enough_time = 1;
+			if (opt->max_repeat_seconds && esec > opt->max_repeat_seconds)
+				break;
+		}
 	}
-	print_model_state(opt, dat, mod,
-		(int)(((double)clock() - start) / CLOCKS_PER_SEC), 0);
-	fprintf(stdout, " %f %f\n",
-		((double)clock() - start) / CLOCKS_PER_SEC / opt->n_repeat,
-		(double)total / opt->n_repeat);
+
+	if (opt->verbosity >= SILENT) {
+		fprintf(stdout, "Data, Method, Model: %s, %s, %s\n", opt->filename,
+			opt->accel_abbreviation,
+			opt->admixture && opt->eta_constrained
+			? "admix constrained" : opt->admixture ? "admix" : "mix");
+		fprintf(stdout, "Run: %e %e %e %e n=%d i=%d u=(%f,%d) w=(%d,%d)\n",
+			opt->abs_error, opt->rel_error, opt->eta_lower_bound,
+			opt->p_lower_bound, opt->n_init, opt->n_init_iter, 0.0, 0,
+			opt->n_repeat, opt->repeat_seconds);
+		fprintf(stdout, "Number of repetitions: %d of %d requested, %d converged, "
+			"%d reach target\n", n_repeats, opt->n_repeat, converged_repeats,
+			target_reached);
+		fprintf(stdout, "Average time: %fs (total: %fs; target: %d)\n",
+			esec / n_repeats, esec, opt->repeat_seconds);
+		fprintf(stdout, "Average log likelihood: %f (+/- %f)\n", sum_ll / n_repeats,
+			sqrt((sum_ll2 - sum_ll * sum_ll / n_repeats) / (n_repeats - 1)));
+		fprintf(stdout, "Maximum log likelihood: %f first hit at run %d (AIC %f; "
+			"BIC %f; RAND: %f)\n", max_ll, first_hit_index, min_aic, min_bic,
+			max_ll_rand);
+		fprintf(stdout, "Adjusted RAND: avg = %f +/- %f; max = %f\n",
+			sum_ar / n_repeats,
+			sqrt((sum_ar2 - sum_ar * sum_ar / n_repeats) / (n_repeats - 1)), max_ar);
+		if (opt->max_K != opt->min_K) {
+			fprintf(stdout, "Average K (AIC): %f (+/- %f)\n", sum_aic_K / n_repeats,
+				sqrt((sum_aic_K2 - sum_aic_K * sum_aic_K / n_repeats)
+					/ (n_repeats - 1)));
+			fprintf(stdout, "Average K (BIC): %f (+/- %f)\n", sum_bic_K / n_repeats,
+				sqrt((sum_bic_K2 - sum_bic_K * sum_bic_K / n_repeats)
+					/ (n_repeats - 1)));
+		} else {
+			fprintf(stdout, "Total initializations, iterations: %d, %d\n",
+				(int)sum_init, (int)sum_iter);
+			fprintf(stdout, "Average initializations: %f (+/- %f) [%e, %e]\n",
+				sum_init / n_repeats,
+				sqrt((sum_init2 - sum_init * sum_init / n_repeats)
+					/ (n_repeats - 1)), sum_init2, sum_init);
+			fprintf(stdout, "Average iterations: %f (+/- %f) [%e %e]\n",
+				sum_iter / sum_init,
+				sqrt((sum_iter2 - sum_iter * sum_iter / sum_init)
+					/ (sum_init - 1)), sum_iter2, sum_iter);
+			fprintf(stdout, "Maximum initializations: %d\n", max_init);
+			fprintf(stdout, "Maximum iterations: %d\n", max_iter);
+		}
+	}
 	return NO_ERROR;
 }
 

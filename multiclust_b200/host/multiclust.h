@@ -87,6 +87,8 @@ struct _options {
 	double eta_lower_bound, p_lower_bound;
 	int n_bootstrap;		/* -b n: parametric bootstrap of H0: K-1 against Ha: K */
 	int n_repeat;			/* -w n */
+	int repeat_seconds;		/* -w t <minutes>: keep repeating until then */
+	int max_repeat_seconds;		/* -w m <minutes>: stop repeating after */
 	int write_files;
 	int parallel;			/* -M */
 	/* new in this program */
