@@ -48,7 +48,11 @@ the reference's stop() needs it (em_alg.c:195-207).
   other_configs  the other BASELINE configurations, ms per step: C1 (the
              reference's own CPU-runnable case), C2 (mixture, biallelic, SQUAREM),
              one GPU's share of C5 -- and with --gpus 8 the WHOLE C5 (I=1M
-             tetraploid, K=8, QN q=2) sharded over the 8 ranks.
+             tetraploid, K=8, QN q=2) sharded over the 8 ranks -- and C4
+             (K = 2..12 x 64 initialisations x 100 iterations = 704 whole fits)
+             through the drop-in command line, the fits dealt to the N devices
+             (`--gpus N --shard-fits --fits-per-gpu 4`, no collective) while the
+             ranks' own devices are idle: seconds for the fits phase.
 
 N > 1 (torchrun, one rank per GPU): individuals are sharded.  `value` is weak
 scaling (every rank holds I individuals, global I = N * 100k; value = N *
@@ -296,6 +300,8 @@ class Env:
             import torch.distributed as dist
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             self.dist = dist
+            # a wait that keeps the devices idle (an NCCL barrier spins on the GPU)
+            self.cpu_group = dist.new_group(backend="gloo")
         # one torch stream carries the context's kernels, the NCCL collectives
         # and the timing events (the legacy default stream has handle 0, which
         # mc_set_stream reads as "use the context's own stream")
@@ -306,6 +312,11 @@ class Env:
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize()
+
+    def cpu_barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.cpu_group)
 
     def max_over_ranks(self, x):
         if self.world == 1:
@@ -529,7 +540,48 @@ def other_configs(env, a):
             "ms_per_em_step": em, "ms_per_accelerated_cycle": cyc, "accel": 5,
             "accelerated_steps_accepted": int(drv.accel_step), "logL": drv.logL}
         ctx.close()
+    # configuration 4 through the command line, on every device of the job; the ranks
+    # wait on the CPU so that their devices are idle meanwhile
+    env.cpu_barrier()
+    if env.rank == 0:
+        try:
+            res["C4 multi-start: admixture I=2000 L=1000, K=2..12 x -n 64, -C 100, "
+                "fits dealt to %d device(s)" % env.world] = c4_shard_fits(env.world)
+        except Exception as exc:        # reported, never required
+            res["C4 multi-start"] = {"error": repr(exc)[:300]}
+    env.cpu_barrier()
     return res
+
+
+def c4_shard_fits(n_gpus, n_init=64, k_min=2, k_max=12, iters=100, per_gpu=4):
+    """BASELINE config 4 (multiclust.c:471-660 dealt to devices, host/shard_fits.c): the
+    product binary on mc_gen data with whole fits dealt to `n_gpus` devices, `per_gpu` fits in
+    flight on each; the binary's own --timing line gives the fits phase"""
+    import re
+    host = os.path.join(ROOT, "multiclust_b200", "host")
+    tmp = tempfile.mkdtemp(prefix="c4_")
+    stru = os.path.join(tmp, "d.stru")
+    subprocess.check_call([os.path.join(host, "mc_gen"), "--I", "2000", "--L", "1000", "--K", "4",
+                           "--jmax", "6", "--miss", "200", "--P", "2", "--stru", stru],
+                          stdout=subprocess.DEVNULL)
+    cmd = [os.path.join(host, "multiclust"), "-f", stru, "-a", "-1", str(k_min), "-2", str(k_max),
+           "-n", str(n_init), "-C", str(iters), "-E", "1e-30", "--timing", "-d", tmp + "/",
+           "--gpus", str(n_gpus), "--shard-fits", "--fits-per-gpu", str(per_gpu)]
+    t0 = time.perf_counter()
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    wall = time.perf_counter() - t0
+    fits = r.stdout.count("initialization =")
+    m = re.search(r"(\d+) workers on (\d+) devices.*fits phase ([0-9.]+)", r.stderr)
+    if r.returncode != 0 or not m or fits != (k_max - k_min + 1) * n_init:
+        raise RuntimeError("multiclust --shard-fits: rc %d, %d fits: %s"
+                           % (r.returncode, fits, r.stderr[-200:]))
+    phase = float(m.group(3))
+    return {"fits": fits, "em_iterations_per_fit": iters, "workers": int(m.group(1)),
+            "devices": int(m.group(2)), "fits_phase_s": phase,
+            "fits_per_s": fits / phase if phase > 0 else None,
+            "us_per_em_iteration": phase / (fits * (iters + 1)) * 1e6,
+            "wall_s_with_cuda_startup": round(wall, 3),
+            "command": "multiclust " + " ".join(c for c in cmd[3:] if c not in ("-d", tmp + "/"))}
 
 
 def ncu_metrics(a):
