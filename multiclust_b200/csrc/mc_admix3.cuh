@@ -147,6 +147,28 @@ static __device__ __noinline__ double a3_slow_ll(double t0, double t1)
 	return log(t0) + log(t1);
 }
 
+/* Pass-2 lanes.  A column owns consecutive LOGICAL lanes; logical lane ln runs on thread
+ * (ln % A3_NQ) * 8 + ln / A3_NQ, i.e. in quarter warp ln % A3_NQ: consecutive logical
+ * lanes sit in different quarter warps, so the 8 lanes of a quarter warp read the lists
+ * of 8 different columns (k3_build_csc, mc_admix3_build.cuh) */
+#define A3_NQ (A3_THREADS / 8)
+__host__ __device__ __forceinline__ int a3_lane_thread(int ln)
+{
+	return (ln % A3_NQ) * 8 + ln / A3_NQ;
+}
+__host__ __device__ __forceinline__ int a3_thread_lane(int t)
+{
+	return (t & 7) * A3_NQ + (t >> 3);
+}
+/* row of logical lane ln in the partial-sum scratch: consecutive lanes in consecutive
+ * rows (the fold walks a column's lanes), one row skipped per A3_NQ lanes so that the 8
+ * lanes of a quarter warp (ln = qw, A3_NQ + qw, ...) store into 8 different bank groups */
+__host__ __device__ __forceinline__ int a3_part_row(int ln)
+{
+	return ln + ln / A3_NQ;
+}
+#define A3_PART_ROWS (A3_THREADS + 8)
+
 /* 16-byte pieces per eta row in shared memory: an odd number, so that the rows
  * of 8 individuals with different i % 8 start in 8 different bank groups */
 template <int KP> struct A3Row { static constexpr int NP = KP | 1; };
@@ -164,7 +186,7 @@ static inline size_t a3_smem_bytes(int KP, int mode, int ncolmax, int cap)
 	if (p1)
 		d += (size_t)KR * A3_PR;
 	if (p2)
-		d += (size_t)A3_IT * NP * 2 + (size_t)A3_THREADS * KR;
+		d += (size_t)A3_IT * NP * 2 + (size_t)A3_PART_ROWS * KR;
 	if (mode == A3_ADMIX_EM)
 		d += (size_t)A3_NC * A3_WP;
 	return d * sizeof(double)
@@ -236,14 +258,15 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 	constexpr int PR = A3_PR;
 	extern __shared__ __align__(128) double smem3d[];
 	const int t = threadIdx.x, lane = t & 31;
+	const int tl = a3_thread_lane(t);	/* logical pass-2 lane of this thread */
 	const int csw = ((a.ncolmax + 1 + 7) / 8) * 8;	/* colstart row, 16-byte multiple */
 	const int cstn = 3 * csw + A3_THREADS / 2;	/* shorts of one tile's column tables */
 
 	/* eta rows first: the xor rotation needs them aligned to their size */
 	double *eta_s = smem3d;						/* [A3_IT][2 NP] */
 	double *w_s = eta_s + (P2 ? (size_t)A3_IT * NP * 2 : 0);	/* [A3_NC][A3_WP] */
-	double *part_s = w_s + (HAS_W ? (size_t)A3_NC * A3_WP : 0);	/* [A3_THREADS][KR] */
-	double *p_s = part_s + (P2 ? (size_t)A3_THREADS * KR : 0);	/* [KR][PR] */
+	double *part_s = w_s + (HAS_W ? (size_t)A3_NC * A3_WP : 0);	/* [A3_PART_ROWS][KR] */
+	double *p_s = part_s + (P2 ? (size_t)A3_PART_ROWS * KR : 0);	/* [KR][PR] */
 	double *red = p_s + (P1 ? (size_t)KR * PR : 0);		/* [16] */
 	unsigned short *csc_s = reinterpret_cast<unsigned short *>(red + 16);	/* [cap] */
 	unsigned short *cst2_s = csc_s + (P2 ? a.cap : 0);		/* [2][cstn]: first entry, first
@@ -496,15 +519,18 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 #pragma unroll
 				for (int k = 0; k < KR; k++)
 					g[k] = 0.0;
-				/* the lane's column, from the tile's lane table */
-				const int col = (cst_s[3 * csw + (t >> 1)] >> ((t & 1) * 8)) & 0xff;
+				/* the lane's column, from the tile's lane table.  A column's lanes
+				 * are consecutive LOGICAL lanes; thread t is logical lane tl, so the
+				 * 8 lanes of a quarter warp belong to 8 different columns (the list
+				 * builder schedules their entries into different bank groups) */
+				const int col = (cst_s[3 * csw + (tl >> 1)] >> ((tl & 1) * 8)) & 0xff;
 				if (col != 255) {
 					const int lane0c = cst_s[csw + col], lane1c = cst_s[csw + col + 1];
 					const int S2 = (lane1c - lane0c) * 2;	/* list stride, bytes */
 					const unsigned wb = w_sa + (unsigned)(cst_s[2 * csw + col] >> 8)
 						* (PP * A3_WP * 8);
 					const unsigned xe = csc_sa + 2u * cst_s[col + 1];
-					unsigned x = csc_sa + 2u * (cst_s[col] + (t - lane0c));
+					unsigned x = csc_sa + 2u * (cst_s[col] + (tl - lane0c));
 					/* ids run two trips ahead and weights one, and nothing is
 					 * computed from a load in the trip that issues it: the warp
 					 * issues in order, so an operation on a fresh load would hold
@@ -543,7 +569,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 				/* the lane's partial sums */
 #pragma unroll
 				for (int pc = 0; pc < KP; pc++)
-					*reinterpret_cast<double2 *>(part_s + (size_t)t * KR + 2 * pc)
+					*reinterpret_cast<double2 *>(part_s + (size_t)a3_part_row(tl) * KR + 2 * pc)
 						= make_double2(g[2 * pc], g[2 * pc + 1]);
 				a3_cp_async_wait<0>();	/* the next tile's p rows */
 				__syncthreads();
@@ -566,23 +592,25 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					double *dst = G_u + (size_t)(tro + rb[info >> 8] + (int)(info & 0xff)) * KR
 						+ 2 * pc;
 					const double2 old = a3_ldcg2(dst, pol_keep);
-					const double2 *src = reinterpret_cast<const double2 *>(
-						part_s + (size_t)lane0 * KR + 2 * pc);
+					const double2 *src = reinterpret_cast<const double2 *>(part_s + 2 * pc);
+					auto part = [&](int sx) {
+						return src[(size_t)a3_part_row(lane0 + sx) * KP];
+					};
 					/* four independent partial sums keep four loads in flight */
 					double2 acc = make_double2(0.0, 0.0), a1 = acc, a2 = acc, a3 = acc;
 					int sx = 0;
 					for (; sx + 3 < S; sx += 4) {
-						const double2 v0 = src[(size_t)sx * KP];
-						const double2 v1 = src[(size_t)(sx + 1) * KP];
-						const double2 v2 = src[(size_t)(sx + 2) * KP];
-						const double2 v3 = src[(size_t)(sx + 3) * KP];
+						const double2 v0 = part(sx);
+						const double2 v1 = part(sx + 1);
+						const double2 v2 = part(sx + 2);
+						const double2 v3 = part(sx + 3);
 						acc.x += v0.x; acc.y += v0.y;
 						a1.x += v1.x; a1.y += v1.y;
 						a2.x += v2.x; a2.y += v2.y;
 						a3.x += v3.x; a3.y += v3.y;
 					}
 					for (; sx < S; sx++) {
-						const double2 v0 = src[(size_t)sx * KP];
+						const double2 v0 = part(sx);
 						acc.x += v0.x;
 						acc.y += v0.y;
 					}

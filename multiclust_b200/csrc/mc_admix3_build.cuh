@@ -51,29 +51,54 @@ __global__ void k3_build_codes(const unsigned char *nat, unsigned char *codes,
 	}
 }
 
+/* shared memory of k3_build_csc */
+static inline size_t a3_build_smem_bytes(int ncolmax, int cap)
+{
+	return (size_t)A3_IT * A3_NC + sizeof(int) * (2 * (size_t)ncolmax + 2)
+		+ sizeof(unsigned) * (size_t)ncolmax * (A3_IT / 32)
+		+ sizeof(unsigned short) * (size_t)cap
+		+ (size_t)A3_THREADS * (8 + 8 + 1 + 1);
+}
+
 /* entry lists of one (itile, ltile): for every real allele column in `colinfo`
  * order, one entry per (individual, allele) carrying it:
  *     i | first copy << 9 | (count - 1) << 12.
- * The column owns S consecutive pass-2 lanes, S chosen per tile from the tile's
- * own counts so that no lane gets more than q = ceil(entries / A3_THREADS) (+1)
- * entries; lane seg reads the entries at start + s * S + seg, s = 0, 1, ...  The eta rows
- * of 8 individuals with different i % 8 lie in different bank groups, so an
- * entry is dealt to a slot whose (lane + step) % 8 equals i % 8 wherever such a
- * slot is still free; the rest fill the remaining positions in ascending order
- * of i. */
+ * The column owns S consecutive logical pass-2 lanes, S chosen per tile from the
+ * tile's own counts so that no lane gets more than q = ceil(entries / A3_THREADS) (+1)
+ * entries; lane seg reads the entries at start + s * S + seg, s = 0, 1, ...
+ *
+ * The eta rows of 8 individuals with different i % 8 lie in different bank groups, so a
+ * quarter warp's LDS.128 costs as many wavefronts as the most frequent residue among
+ * its 8 entries.  Which of its entries a lane reads in which step is free, and the 8
+ * lanes of a quarter warp belong to 8 different columns (a3_thread_lane), so the lists
+ * are scheduled in two stages:
+ *   deal      a column's carriers, residue class by residue class, go round its S
+ *             lanes: every lane gets an even share of every class;
+ *   schedule  per quarter warp and step, the active lanes -- the one with the fewest
+ *             classes left first -- take the best-stocked class nobody in the step has
+ *             taken; a lane that finds none asks a holder of one of its classes to
+ *             move to another free class (one augmenting step); if that fails too it
+ *             takes its best-stocked class and the step costs a wavefront more.
+ * Simulated on config-3 tiles: 1.15 wavefronts per quarter-warp step against 1.50 for
+ * dealing entries to fixed (lane + step) % 8 slots (a full augmenting-path matching
+ * gives the same 1.15; balancing the class totals of the quarter warps while dealing
+ * 1.08, but that couples the columns and runs on one thread). */
 __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 	int ncolmax, int cap, const int *lt_ncol, const unsigned short *colinfo,
 	unsigned short *csc, unsigned short *colstart)
 {
-	extern __shared__ unsigned char sm3[];
+	extern __shared__ __align__(16) unsigned char sm3[];
 	unsigned char *cd = sm3;				/* [A3_IT][A3_NC] */
 	int *cnt = reinterpret_cast<int *>(sm3 + (size_t)A3_IT * A3_NC);	/* [ncolmax] */
-	int *lane_first = cnt + ncolmax;				/* [ncolmax + 1] */
-	/* carriers of every column as a bit mask over the tile's individuals: the
-	 * sweeps below then visit carriers only (a sixth of the individuals at
-	 * config 3) instead of testing every individual three times */
+	int *lane_first = cnt + ncolmax;				/* [ncolmax + 2] (keeps 8-byte alignment) */
+	/* carriers of every column as a bit mask over the tile's individuals */
 	constexpr int MW = A3_IT / 32;
-	unsigned *mask = reinterpret_cast<unsigned *>(lane_first + ncolmax + 1);	/* [ncolmax][MW] */
+	unsigned *mask = reinterpret_cast<unsigned *>(lane_first + ncolmax + 2);	/* [ncolmax][MW] */
+	unsigned short *tmp = reinterpret_cast<unsigned short *>(mask + (size_t)ncolmax * MW);	/* [cap] dealt lists */
+	unsigned char *lcnt = reinterpret_cast<unsigned char *>(tmp + cap);	/* [lanes][8] entries left per class */
+	unsigned char *lptr = lcnt + A3_THREADS * 8;		/* [lanes][8] next list step of the class */
+	unsigned char *lcol = lptr + A3_THREADS * 8;		/* [lanes] column */
+	unsigned char *lfill = lcol + A3_THREADS;		/* [lanes] entries of the lane */
 	const int lt = blockIdx.x % n_ltiles;
 	const int ncol = lt_ncol[lt];
 	const unsigned short *ci = colinfo + (size_t)lt * ncolmax;
@@ -85,6 +110,12 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 
 	for (int x = threadIdx.x; x < A3_IT * (A3_NC / 8); x += blockDim.x)
 		reinterpret_cast<uint2 *>(cd)[x] = src[x];
+	for (int x = threadIdx.x; x < A3_THREADS * 8; x += blockDim.x)
+		lcnt[x] = 0;
+	for (int x = threadIdx.x; x < A3_THREADS; x += blockDim.x) {
+		lcol[x] = 255;
+		lfill[x] = 0;
+	}
 	__syncthreads();
 	for (int x = threadIdx.x; x < ncol * MW; x += blockDim.x) {
 		const int c = x / MW, w = x - c * MW;
@@ -141,87 +172,161 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 			cs[2 * csw + c] = c < ncol ? ci[c] : 0;
 	}
 	__syncthreads();
-	/* the column of every pass-2 lane, two lanes per 16-bit word */
-	for (int x = threadIdx.x; x < A3_THREADS / 2; x += blockDim.x) {
-		unsigned v = 0;
-		for (int h = 0; h < 2; h++) {
-			const int ln = 2 * x + h;
-			int col = 255;
-			if (ln < lane_first[ncol]) {
-				int lo = 0, hi = ncol - 1;	/* last column with lane_first <= ln */
-				while (lo < hi) {
-					const int mid = (lo + hi + 1) >> 1;
-					if (lane_first[mid] <= ln)
-						lo = mid;
-					else
-						hi = mid - 1;
-				}
-				col = lo;
-				/* columns without entries own no lane: step to the owner */
-				while (lane_first[col + 1] <= ln)
-					col++;
-			}
-			v |= (unsigned)col << (8 * h);
-		}
-		cs[3 * csw + x] = (unsigned short)v;
-	}
+	/* the column of every logical pass-2 lane */
+	for (int c = threadIdx.x; c < ncol; c += blockDim.x)
+		for (int ln = lane_first[c]; ln < lane_first[c + 1]; ln++)
+			lcol[ln] = (unsigned char)c;
+	__syncthreads();
+	for (int x = threadIdx.x; x < A3_THREADS / 2; x += blockDim.x)
+		cs[3 * csw + x] = (unsigned short)(lcol[2 * x] | (unsigned)lcol[2 * x + 1] << 8);
+
+	/* ---- deal: one thread per column ---- */
 	for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
-		const int ll = ci[c] >> 8, j = ci[c] & 0xff;
-		const int n = cnt[c], start = cs[c];
-		const int lane0 = lane_first[c], S = lane_first[c + 1] - lane0;
+		const int n = cnt[c];
 		if (!n)
 			continue;
+		const int ll = ci[c] >> 8, j = ci[c] & 0xff;
+		const int start = cs[c], lane0 = lane_first[c], S = lane_first[c + 1] - lane0;
 		const int q = n / S, rem = n - q * S;	/* lane seg holds q + (seg < rem) entries */
-		for (int x = 0; x < n; x++)
-			out[start + x] = 0xffff;
-		/* slot (seg, s) belongs to residue class (lane0 + seg + s) % 8: in step s
-		 * the 8 lanes of a quarter warp then want 8 different residues, and every
-		 * lane meets every residue once in 8 steps, so a column finds room for
-		 * all residues however few lanes it owns.  Two sweeps over the carriers:
-		 * the first places the entries that find a slot of their class, the
-		 * second the others */
-		for (int sweep = 0; sweep < 2; sweep++) {
-			int cs_s[8], cs_seg[8];		/* next free slot of every class */
-			for (int r = 0; r < 8; r++) {
-				cs_s[r] = 0;
-				cs_seg[r] = (r - lane0) & 7;
+		for (int seg = 0; seg < S; seg++)
+			lfill[lane0 + seg] = (unsigned char)(q + (seg < rem));
+		int k = 0, seg = 0;
+		for (int r = 0; r < 8; r++)
+		for (int w = 0; w < MW; w++)
+		for (unsigned mm = mask[c * MW + w] & (0x01010101u << r); mm; mm &= mm - 1) {
+			const int ii = w * 32 + __ffs((int)mm) - 1;
+			int cn = 0, first = 0;
+			for (int a = PP - 1; a >= 0; a--)
+				if (cd[ii * A3_NC + ll * PP + a] == j) {
+					cn++;
+					first = a;
+				}
+			/* the k-th carrier in class order is entry k / S of lane k % S */
+			tmp[start + k++] = (unsigned short)(ii | first << 9 | (cn - 1) << 12);
+			lcnt[(lane0 + seg) * 8 + r]++;
+			if (++seg == S)
+				seg = 0;
+		}
+	}
+	__syncthreads();
+	/* a lane's dealt list is sorted by class: where each class starts */
+	for (int ln = threadIdx.x; ln < A3_THREADS; ln += blockDim.x) {
+		int acc = 0;
+		for (int r = 0; r < 8; r++) {
+			lptr[ln * 8 + r] = (unsigned char)acc;
+			acc += lcnt[ln * 8 + r];
+		}
+	}
+	__syncthreads();
+
+	/* ---- schedule: one thread per quarter warp; fixed-length loops, so the threads of
+	 * the warp stay together ---- */
+	for (int qw = threadIdx.x; qw < A3_NQ; qw += blockDim.x) {
+		int lstart[8], lS[8], lseg[8], lquota[8];
+		int maxq = 0;
+#pragma unroll
+		for (int b = 0; b < 8; b++) {
+			const int ln = b * A3_NQ + qw;
+			const int c = lcol[ln];
+			lstart[b] = lS[b] = lseg[b] = lquota[b] = 0;
+			if (c == 255)
+				continue;
+			lstart[b] = cs[c];
+			lS[b] = lane_first[c + 1] - lane_first[c];
+			lseg[b] = ln - lane_first[c];
+			lquota[b] = lfill[ln];
+			maxq = max(maxq, lquota[b]);
+		}
+		/* the 8 per-class counts of lane slot b, one byte each */
+		auto counts = [&](int b) {
+			return *reinterpret_cast<const unsigned long long *>(lcnt + (b * A3_NQ + qw) * 8);
+		};
+		auto classes = [](unsigned long long c8) {	/* bit r: class r has entries */
+			unsigned m = 0;
+#pragma unroll
+			for (int r = 0; r < 8; r++)
+				m |= (unsigned)((c8 >> (8 * r) & 0xff) != 0) << r;
+			return m;
+		};
+		auto best = [](unsigned long long c8, unsigned among) {	/* best-stocked class */
+			int r = 0, bc = -1;
+#pragma unroll
+			for (int rr = 0; rr < 8; rr++) {
+				const int cc = (int)(c8 >> (8 * rr) & 0xff);
+				if ((among >> rr & 1) && cc > bc) {
+					bc = cc;
+					r = rr;
+				}
 			}
-			int fill = 0;
-			for (int w = 0; w < MW; w++)
-			for (unsigned mm = mask[c * MW + w]; mm; mm &= mm - 1) {
-				const int ii = w * 32 + __ffs((int)mm) - 1;
-				int cn = 0, first = 0;
-				for (int a = PP - 1; a >= 0; a--)
-					if (cd[ii * A3_NC + ll * PP + a] == j) {
-						cn++;
-						first = a;
+			return r;
+		};
+		for (int st = 0; st < maxq; st++) {
+			unsigned used = 0, todo = 0;
+			unsigned holder = 0xffffffffu;	/* nibble r: lane slot holding class r */
+			unsigned choice = 0;		/* nibble b: class of lane slot b */
+#pragma unroll
+			for (int b = 0; b < 8; b++)
+				todo |= (unsigned)(st < lquota[b]) << b;
+			const unsigned active = todo;
+			unsigned nopt = 0;		/* nibble b: classes lane slot b has left */
+#pragma unroll
+			for (int b = 0; b < 8; b++)
+				nopt |= (unsigned)__popc(classes(counts(b))) << (4 * b);
+			for (int round = 0; round < 8 && todo; round++) {
+				/* the lane with the fewest classes left */
+				int b = 0, bn = 99;
+#pragma unroll
+				for (int bb = 0; bb < 8; bb++) {
+					const int n = (int)(nopt >> (4 * bb) & 0xfu);
+					if ((todo >> bb & 1) && n < bn) {
+						bn = n;
+						b = bb;
 					}
-				const int r = ii & 7;
-				/* skip over slots that do not exist (segments beyond S, the
-				 * short last step) */
-				int s_ = cs_s[r], seg = cs_seg[r];
-				while (s_ <= q && (seg >= S || (s_ == q && seg >= rem))) {
-					s_++;
-					seg = (r - lane0 - s_) & 7;
 				}
-				const bool ok = s_ < q || (s_ == q && seg < rem);
-				if (ok) {
-					if (sweep == 0)
-						out[start + s_ * S + seg] = (unsigned short)(ii | first << 9
-							| (cn - 1) << 12);
-					cs_s[r] = s_;
-					cs_seg[r] = seg + 8;
+				todo &= ~(1u << b);
+				const unsigned long long c8 = counts(b);
+				const unsigned av = classes(c8);
+				int r;
+				if (av & ~used) {
+					r = best(c8, av & ~used);
+					used |= 1u << r;
+					holder = (holder & ~(0xfu << (4 * r))) | (unsigned)b << (4 * r);
 				} else {
-					cs_s[r] = q + 1;
-					if (sweep == 1) {
-						while (out[start + fill] != 0xffff)
-							fill++;
-						out[start + fill++] = (unsigned short)(ii | first << 9
-							| (cn - 1) << 12);
+					/* every class of this lane is taken: ask a holder to move */
+					unsigned tr = av;
+					r = -1;
+					for (int k = 0; k < 8 && tr && r < 0; k++) {
+						const int rr = best(c8, tr);
+						tr &= ~(1u << rr);
+						const unsigned h = holder >> (4 * rr) & 0xfu;
+						if (h == 0xfu)
+							continue;
+						const unsigned long long h8 = counts((int)h);
+						const unsigned alt = classes(h8) & ~used;
+						if (!alt)
+							continue;
+						const int r2 = best(h8, alt);
+						used |= 1u << r2;
+						holder = (holder & ~(0xfu << (4 * r2))) | h << (4 * r2);
+						choice = (choice & ~(0xfu << (4 * h))) | (unsigned)r2 << (4 * h);
+						holder = (holder & ~(0xfu << (4 * rr))) | (unsigned)b << (4 * rr);
+						r = rr;
 					}
+					if (r < 0)
+						r = best(c8, av);	/* a wavefront more */
 				}
+				choice = (choice & ~(0xfu << (4 * b))) | (unsigned)r << (4 * b);
+			}
+#pragma unroll
+			for (int b = 0; b < 8; b++) {
+				if (!(active >> b & 1))
+					continue;
+				const int ln = b * A3_NQ + qw, r = (int)(choice >> (4 * b) & 0xfu);
+				const int from = lptr[ln * 8 + r]++;
+				lcnt[ln * 8 + r]--;
+				out[lstart[b] + st * lS[b] + lseg[b]]
+					= tmp[lstart[b] + from * lS[b] + lseg[b]];
 			}
 		}
 	}
 }
-

@@ -750,8 +750,7 @@ static int make_plan3(mc_ctx *c)
 			c->d_nat, c->d3_codes, c->I, L, c->P, PP, (int)n_itiles, n_ltiles);
 		LAUNCH_CHECK("k3_build_codes");
 		mark("k3_build_codes");
-		const size_t bsm = (size_t)A3_IT * A3_NC + sizeof(int) * (2 * (size_t)ncm + 1)
-			+ sizeof(unsigned) * (size_t)ncm * (A3_IT / 32);
+		const size_t bsm = a3_build_smem_bytes(ncm, cap);
 		k3_build_csc<<<(unsigned)ntile, 128, bsm, c->stream>>>(c->d3_codes, PP, n_ltiles,
 			ncm, cap, c->d3_lt_ncol, c->d3_colinfo, c->d3_csc, c->d3_colstart);
 		LAUNCH_CHECK("k3_build_csc");
