@@ -75,6 +75,10 @@ struct Admix3Args {
 	const unsigned short *colinfo;	/* [n_ltiles][ncolmax] locus_in_tile << 8 | allele */
 	const int *lc_first;		/* [n_lchunks + 1] first locus tile of each chunk */
 	const int *off;			/* [L + 1] prefix sums of J */
+	const int *nat_of;		/* [T] row inside the kernel -> allele slot, or null: the rows
+					 * of a locus with more than 16 slots are reordered (mc_cuda.cu);
+					 * `p` then is the parameter slot in kernel row order
+					 * (k3_permute_rows) and `p_nat` the slot itself */
 	/* data */
 	const unsigned char *codes;	/* [n_itiles][n_ltiles][A3_THREADS][A3_NC] */
 	const unsigned short *csc;	/* [n_itiles][n_ltiles][cap] sorted entries */
@@ -84,7 +88,7 @@ struct Admix3Args {
 					 * then the column of every pass-2 lane as bytes (255: idle) */
 	int cap;			/* entries per tile: A3_IT * A3_NC */
 	/* parameters */
-	const double *p, *eta;
+	const double *p, *eta, *p_nat;
 	long long eta_stride;
 	/* outputs */
 	double *Apart;			/* [n_lchunks][Ipad][K] */
@@ -637,9 +641,10 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 			double *Np = a.Npart + (size_t)r * a.K * a.T;
 			for (int x = t; x < chunk_rows * a.K; x += A3_THREADS) {
 				const int k = x / chunk_rows, row = x - k * chunk_rows;
-				const size_t gx = (size_t)k * a.T + row0 + row;
+				const size_t gx = (size_t)k * a.T
+					+ (a.nat_of ? __ldg(a.nat_of + row0 + row) : row0 + row);
 				const double gv = __ldcg(G_u + (size_t)row * KR + k);
-				Np[gx] = MODE == A3_ADMIX_EM ? gv * __ldg(a.p + gx) : gv;
+				Np[gx] = MODE == A3_ADMIX_EM ? gv * __ldg(a.p_nat + gx) : gv;
 			}
 		}
 		/* ---- log likelihood of the unit ---- */

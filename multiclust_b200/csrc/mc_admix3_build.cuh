@@ -27,9 +27,11 @@ __global__ void k_allele_hist(const unsigned char *nat, long long I, int L, int 
 }
 
 /* natural [I][L][P] codes -> A3_NC bytes per (tile, individual): LT = A3_NC / PP
- * loci x PP copies, thread-major inside a tile */
+ * loci x PP copies, thread-major inside a tile; an allele is stored as its row inside
+ * the kernel's p tile (perm_of: allele slot -> row of the locus, mc_cuda.cu) */
 __global__ void k3_build_codes(const unsigned char *nat, unsigned char *codes,
-	long long I, int L, int P, int PP, int n_itiles, int n_ltiles)
+	long long I, int L, int P, int PP, int n_itiles, int n_ltiles,
+	const int *off, const unsigned char *perm_of)
 {
 	const int LT = A3_NC / PP;
 	const long long n = (long long)n_itiles * n_ltiles * A3_THREADS;
@@ -43,11 +45,27 @@ __global__ void k3_build_codes(const unsigned char *nat, unsigned char *codes,
 			unsigned char b[8];
 			for (int q = 0; q < 8; q++) {
 				const int l = lt * LT + (h * 8 + q) / PP, a = q % PP;
-				b[q] = (i < I && l < L && a < P) ? nat[((size_t)i * L + l) * P + a] : 255;
+				unsigned char v = (i < I && l < L && a < P)
+					? nat[((size_t)i * L + l) * P + a] : 255;
+				if (v != 255)
+					v = perm_of[off[l] + v];
+				b[q] = v;
 			}
 			*reinterpret_cast<uint2 *>(codes + (size_t)x * A3_NC + h * 8)
 				= *reinterpret_cast<uint2 *>(b);
 		}
+	}
+}
+
+/* the parameter slot (or log p table) in the kernel's row order: pp[k][g] = p[k][nat_of[g]] */
+__global__ void k3_permute_rows(const double *p, double *pp, const int *nat_of, int K,
+	long long T)
+{
+	const long long n = (long long)K * T;
+	for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+		x += (long long)gridDim.x * blockDim.x) {
+		const long long k = x / T, g = x - k * T;
+		pp[x] = p[k * T + nat_of[g]];
 	}
 }
 

@@ -94,6 +94,10 @@ struct mc_ctx {
 	double *d3_Gacc = nullptr;
 	unsigned short *d3_colinfo = nullptr, *d3_csc = nullptr, *d3_colstart = nullptr;
 	unsigned char *d3_codes = nullptr;
+	unsigned char *d3_perm_of = nullptr;	/* [T] allele slot -> row of its locus in the kernel */
+	int *d3_nat_of = nullptr;		/* [T] kernel row -> allele slot (both from the start of p) */
+	bool l3_permuted = false;		/* some locus has its rows reordered */
+	double *d3_pperm = nullptr;		/* [K][T] the parameter slot in kernel row order */
 	/* dense DMMA plan for biallelic data (mc_dense.cuh); used when `use_dn` */
 	bool use_dn = false;
 	bool layout_dn = false;		/* packed counts are built */
@@ -284,7 +288,7 @@ static void free_plan(mc_ctx *c)
 	dfree(c->d_group_rowbase); dfree(c->d_group_rows); dfree(c->d_tile_rows);
 	dfree(c->d_tiled); dfree(c->d_Apart); dfree(c->d_Npart);
 	dfree(c->d_llpart); dfree(c->d_xbuf); dfree(c->d_red);
-	dfree(c->d3_lc_first); dfree(c->d3_Gacc);
+	dfree(c->d3_lc_first); dfree(c->d3_Gacc); dfree(c->d3_pperm);
 	dfree(c->d_dn_pd); dfree(c->d_dn_lc_first);
 	dfree(c->d_dg_tabE); dfree(c->d_dg_tabM); dfree(c->d_dg_flag); dfree(c->d_dg_vscale);
 	c->use3 = false;
@@ -299,8 +303,9 @@ static void free_layout3(mc_ctx *c)
 {
 	dfree(c->d3_lt_ncol); dfree(c->d3_colinfo);
 	dfree(c->d3_csc); dfree(c->d3_colstart);
-	dfree(c->d3_codes);
+	dfree(c->d3_codes); dfree(c->d3_perm_of); dfree(c->d3_nat_of);
 	c->layout3 = false;
+	c->l3_permuted = false;
 	dfree(c->d_dn_cnt);
 	c->layout_dn = false;
 }
@@ -707,6 +712,44 @@ static int make_plan3(mc_ctx *c)
 		cudaFree(d_hist);
 		mark("allele histogram");
 
+		/* Rows of a locus inside the kernel.  Pass 1 reads p_s[k][row] with 8-byte
+		 * loads, so rows r and r + 16 of a locus share a bank pair and two lanes of a
+		 * half warp that carry them cost a wavefront more.  A locus with 17..32
+		 * allele slots gets its rows in an order that pairs the rarest alleles with
+		 * each other: with m = J - 16, the 16 - m most frequent alleles take rows
+		 * m..15 (no partner), the next m rows 0..m-1, and the m rarest rows 16..16+m-1,
+		 * the very rarest (the phantom slot of a locus with missing data: no carriers)
+		 * opposite row 0, which is also what a missing copy reads. */
+		std::vector<unsigned char> perm_of((size_t)c->T);
+		std::vector<int> nat_of((size_t)c->T);
+		bool permuted = false;
+		{
+			std::vector<int> rk;
+			for (int l = 0; l < L; l++) {
+				const int J = c->J[l], o = c->off[l];
+				rk.resize((size_t)J);
+				for (int j = 0; j < J; j++)
+					rk[(size_t)j] = j;
+				if (J > 16 && J <= 32) {
+					permuted = true;
+					std::stable_sort(rk.begin(), rk.end(), [&](int x, int y) {
+						return hist[(size_t)o + x] > hist[(size_t)o + y]; });
+					const int m = J - 16;
+					std::vector<int> at((size_t)J);	/* row -> allele */
+					for (int r = m; r < 16; r++)
+						at[(size_t)r] = rk[(size_t)(r - m)];
+					for (int k = 0; k < m; k++) {
+						at[(size_t)k] = rk[(size_t)(16 - m + k)];
+						at[(size_t)(16 + k)] = rk[(size_t)(J - 1 - k)];
+					}
+					rk = at;
+				}
+				for (int r = 0; r < J; r++) {
+					perm_of[(size_t)o + rk[(size_t)r]] = (unsigned char)r;
+					nat_of[(size_t)o + r] = o + rk[(size_t)r];
+				}
+			}
+		}
 		std::vector<int> lt_ncol((size_t)n_ltiles);
 		std::vector<std::vector<std::pair<unsigned, unsigned short>>> cols((size_t)n_ltiles);
 		int ncm = 1, mtr = 1;
@@ -718,7 +761,8 @@ static int make_plan3(mc_ctx *c)
 				for (int j = 0; j < c->J[l]; j++)
 					if (hist[(size_t)c->off[l] + j])
 						v.push_back({ hist[(size_t)c->off[l] + j],
-							(unsigned short)((l - lf) << 8 | j) });
+							(unsigned short)((l - lf) << 8
+								| perm_of[(size_t)c->off[l] + j]) });
 			std::stable_sort(v.begin(), v.end(),
 				[](const std::pair<unsigned, unsigned short> &x,
 				   const std::pair<unsigned, unsigned short> &y) { return x.first > y.first; });
@@ -739,6 +783,8 @@ static int make_plan3(mc_ctx *c)
 		int rc;
 		if ((rc = upload(c, c->d3_lt_ncol, lt_ncol))) return rc;
 		if ((rc = upload(c, c->d3_colinfo, colinfo))) return rc;
+		if ((rc = upload(c, c->d3_perm_of, perm_of))) return rc;
+		if ((rc = upload(c, c->d3_nat_of, nat_of))) return rc;
 		const size_t ntile = (size_t)n_itiles * n_ltiles;
 		mark("column order + uploads");
 		CK(MC_DEV_MALLOC(&c->d3_codes, ntile * A3_THREADS * A3_NC));
@@ -747,7 +793,8 @@ static int make_plan3(mc_ctx *c)
 			+ A3_THREADS / 2) * sizeof(unsigned short)));
 		mark("cudaMalloc codes/lists");
 		k3_build_codes<<<grid_for(c, (long long)ntile * A3_THREADS, 256), 256, 0, c->stream>>>(
-			c->d_nat, c->d3_codes, c->I, L, c->P, PP, (int)n_itiles, n_ltiles);
+			c->d_nat, c->d3_codes, c->I, L, c->P, PP, (int)n_itiles, n_ltiles,
+			c->d_off, c->d3_perm_of);
 		LAUNCH_CHECK("k3_build_codes");
 		mark("k3_build_codes");
 		const size_t bsm = a3_build_smem_bytes(ncm, cap);
@@ -755,6 +802,7 @@ static int make_plan3(mc_ctx *c)
 			ncm, cap, c->d3_lt_ncol, c->d3_colinfo, c->d3_csc, c->d3_colstart);
 		LAUNCH_CHECK("k3_build_csc");
 		mark("k3_build_csc");
+		c->l3_permuted = permuted;
 		c->l3_ncolmax = ncm;
 		c->l3_max_tile_rows = mtr;
 		c->layout3 = true;
@@ -798,9 +846,12 @@ static int make_plan3(mc_ctx *c)
 	if ((rc = upload(c, c->d3_lc_first, lc_first))) return rc;
 	a.lt_ncol = c->d3_lt_ncol; a.colinfo = c->d3_colinfo;
 	 a.lc_first = c->d3_lc_first; a.off = c->d_off;
+	a.nat_of = c->l3_permuted ? c->d3_nat_of : nullptr;
 	a.codes = c->d3_codes; a.csc = c->d3_csc; a.colstart = c->d3_colstart;
 	if ((rc = alloc_outputs(c, n_lchunks, n_ichunks, a.n_units, a.Ipad))) return rc;
 	CK(MC_DEV_MALLOC(&c->d3_Gacc, sizeof(double) * (size_t)n_ichunks * c->T * KR));
+	if (c->l3_permuted)
+		CK(MC_DEV_MALLOC(&c->d3_pperm, sizeof(double) * (size_t)c->K * c->T));
 	a.Apart = c->d_Apart; a.Npart = c->d_Npart; a.llpart = c->d_llpart;
 	a.Gacc = c->d3_Gacc;
 	CK(cudaStreamSynchronize(c->stream));
@@ -817,7 +868,13 @@ static int launch_admix3(mc_ctx *c, int mode, const double *p, const double *eta
 	if (!fn)
 		return fail(c, MC_ERR_UNSUPPORTED, "no admix3 kernel for K=%d P=%d", c->K, c->P);
 	Admix3Args a = c->a3;
-	a.p = p; a.eta = eta; a.eta_stride = eta_stride;
+	a.p = a.p_nat = p; a.eta = eta; a.eta_stride = eta_stride;
+	if (a.nat_of && p) {	/* the rows of some loci are reordered inside the kernel */
+		k3_permute_rows<<<grid_for(c, (long long)c->K * c->T, 256), 256, 0, c->stream>>>(
+			p, c->d3_pperm, a.nat_of, c->K, c->T);
+		LAUNCH_CHECK("k3_permute_rows");
+		a.p = c->d3_pperm;
+	}
 	if (fallback) {	/* behind the digit kernels: runs only when they declined */
 		a.run_if = c->d_dg_flag;
 		a.n_chunks_dev = c->d_dg_flag + 1;
