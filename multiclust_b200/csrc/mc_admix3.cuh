@@ -82,7 +82,7 @@ struct Admix3Args {
 	/* data */
 	const unsigned char *codes;	/* [n_itiles][n_ltiles][A3_THREADS][A3_NC] */
 	const unsigned short *csc;	/* [n_itiles][n_ltiles][cap] sorted entries */
-	const unsigned short *colstart;	/* [n_itiles][n_ltiles][3 csw + A3_THREADS / 2], csw =
+	const unsigned short *colstart;	/* [n_itiles][n_ltiles][3 csw + A3_THREADS], csw =
 					 * ncolmax + 1 rounded up to a multiple of 8: first entry,
 					 * first lane, locus_in_tile << 8 | allele of every column,
 					 * then the column of every pass-2 lane as bytes (255: idle) */
@@ -137,10 +137,10 @@ __device__ __forceinline__ double a3_lds_f64(unsigned addr)
 	asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
 	return v;
 }
-__device__ __forceinline__ unsigned a3_lds_u16(unsigned addr)
+__device__ __forceinline__ unsigned a3_lds_u32(unsigned addr)
 {
-	unsigned short v;
-	asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+	unsigned v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
 	return v;
 }
 
@@ -194,7 +194,7 @@ static inline size_t a3_smem_bytes(int KP, int mode, int ncolmax, int cap)
 	if (mode == A3_ADMIX_EM)
 		d += (size_t)A3_NC * A3_WP;
 	return d * sizeof(double)
-		+ ((p2 ? (size_t)cap : 0) + 2 * (3 * csw + A3_THREADS / 2)) * sizeof(unsigned short)
+		+ ((p2 ? (size_t)cap : 0) + 2 * (3 * csw + A3_THREADS)) * sizeof(unsigned short)
 		+ 2 * 16 * sizeof(int);
 }
 
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 	const int t = threadIdx.x, lane = t & 31;
 	const int tl = a3_thread_lane(t);	/* logical pass-2 lane of this thread */
 	const int csw = ((a.ncolmax + 1 + 7) / 8) * 8;	/* colstart row, 16-byte multiple */
-	const int cstn = 3 * csw + A3_THREADS / 2;	/* shorts of one tile's column tables */
+	const int cstn = 3 * csw + A3_THREADS;	/* shorts of one tile's column tables */
 
 	/* eta rows first: the xor rotation needs them aligned to their size */
 	double *eta_s = smem3d;						/* [A3_IT][2 NP] */
@@ -527,47 +527,67 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 				 * are consecutive LOGICAL lanes; thread t is logical lane tl, so the
 				 * 8 lanes of a quarter warp belong to 8 different columns (the list
 				 * builder schedules their entries into different bank groups) */
-				const int col = (cst_s[3 * csw + (tl >> 1)] >> ((tl & 1) * 8)) & 0xff;
+				const unsigned lane_info = cst_s[3 * csw + tl];	/* column | entries << 8 */
+				const int col = (int)(lane_info & 0xffu);
 				if (col != 255) {
-					const int lane0c = cst_s[csw + col], lane1c = cst_s[csw + col + 1];
-					const int S2 = (lane1c - lane0c) * 2;	/* list stride, bytes */
+					const int nq = (int)(lane_info >> 8);	/* entries of this lane (>= 1) */
 					const unsigned wb = w_sa + (unsigned)(cst_s[2 * csw + col] >> 8)
 						* (PP * A3_WP * 8);
-					const unsigned xe = csc_sa + 2u * cst_s[col + 1];
-					unsigned x = csc_sa + 2u * (cst_s[col] + (tl - lane0c));
-					/* ids run two trips ahead and weights one, and nothing is
-					 * computed from a load in the trip that issues it: the warp
-					 * issues in order, so an operation on a fresh load would hold
-					 * the accumulation of the current entry back */
+					/* entries 2j and 2j + 1 of thread t are the 32-bit word
+					 * j * A3_THREADS + t of the tile's list: a warp reads 128
+					 * consecutive bytes every other entry */
+					unsigned x = csc_sa + 4u * (unsigned)t;
 					auto w_addr = [&](unsigned en) {
 						return wb + ((en >> 9) & 7) * (A3_WP * 8) + (en & (A3_IT - 1)) * 8;
 					};
-					unsigned e0 = x < xe ? a3_lds_u16(x) : 0u;
-					unsigned e1 = x + S2 < xe ? a3_lds_u16(x + S2) : 0u;
-					double w0 = (HAS_W && x < xe) ? a3_lds_f64(w_addr(e0)) : 0.0;
-					while (x < xe) {
-						const unsigned rm = eta_sa + (e0 & (A3_IT - 1)) * (NP * 16);
-						/* mixture: the weight is the number of copies of the allele,
-						 * made a double as 2^52 + n - 2^52 (an I2F.F64 here came out
-						 * of ptxas 12.9 with its source inside the destination pair
-						 * for even KP and faulted as an illegal instruction on B200) */
-						const double wc = HAS_W ? w0
-							: __hiloint2double(0x43300000, (int)((e0 >> 12) + 1)) - 4503599627370496.0;
-						const unsigned e2 = x + 2 * S2 < xe ? a3_lds_u16(x + 2 * S2) : 0u;
-						double2 v[KP];
+					/* mixture: the weight is the number of copies of the allele,
+					 * made a double as 2^52 + n - 2^52 (an I2F.F64 here came out
+					 * of ptxas 12.9 with its source inside the destination pair
+					 * for even KP and faulted as an illegal instruction on B200) */
+					auto copies = [](unsigned en) {
+						return __hiloint2double(0x43300000, (int)((en >> 12) + 1))
+							- 4503599627370496.0;
+					};
+					auto load_row = [&](unsigned en, double2 (&v)[KP]) {
+						const unsigned rm = eta_sa + (en & (A3_IT - 1)) * (NP * 16);
 #pragma unroll
 						for (int s = 0; s < KP; s++)
 							v[s] = a3_lds_f64x2(rm + (s << 4));
-						x += S2;
-						if (HAS_W)
-							w0 = x < xe ? a3_lds_f64(w_addr(e1)) : 0.0;
+					};
+					auto add_row = [&](const double2 (&v)[KP], double wc) {
 #pragma unroll
 						for (int s = 0; s < KP; s++) {
 							g[2 * s] = fma(v[s].x, wc, g[2 * s]);
 							g[2 * s + 1] = fma(v[s].y, wc, g[2 * s + 1]);
 						}
-						e0 = e1;
-						e1 = e2;
+					};
+					/* ids run a pair ahead and weights one entry, and nothing is
+					 * computed from a load in the trip that issues it: the warp
+					 * issues in order, so an operation on a fresh load would hold
+					 * the accumulation of the current entry back */
+					unsigned pr = a3_lds_u32(x);
+					unsigned prn = nq > 2 ? a3_lds_u32(x + 4 * A3_THREADS) : 0u;
+					unsigned e0 = pr & 0xffffu;
+					double w0 = HAS_W ? a3_lds_f64(w_addr(e0)) : 0.0;
+					for (int j = 0; j < nq; j += 2) {
+						const unsigned e1 = pr >> 16;
+						double2 v[KP];
+						double wc = HAS_W ? w0 : copies(e0);
+						load_row(e0, v);
+						if (HAS_W)
+							w0 = j + 1 < nq ? a3_lds_f64(w_addr(e1)) : 0.0;
+						add_row(v, wc);
+						if (j + 1 >= nq)
+							break;
+						pr = prn;
+						x += 4 * A3_THREADS;
+						prn = j + 4 < nq ? a3_lds_u32(x + 4 * A3_THREADS) : 0u;
+						e0 = pr & 0xffffu;
+						wc = HAS_W ? w0 : copies(e1);
+						load_row(e1, v);
+						if (HAS_W)
+							w0 = j + 2 < nq ? a3_lds_f64(w_addr(e0)) : 0.0;
+						add_row(v, wc);
 					}
 				}
 				/* the lane's partial sums */

@@ -70,11 +70,11 @@ __global__ void k3_permute_rows(const double *p, double *pp, const int *nat_of, 
 }
 
 /* shared memory of k3_build_csc */
-static inline size_t a3_build_smem_bytes(int ncolmax, int cap)
+static inline size_t a3_build_smem_bytes(int ncolmax)
 {
 	return (size_t)A3_IT * A3_NC + sizeof(int) * (2 * (size_t)ncolmax + 2)
 		+ sizeof(unsigned) * (size_t)ncolmax * (A3_IT / 32)
-		+ sizeof(unsigned short) * (size_t)cap
+		+ sizeof(unsigned short) * (size_t)A3_IT * A3_NC
 		+ (size_t)A3_THREADS * (8 + 8 + 1 + 1);
 }
 
@@ -103,7 +103,7 @@ static inline size_t a3_build_smem_bytes(int ncolmax, int cap)
  * 1.08, but that couples the columns and runs on one thread). */
 __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 	int ncolmax, int cap, const int *lt_ncol, const unsigned short *colinfo,
-	unsigned short *csc, unsigned short *colstart)
+	unsigned short *csc, unsigned short *colstart, int *qmax_out)
 {
 	extern __shared__ __align__(16) unsigned char sm3[];
 	unsigned char *cd = sm3;				/* [A3_IT][A3_NC] */
@@ -112,8 +112,8 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 	/* carriers of every column as a bit mask over the tile's individuals */
 	constexpr int MW = A3_IT / 32;
 	unsigned *mask = reinterpret_cast<unsigned *>(lane_first + ncolmax + 2);	/* [ncolmax][MW] */
-	unsigned short *tmp = reinterpret_cast<unsigned short *>(mask + (size_t)ncolmax * MW);	/* [cap] dealt lists */
-	unsigned char *lcnt = reinterpret_cast<unsigned char *>(tmp + cap);	/* [lanes][8] entries left per class */
+	unsigned short *tmp = reinterpret_cast<unsigned short *>(mask + (size_t)ncolmax * MW);	/* [A3_IT * A3_NC] dealt lists, column after column */
+	unsigned char *lcnt = reinterpret_cast<unsigned char *>(tmp + A3_IT * A3_NC);	/* [lanes][8] entries left per class */
 	unsigned char *lptr = lcnt + A3_THREADS * 8;		/* [lanes][8] next list step of the class */
 	unsigned char *lcol = lptr + A3_THREADS * 8;		/* [lanes] column */
 	unsigned char *lfill = lcol + A3_THREADS;		/* [lanes] entries of the lane */
@@ -122,7 +122,7 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 	const unsigned short *ci = colinfo + (size_t)lt * ncolmax;
 	unsigned short *out = csc + (size_t)blockIdx.x * cap;
 	const int csw = ((ncolmax + 1 + 7) / 8) * 8;
-	unsigned short *cs = colstart + (size_t)blockIdx.x * (3 * csw + A3_THREADS / 2);
+	unsigned short *cs = colstart + (size_t)blockIdx.x * (3 * csw + A3_THREADS);
 	const uint2 *src = reinterpret_cast<const uint2 *>(codes)
 		+ (size_t)blockIdx.x * A3_THREADS * (A3_NC / 8);
 
@@ -158,13 +158,8 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		int acc = 0;
-		for (int c = 0; c < ncol; c++) {
-			const int n = cnt[c];
-			cs[c] = (unsigned short)acc;
-			acc += n;
-		}
-		for (int c = ncol; c < csw; c++)
-			cs[c] = (unsigned short)acc;
+		for (int c = 0; c < ncol; c++)
+			acc += cnt[c];
 		/* lanes of THIS tile: the smallest list length q with
 		 * sum_c ceil(n_c / q) <= A3_THREADS, column c gets ceil(n_c / q) lanes */
 		int q = (acc + A3_THREADS - 1) / A3_THREADS;
@@ -177,26 +172,37 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 			if (lanes <= A3_THREADS)
 				break;
 		}
-		int l0 = 0;
-		for (int c = 0; c < ncol; c++) {
-			lane_first[c] = l0;
-			cs[csw + c] = (unsigned short)l0;
-			l0 += (cnt[c] + q - 1) / q;
+		if (qmax_out) {		/* first launch: the longest list of any tile */
+			atomicMax(qmax_out, q);
+		} else {
+			acc = 0;
+			for (int c = 0; c < ncol; c++) {
+				cs[c] = (unsigned short)acc;	/* first entry in the dealt order */
+				acc += cnt[c];
+			}
+			for (int c = ncol; c < csw; c++)
+				cs[c] = (unsigned short)acc;
+			int l0 = 0;
+			for (int c = 0; c < ncol; c++) {
+				lane_first[c] = l0;
+				cs[csw + c] = (unsigned short)l0;
+				l0 += (cnt[c] + q - 1) / q;
+			}
+			lane_first[ncol] = l0;
+			for (int c = ncol; c < csw; c++)
+				cs[csw + c] = (unsigned short)l0;
+			for (int c = 0; c < csw; c++)	/* column -> locus_in_tile << 8 | allele */
+				cs[2 * csw + c] = c < ncol ? ci[c] : 0;
 		}
-		lane_first[ncol] = l0;
-		for (int c = ncol; c < csw; c++)
-			cs[csw + c] = (unsigned short)l0;
-		for (int c = 0; c < csw; c++)	/* column -> locus_in_tile << 8 | allele */
-			cs[2 * csw + c] = c < ncol ? ci[c] : 0;
 	}
+	if (qmax_out)
+		return;
 	__syncthreads();
 	/* the column of every logical pass-2 lane */
 	for (int c = threadIdx.x; c < ncol; c += blockDim.x)
 		for (int ln = lane_first[c]; ln < lane_first[c + 1]; ln++)
 			lcol[ln] = (unsigned char)c;
 	__syncthreads();
-	for (int x = threadIdx.x; x < A3_THREADS / 2; x += blockDim.x)
-		cs[3 * csw + x] = (unsigned short)(lcol[2 * x] | (unsigned)lcol[2 * x + 1] << 8);
 
 	/* ---- deal: one thread per column ---- */
 	for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
@@ -227,8 +233,10 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 		}
 	}
 	__syncthreads();
-	/* a lane's dealt list is sorted by class: where each class starts */
+	/* a lane's dealt list is sorted by class: where each class starts; and the lane
+	 * table of the kernel: column | entries << 8 (255: idle) */
 	for (int ln = threadIdx.x; ln < A3_THREADS; ln += blockDim.x) {
+		cs[3 * csw + ln] = (unsigned short)(lcol[ln] | (unsigned)lfill[ln] << 8);
 		int acc = 0;
 		for (int r = 0; r < 8; r++) {
 			lptr[ln * 8 + r] = (unsigned char)acc;
@@ -342,7 +350,8 @@ __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 				const int ln = b * A3_NQ + qw, r = (int)(choice >> (4 * b) & 0xfu);
 				const int from = lptr[ln * 8 + r]++;
 				lcnt[ln * 8 + r]--;
-				out[lstart[b] + st * lS[b] + lseg[b]]
+				/* entry st of the lane: half (st & 1) of word (st / 2) * A3_THREADS + thread */
+				out[((st >> 1) * A3_THREADS + a3_lane_thread(ln)) * 2 + (st & 1)]
 					= tmp[lstart[b] + from * lS[b] + lseg[b]];
 			}
 		}

@@ -97,6 +97,7 @@ struct mc_ctx {
 	unsigned char *d3_perm_of = nullptr;	/* [T] allele slot -> row of its locus in the kernel */
 	int *d3_nat_of = nullptr;		/* [T] kernel row -> allele slot (both from the start of p) */
 	bool l3_permuted = false;		/* some locus has its rows reordered */
+	int l3_cap = 0;				/* 16-bit entries per tile of the pass-2 lists */
 	double *d3_pperm = nullptr;		/* [K][T] the parameter slot in kernel row order */
 	/* dense DMMA plan for biallelic data (mc_dense.cuh); used when `use_dn` */
 	bool use_dn = false;
@@ -681,7 +682,7 @@ static int make_plan3(mc_ctx *c)
 	const int LT = A3_NC / PP;
 	const int n_ltiles = (L + LT - 1) / LT;
 	const long long n_itiles = (c->I + A3_IT - 1) / A3_IT;
-	const int cap = A3_IT * A3_NC;
+	int cap = c->l3_cap;	/* entries of a tile's list (set when the layout is built) */
 	const bool timing = c->opt_timing != 0;
 	auto t_prev = std::chrono::steady_clock::now();
 	auto mark = [&](const char *what) {
@@ -788,20 +789,34 @@ static int make_plan3(mc_ctx *c)
 		const size_t ntile = (size_t)n_itiles * n_ltiles;
 		mark("column order + uploads");
 		CK(MC_DEV_MALLOC(&c->d3_codes, ntile * A3_THREADS * A3_NC));
-		CK(MC_DEV_MALLOC(&c->d3_csc, ntile * cap * sizeof(unsigned short)));
 		CK(MC_DEV_MALLOC(&c->d3_colstart, ntile * (3 * (size_t)((ncm + 1 + 7) / 8 * 8)
-			+ A3_THREADS / 2) * sizeof(unsigned short)));
-		mark("cudaMalloc codes/lists");
+			+ A3_THREADS) * sizeof(unsigned short)));
+		mark("cudaMalloc codes/tables");
 		k3_build_codes<<<grid_for(c, (long long)ntile * A3_THREADS, 256), 256, 0, c->stream>>>(
 			c->d_nat, c->d3_codes, c->I, L, c->P, PP, (int)n_itiles, n_ltiles,
 			c->d_off, c->d3_perm_of);
 		LAUNCH_CHECK("k3_build_codes");
 		mark("k3_build_codes");
-		const size_t bsm = a3_build_smem_bytes(ncm, cap);
+		/* the lists are stored step-major, [pair of steps][thread][2]: their length is
+		 * the longest lane list of any tile (an even number of steps) x A3_THREADS, known
+		 * after a first, counting-only launch of the builder */
+		const size_t bsm = a3_build_smem_bytes(ncm);
+		int qmax = 0;
+		CK(cudaMemsetAsync(c->d_small, 0, sizeof(int), c->stream));
 		k3_build_csc<<<(unsigned)ntile, 128, bsm, c->stream>>>(c->d3_codes, PP, n_ltiles,
-			ncm, cap, c->d3_lt_ncol, c->d3_colinfo, c->d3_csc, c->d3_colstart);
+			ncm, 0, c->d3_lt_ncol, c->d3_colinfo, nullptr, c->d3_colstart,
+			reinterpret_cast<int *>(c->d_small));
+		LAUNCH_CHECK("k3_build_csc (count)");
+		CK(cudaMemcpyAsync(&qmax, c->d_small, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		cap = (std::max(qmax, 1) + 1) / 2 * 2 * A3_THREADS;
+		mark("k3_build_csc (count)");
+		CK(MC_DEV_MALLOC(&c->d3_csc, ntile * (size_t)cap * sizeof(unsigned short)));
+		k3_build_csc<<<(unsigned)ntile, 128, bsm, c->stream>>>(c->d3_codes, PP, n_ltiles,
+			ncm, cap, c->d3_lt_ncol, c->d3_colinfo, c->d3_csc, c->d3_colstart, nullptr);
 		LAUNCH_CHECK("k3_build_csc");
 		mark("k3_build_csc");
+		c->l3_cap = cap;
 		c->l3_permuted = permuted;
 		c->l3_ncolmax = ncm;
 		c->l3_max_tile_rows = mtr;
