@@ -595,6 +595,25 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 				for (int pc = 0; pc < KP; pc++)
 					*reinterpret_cast<double2 *>(part_s + (size_t)a3_part_row(tl) * KR + 2 * pc)
 						= make_double2(g[2 * pc], g[2 * pc + 1]);
+				/* ---- fold: thread <-> (column, piece), lanes in order; the
+				 * column's running sum lives in L2.  The sums of the thread's first
+				 * two (column, piece) items are requested before the barrier, so the
+				 * L2 round trip overlaps the wait for the other warps' pass 2 ---- */
+				auto fold_dst = [&](int f) -> double * {
+					if (f >= a.ncolmax * KP)
+						return nullptr;
+					const int cc = f / KP, pc = f - cc * KP;
+					if ((int)cst_s[csw + cc + 1] - (int)cst_s[csw + cc] <= 0)
+						return nullptr;
+					const unsigned info = cst_s[2 * csw + cc];
+					return G_u + (size_t)(tro + rb[info >> 8] + (int)(info & 0xff)) * KR + 2 * pc;
+				};
+				double *dst0 = fold_dst(t), *dst1 = fold_dst(t + A3_THREADS);
+				double2 old0 = make_double2(0.0, 0.0), old1 = old0;
+				if (dst0)
+					old0 = a3_ldcg2(dst0, pol_keep);
+				if (dst1)
+					old1 = a3_ldcg2(dst1, pol_keep);
 				a3_cp_async_wait<0>();	/* the next tile's p rows */
 				__syncthreads();
 				if (more) {
@@ -605,17 +624,9 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					a3_cp_async_commit();
 				}
 
-				/* ---- fold: thread <-> (column, piece), lanes in order; the
-				 * column's running sum lives in L2 ---- */
-				for (int f = t; f < a.ncolmax * KP; f += A3_THREADS) {
+				auto fold_item = [&](int f, double *dst, double2 old) {
 					const int cc = f / KP, pc = f - cc * KP;
 					const int lane0 = cst_s[csw + cc], S = cst_s[csw + cc + 1] - lane0;
-					if (S <= 0)
-						continue;
-					const unsigned info = cst_s[2 * csw + cc];
-					double *dst = G_u + (size_t)(tro + rb[info >> 8] + (int)(info & 0xff)) * KR
-						+ 2 * pc;
-					const double2 old = a3_ldcg2(dst, pol_keep);
 					const double2 *src = reinterpret_cast<const double2 *>(part_s + 2 * pc);
 					auto part = [&](int sx) {
 						return src[(size_t)a3_part_row(lane0 + sx) * KP];
@@ -642,6 +653,15 @@ __global__ void __launch_bounds__(A3_THREADS, A3_CTAS_PER_SM) admix3_kernel(cons
 					v.x += (acc.x + a1.x) + (a2.x + a3.x);
 					v.y += (acc.y + a1.y) + (a2.y + a3.y);
 					a3_stcg2(dst, v, pol_keep);
+				};
+				if (dst0)
+					fold_item(t, dst0, old0);
+				if (dst1)
+					fold_item(t + A3_THREADS, dst1, old1);
+				for (int f = t + 2 * A3_THREADS; f < a.ncolmax * KP; f += A3_THREADS) {
+					double *dst = fold_dst(f);
+					if (dst)
+						fold_item(f, dst, a3_ldcg2(dst, pol_keep));
 				}
 			}
 			if (HAS_A) {
