@@ -20,20 +20,24 @@
  *           8-byte word each from <= J_l consecutive words: 2 wavefronts per
  *           LDS.64, the minimum.  w goes to shared memory, w_s[copy][i].
  *   pass 2  thread <-> (allele column, segment); a column gets a number of
- *           lanes proportional to its allele count.  The eta rows live in
- *           shared memory with a pitch of an odd number of 16-byte pieces, so
- *           the rows of individuals with different i % 8 start in different
- *           bank groups, and the entry lists are built (k3_build_csc, once per
- *           data set) so that lane t mostly reads individuals with
- *           i % 8 == t % 8: the 8 lanes of a quarter warp then touch 8
- *           different bank groups, 4 wavefronts per LDS.128, the minimum.
+ *           logical lanes proportional to its allele count, spread over the
+ *           quarter warps (a3_thread_lane).  The eta rows live in shared
+ *           memory with a pitch of an odd number of 16-byte pieces, so the rows
+ *           of individuals with different i % 8 start in different bank groups
+ *           and a quarter warp's LDS.128 costs as many wavefronts as the most
+ *           frequent residue among its 8 entries.  Which entry a lane reads in
+ *           which step is scheduled by the list builder (k3_build_csc, once per
+ *           data set) so that the 8 lanes of a quarter warp mostly touch 8
+ *           different bank groups.  The lists are stored step-major, two
+ *           entries per 32-bit word and thread.
  *           (A first version padded the rows to 8 pieces and rotated the
  *           piece order per lane -- conflict-free for any assignment but 8
  *           loads for 5 useful pieces at K = 10.)
  *   fold    the lanes' partial sums go through a shared scratch; thread
  *           (column, piece) adds the column's partials in lane order and
- *           updates the CTA's accumulator B_s: no atomics, fixed order.
- * Two barriers per (A3_IT individuals x 8 copies) tile; two CTAs per SM so
+ *           read-modify-writes the column's running sum in L2 (Gacc): no
+ *           atomics, fixed order.
+ * Two barriers per (A3_IT individuals x A3_NC copies) tile; two CTAs per SM so
  * that one's pass 1 (FP64) overlaps the other's pass 2 (shared-memory pipe).
  */
 #pragma once
@@ -81,12 +85,16 @@ struct Admix3Args {
 					 * (k3_permute_rows) and `p_nat` the slot itself */
 	/* data */
 	const unsigned char *codes;	/* [n_itiles][n_ltiles][A3_THREADS][A3_NC] */
-	const unsigned short *csc;	/* [n_itiles][n_ltiles][cap] sorted entries */
+	const unsigned short *csc;	/* [n_itiles][n_ltiles][cap / (2 A3_THREADS)][A3_THREADS][2]:
+					 * entries 2j and 2j + 1 of thread t, i | first copy << 9 |
+					 * (count - 1) << 12 */
 	const unsigned short *colstart;	/* [n_itiles][n_ltiles][3 csw + A3_THREADS], csw =
-					 * ncolmax + 1 rounded up to a multiple of 8: first entry,
-					 * first lane, locus_in_tile << 8 | allele of every column,
-					 * then the column of every pass-2 lane as bytes (255: idle) */
-	int cap;			/* entries per tile: A3_IT * A3_NC */
+					 * ncolmax + 1 rounded up to a multiple of 8: first entry
+					 * (builder only), first logical lane, locus_in_tile << 8 | row
+					 * of every column, then column | entries << 8 of every
+					 * logical pass-2 lane (column 255: idle) */
+	int cap;			/* 16-bit entries per tile: the longest lane list of any tile,
+					 * rounded up to an even number, x A3_THREADS */
 	/* parameters */
 	const double *p, *eta, *p_nat;
 	long long eta_stride;
