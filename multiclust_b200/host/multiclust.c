@@ -478,8 +478,9 @@ int parse_options(options *opt, data *dat, int argc, const char **argv)
 						opt->repeat_seconds = 60 * tmp;
 					else
 						opt->max_repeat_seconds = 60 * tmp;
-				} else {
-					goto bad_arg;
+				} else {	/* reference multiclust.c:1706-1708 */
+					usage_error(argv, i);
+					return INVALID_CMD_OPTION;
 				}
 			}
 			i--;

@@ -149,3 +149,19 @@ def test_missing_file_and_bad_option(tmp_path):
     assert r.returncode == 9                                          # INVALID_CMD_OPTION
     r = subprocess.run([CLI, "-k", "3"], capture_output=True, text=True)
     assert r.returncode == 8                                          # INVALID_CMDLINE
+
+
+def test_timed_repetition_option_checks(tmp_path):
+    """-w n <r> [t <min>] [m <min>] (reference multiclust.c:1683-1714): the number of
+    repetitions must be positive, an unknown sub-option is an invalid option, and the
+    bootstrap cannot be timed"""
+    stru = write(tmp_path / "e.stru", EDGE["r_format"][0])
+    r = subprocess.run([CLI, "-f", stru, "-R", "-k", "2", "-w", "n", "0"], capture_output=True, text=True)
+    assert r.returncode == 10                                      # INVALID_CMD_ARGUMENT
+    r = subprocess.run([CLI, "-f", stru, "-R", "-k", "2", "-w", "x", "3"], capture_output=True, text=True)
+    assert r.returncode == 9                                       # INVALID_CMD_OPTION
+    r = subprocess.run([CLI, "-f", stru, "-R", "-k", "2", "-w", "n", "2", "t"], capture_output=True, text=True)
+    assert r.returncode == 10
+    r = subprocess.run([CLI, "-f", stru, "-R", "-k", "2", "-w", "n", "2", "-b", "2"],
+                       capture_output=True, text=True)
+    assert r.returncode == 11 and "cannot be timed" in r.stderr   # INVALID_USER_SETUP
