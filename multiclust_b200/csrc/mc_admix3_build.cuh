@@ -82,8 +82,11 @@ static inline size_t a3_build_smem_bytes(int ncolmax)
  * order, one entry per (individual, allele) carrying it:
  *     i | first copy << 9 | (count - 1) << 12.
  * The column owns S consecutive logical pass-2 lanes, S chosen per tile from the
- * tile's own counts so that no lane gets more than q = ceil(entries / A3_THREADS) (+1)
- * entries; lane seg reads the entries at start + s * S + seg, s = 0, 1, ...
+ * tile's own counts so that no lane gets more than q entries (q the smallest list
+ * length for which the columns need at most A3_THREADS lanes).  The list of the tile is
+ * stored step-major: entry st of logical lane ln is half (st & 1) of the 32-bit word
+ * (st / 2) * A3_THREADS + a3_lane_thread(ln).  With `qmax_out` the launch only counts:
+ * it reports the largest q of any tile, which sizes the lists.
  *
  * The eta rows of 8 individuals with different i % 8 lie in different bank groups, so a
  * quarter warp's LDS.128 costs as many wavefronts as the most frequent residue among
@@ -97,10 +100,11 @@ static inline size_t a3_build_smem_bytes(int ncolmax)
  *             taken; a lane that finds none asks a holder of one of its classes to
  *             move to another free class (one augmenting step); if that fails too it
  *             takes its best-stocked class and the step costs a wavefront more.
- * Simulated on config-3 tiles: 1.15 wavefronts per quarter-warp step against 1.50 for
- * dealing entries to fixed (lane + step) % 8 slots (a full augmenting-path matching
- * gives the same 1.15; balancing the class totals of the quarter warps while dealing
- * 1.08, but that couples the columns and runs on one thread). */
+ * Restated in tools/list_schedule_sim.py on tiles of the bench's generator: 1.21
+ * wavefronts per quarter-warp step against 1.52 for dealing entries to fixed
+ * (lane + step) % 8 slots (a full augmenting-path matching gives the same; balancing the
+ * class totals of the quarter warps while dealing is better still, but couples the
+ * columns and runs on one thread per tile). */
 __global__ void k3_build_csc(const unsigned char *codes, int PP, int n_ltiles,
 	int ncolmax, int cap, const int *lt_ncol, const unsigned short *colinfo,
 	unsigned short *csc, unsigned short *colstart, int *qmax_out)
