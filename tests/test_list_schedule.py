@@ -53,6 +53,14 @@ def test_schedule_places_every_entry_once_and_saves_wavefronts():
     per_lane = {}
     for ln, classes in enumerate(sub):
         per_lane[ln] = sorted(ii for v in classes.values() for ii in v)
+    # an optimal schedule of the same lists (edge colouring): conflict-free in `best` steps
+    opt = sim.schedule_optimal(sub)
+    w_opt, s_opt = sim.wavefronts(opt)
+    assert w_opt == s_opt == best
+    got = {}
+    for (qw, slot, st), ii in opt.items():
+        got.setdefault(slot * sim.NQ + qw, []).append(ii)
+    assert all(sorted(got.get(ln, [])) == want for ln, want in per_lane.items())
     out = sim.schedule(sub)
     got = {}
     for (qw, slot, st), ii in out.items():
