@@ -46,7 +46,9 @@ the reference's stop() needs it (em_alg.c:195-207).
              absolute) are compared with the reference's.  A failure exits
              non-zero.
   other_configs  the other BASELINE configurations, ms per step: C1 (the
-             reference's own CPU-runnable case), C2 (mixture, biallelic, SQUAREM),
+             reference's own CPU-runnable case) and C2 (mixture, biallelic, SQUAREM),
+             each with the reference's own em_step on one host core beside it
+             (`reference_cpu`: C1 whole, C2 on 500 of its 10k individuals),
              one GPU's share of C5 -- and with --gpus 8 the WHOLE C5 (I=1M
              tetraploid, K=8, QN q=2) sharded over the 8 ranks -- and C4
              (K = 2..12 x 64 initialisations x 100 iterations = 704 whole fits)
@@ -233,6 +235,30 @@ def run_reference_sample(a, path, steps):
     for _ in range(steps):
         fit.e_step(); fit.m_step()
     return (time.perf_counter() - t0) / steps, "port"
+
+
+def reference_step_ms(I, I_sample, L, K, P, jmax, miss, admixture, steps=3):
+    """ms per em_step of the unmodified reference (one host core) on the first I_sample of I
+    individuals of a configuration, extrapolated linearly in I -- for `other_configs`"""
+    from oracle import orc
+    if not orc.have_ref():
+        raise RuntimeError("oracle/_ref is not built")
+    a = argparse.Namespace(L=L, K=K, jmax=jmax, miss_bp=miss, ploidy=P)
+    path = make_sample_mcb(a, I_sample)
+    try:
+        r = orc.run_ref(["-f", "sample", "-k", str(K), "-p", str(P), "-n", "1", "-E", "1e-30"]
+                        + (["-a"] if admixture else []), mcb=path, time_steps=steps, timeout=600)
+    finally:
+        try:
+            os.remove(path)
+        except OSError:
+            pass
+    if r.returncode != 0 or not r.stdout.strip():
+        raise RuntimeError("reference harness failed: " + r.stderr[-300:])
+    sec = json.loads(r.stdout.strip().splitlines()[-1])["sec_per_step"]
+    return {"ms_per_em_step": sec * 1e3 * (I / float(I_sample)), "cores": 1, "kind": "reference",
+            "sample": "%d of %d individuals, %d timed em_step calls%s" % (
+                I_sample, I, steps, "" if I_sample == I else ", extrapolated linearly in I")}
 
 
 def cpu_baseline(a, steps):
@@ -480,7 +506,7 @@ def other_configs(env, a):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
 
-    def single(name, I, L, K, P, jmax, miss, admixture, accel, steps):
+    def single(name, I, L, K, P, jmax, miss, admixture, accel, steps, ref_sample=0):
         ctx = env.context()
         sp = SynthParams(seed=SEED, K=min(K, 8), jmax=jmax, miss_bp=miss, ploidy=P)
         ctx.set_data_synth(I, L, sp)
@@ -503,13 +529,20 @@ def other_configs(env, a):
                                                      drv.accelerated_em_step)
             out["accel"] = accel
         ctx.close()
+        if ref_sample and not a.no_cpu:
+            # the reference's own em_step beside it (reported, never required)
+            try:
+                out["reference_cpu"] = reference_step_ms(I, min(I, ref_sample), L, K, P, jmax,
+                                                         miss, admixture)
+            except Exception as exc:
+                out["reference_cpu"] = {"error": repr(exc)[:200]}
         res[name] = out
 
     if env.rank == 0:
         single("C1 admixture I=200 L=100 K=3 <=5 alleles (-C 500 fit: x500)",
-               200, 100, 3, 2, 5, 300, 1, 0, 50)
+               200, 100, 3, 2, 5, 300, 1, 0, 50, ref_sample=200)
         single("C2 mixture I=10k L=5k K=5 biallelic diploid, SQUAREM -s 1",
-               10000, 5000, 5, 2, 2, 0, 0, 1, 20)
+               10000, 5000, 5, 2, 2, 0, 0, 1, 20, ref_sample=500)
         if env.world != 8:      # with 8 ranks the whole configuration runs below
             single("C5 share: admixture I=125k (1M / 8) L=50k K=8 biallelic tetraploid, QN -s 5",
                    125000, 50000, 8, 4, 2, 0, 1, 5, 5)
